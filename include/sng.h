@@ -1,0 +1,181 @@
+/* sng.h -- C ABI of the B200-native batched smart-nanogrid environment step.
+ *
+ * This is the drop-in boundary for the reference's hot path.  The reference has no native
+ * interface (it is pure Python); each entry point below names the Python method(s) of
+ * Dellintel98/smart-nanogrid-gym it replaces for E environments at once
+ * (paths relative to the reference tree, smart_nanogrid_gym/...):
+ *
+ *   sng_create          SmartNanogridEnv.__init__             envs/smart_nanogrid_environment.py:32-120
+ *                       (+ CentralManagementSystem.__init__   utils/central_management_system.py:11-43)
+ *   sng_reset           SmartNanogridEnv.reset                envs/smart_nanogrid_environment.py:311-351
+ *                       (+ ChargingStation.generate_new_initial_values  utils/charging_station.py:152-279)
+ *   sng_load_schedule   ChargingStation.load_initial_values   utils/charging_station.py:119-136
+ *   sng_step            SmartNanogridEnv.step                 envs/smart_nanogrid_environment.py:140-188
+ *                       (+ CentralManagementSystem.manage_nanogrid  utils/central_management_system.py:84-185)
+ *   sng_step_host       the same call made with host (numpy) arrays, as a gym caller does
+ *   sng_rollout         n consecutive step() calls of a trainer's rollout loop   solvers/RL/ppo_train.py:94-101
+ *   sng_sample_plan     the `initial_values.json` dump        utils/charging_station.py:173-186
+ *   sng_error_flags     the reference's `raise ValueError` sites
+ *                       (central_management_system.py:158-159, penaliser.py:111)
+ *
+ * Conventions: plain pointers and sizes only.  All device buffers are owned by the caller
+ * (torch) and merely borrowed between sng_bind and sng_destroy.  Every call is asynchronous
+ * on the given CUDA stream (a cudaStream_t passed as void*) unless stated otherwise; there are
+ * no hidden allocations or synchronisations in sng_step / sng_rollout.  Return value 0 = OK,
+ * negative = error; sng_last_error() gives the message (thread local).  No C++ exception
+ * crosses the boundary.  A handle may be used by one host thread at a time.
+ */
+#ifndef SNG_H
+#define SNG_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SNG_ABI_VERSION 1
+#define SNG_MAX_VEHICLES 8   /* schedule slots per spot and day */
+#define SNG_MAX_SPOTS 255
+#define SNG_MAX_TABLE 512    /* entries of the shared PV / price tables (two days) */
+
+typedef struct sng_env sng_env;
+
+enum { SNG_OK = 0, SNG_ERR_ARG = -1, SNG_ERR_CUDA = -2, SNG_ERR_STATE = -3, SNG_ERR_UNSUPPORTED = -4 };
+enum { SNG_PEN_NONE = 0, SNG_PEN_ON_DEPARTURE = 1, SNG_PEN_SPARSE = 2, SNG_PEN_DENSE = 3 };
+enum { SNG_F32 = 32, SNG_F64 = 64 };
+
+/* sticky per-env error bits (the reference raises instead; kernels never trap) */
+enum {
+    SNG_FLAG_NEG_DEMAND = 1u,  /* total EV power < 0 without V2X: central_management_system.py:158-159 */
+    SNG_FLAG_BATT_SOC_GT1 = 2u, /* penaliser.py:111 */
+    SNG_FLAG_NAN_ACTION = 4u
+};
+
+/* Mirrors the reference constructor arguments and its hard-coded physical constants. */
+typedef struct {
+    uint32_t struct_size;   /* = sizeof(sng_config) */
+    int32_t precision;      /* SNG_F32 (production) or SNG_F64 (validation build, bit-faithful arithmetic) */
+    int64_t n_envs;         /* environments owned by this handle (this GPU's slice) */
+    int64_t env_gid0;       /* global id of local env 0: RNG streams are keyed by global id */
+    int32_t n_spots;        /* number_of_chargers */
+    int32_t n_steps;        /* 24 / time_interval */
+    int32_t horizon;        /* NUMBER_OF_HOURS_AHEAD = 3 */
+    int32_t table_len;      /* entries of each table below (>= n_steps + horizon) */
+    int32_t pv;             /* pv_system_available_in_model */
+    int32_t batt;           /* battery_system_available_in_model */
+    int32_t v2x;            /* vehicle_to_everything */
+    int32_t penalty_mode;   /* SNG_PEN_* (vehicle_uncharged_penalty_mode) */
+    int32_t diff_cap;       /* enable_different_vehicle_battery_capacities */
+    int32_t req_soc;        /* enable_requested_state_of_charge */
+    int32_t default_cap;    /* 40 kWh */
+    int32_t auto_reset;     /* 1: a finished env is reset inside the same step (VecEnv semantics) */
+    double dt;              /* hours per step */
+    double ev_pmax, ev_eff; /* 22 kW, 0.95 */
+    double b_cap, b_pmax, b_eff, b_dod, b_soc0; /* 80 kWh, 44 kW, 0.95, 0.15, 0.5 */
+    double sell_coeff, cost_weight, batt_pen_w, margin, dep_norm; /* 0.8, 0.75, 0.8, 0.05, 24 */
+    const double *pv_power;   /* host pointers, table_len entries, copied by sng_create */
+    const double *irr_norm;
+    const double *price;
+    const double *price_norm;
+} sng_config;
+
+/* Byte sizes of the opaque per-env state arrays for a given config (caller allocates). */
+typedef struct {
+    uint32_t struct_size;
+    int32_t act_dim, obs_dim;
+    int32_t real_bytes;     /* 4 or 8: element size of actions / reward / soc */
+    int32_t rec_bytes;      /* one current-vehicle record (12 or 24) */
+    int32_t envst_bytes;    /* one per-env scalar block (16 or 32) */
+    int32_t plan_slots;     /* SNG_MAX_VEHICLES */
+    int32_t diag_count;     /* reals per env in the optional diagnostics row */
+    int32_t env_align;      /* n_envs granularity for which the fast (bulk-copy) path applies */
+} sng_layout;
+
+/* Device buffers.  `real` = float (SNG_F32) or double (SNG_F64).  Optional pointers may be NULL. */
+typedef struct {
+    uint32_t struct_size;
+    uint32_t _pad;
+    const void *actions;    /* in   [E][act_dim] real, row-major, dense */
+    float *obs;             /* out  [E][obs_dim] float32 (the reference casts obs to float32) */
+    void *reward;           /* out  [E] real */
+    uint8_t *done;          /* out  [E] terminated flag (truncated is always 0 in the reference) */
+    float *terminal_obs;    /* out, optional [E][obs_dim]: last obs of the finished episode (auto_reset) */
+    void *soc;              /* state [E][n_spots] real: SoC of the vehicle at each spot after the last step */
+    void *rec;              /* state [E][n_spots] x rec_bytes: current / last vehicle record per spot */
+    void *envst;            /* state [E] x envst_bytes: battery SoC, pv_shift, episode return, (episode, t) */
+    void *plan;             /* optional [E][n_spots][SNG_MAX_VEHICLES] x rec_bytes: full-day schedule */
+    uint32_t *err;          /* optional [E] sticky SNG_FLAG_* bits */
+    void *diag;             /* optional [E][diag_count] real per-step diagnostics */
+    void *last_return;      /* optional [E] real: return of the most recently finished episode */
+} sng_buffers;
+
+enum { /* diagnostics row, subset of central_management_system.py:128-155 */
+    SNG_D_TOTAL_CH = 0, SNG_D_TOTAL_DIS, SNG_D_SOLAR, SNG_D_BATT_POWER, SNG_D_GRID_POWER,
+    SNG_D_GRID_COST, SNG_D_PEN_VEH, SNG_D_PEN_BATT, SNG_D_COUNT
+};
+
+/* Host view of a schedule to replay (compact per-vehicle records). */
+typedef struct {
+    uint32_t struct_size;
+    int32_t n_slots;          /* V <= SNG_MAX_VEHICLES */
+    const int32_t *arr;       /* [E][N][V] arrival step */
+    const int32_t *dep;       /* [E][N][V] departure step */
+    const int32_t *cap;       /* [E][N][V] capacity, integer kWh */
+    const double *soc0;       /* [E][N][V] arrival SoC */
+    const double *req;        /* [E][N][V] requested SoC */
+    const int32_t *n_veh;     /* [E][N] */
+    const double *pv_shift;   /* optional [E] */
+    const double *soc_b;      /* optional [E] battery SoC to start from */
+} sng_schedule_view;
+
+int sng_abi_version(void);
+/* sizeof() of the ABI structs as compiled: 0 config, 1 layout, 2 buffers, 3 schedule_view (binding self-check). */
+int sng_sizeof(int which);
+const char *sng_last_error(void);
+
+int sng_query_layout(const sng_config *cfg, sng_layout *out);
+int sng_create(const sng_config *cfg, int device, sng_env **out);
+void sng_destroy(sng_env *env);
+int sng_bind(sng_env *env, const sng_buffers *buffers);
+
+/* Start new episodes (sampling mode).  mask: optional DEVICE pointer [E] (1 = reset this env).
+ * reset_battery != 0 also sets the battery SoC to b_soc0 (the reference never does after
+ * construction, quirk Q8).  Writes the reset observation of the selected envs to `obs`. */
+int sng_reset(sng_env *env, uint64_t seed, const uint8_t *mask, int reset_battery, void *stream);
+
+/* Replay mode: upload a schedule (host arrays), rewind to t = 0 and write the reset obs.
+ * Synchronous w.r.t. the host arrays. */
+int sng_load_schedule(sng_env *env, const sng_schedule_view *view, void *stream);
+
+/* One env.step() for all envs: reads `actions`, updates state, writes obs/reward/done. */
+int sng_step(sng_env *env, void *stream);
+
+/* n_steps consecutive steps in one launch.  actions [n_steps][E][act_dim], obs [n_steps][E][obs_dim],
+ * reward [n_steps][E], done [n_steps][E] (device).  actions == NULL: uniform random actions from
+ * the action box are drawn in-kernel (throughput probe). */
+int sng_rollout(sng_env *env, const void *actions, float *obs, void *reward, uint8_t *done, int n_steps,
+                void *stream);
+
+/* The gym-facing call with HOST buffers (pinned recommended): H2D actions, step, D2H results,
+ * then waits for completion.  Sizes as in sng_buffers. */
+int sng_step_host(sng_env *env, const void *actions_host, float *obs_host, void *reward_host,
+                  uint8_t *done_host, void *stream);
+
+/* Eagerly generate the whole-day schedule of the CURRENT episode of every env into `plan`
+ * (same Philox streams the lazy in-step sampler uses), for export / inspection. */
+int sng_sample_plan(sng_env *env, void *stream);
+
+/* OR of all per-env error flags (synchronises the stream). */
+int sng_error_flags(sng_env *env, uint32_t *host_out, void *stream);
+
+/* Kernels launched by this handle so far (bench.py's gpu_launches claim). */
+int64_t sng_launch_count(const sng_env *env);
+
+/* Tuning knob for experiments: lanes per env (0 = auto) and envs per tile (0 = auto). */
+int sng_set_tuning(sng_env *env, int lanes_per_env, int envs_per_tile, int use_bulk_copy);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SNG_H */

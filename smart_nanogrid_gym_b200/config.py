@@ -165,7 +165,8 @@ class NanogridConfig:
 
     @property
     def penalty_mode_id(self) -> int:
-        return PENALTY_MODES[self.vehicle_uncharged_penalty_mode]
+        # invalid modes are only rejected at reset(), like the reference (validate_modes)
+        return PENALTY_MODES.get(self.vehicle_uncharged_penalty_mode, 0)
 
     def action_bounds(self):
         """Box bounds of ...environment.py:101-118."""

@@ -1,0 +1,154 @@
+// sng_api.cu -- the C ABI declared in include/sng.h, plus the float32 production engine.
+#include "sng_engine.cuh"
+
+namespace sng {
+EngineBase *make_engine_f32(const sng_config &cfg, int device, std::string &err)
+{
+    auto *e = new Engine<float, false>();
+    if (e->init(cfg, device) != SNG_OK) {
+        err = e->error;
+        delete e;
+        return nullptr;
+    }
+    return e;
+}
+}  // namespace sng
+
+struct sng_env {
+    sng::EngineBase *eng;
+};
+
+static thread_local std::string g_last_error;
+
+static int fail(int code, const std::string &msg)
+{
+    g_last_error = msg;
+    return code;
+}
+
+static int done(sng_env *env, int rc)
+{
+    if (rc != SNG_OK) g_last_error = env->eng->error;
+    return rc;
+}
+
+extern "C" {
+
+int sng_abi_version(void) { return SNG_ABI_VERSION; }
+
+int sng_sizeof(int which)
+{
+    switch (which) {
+    case 0: return (int)sizeof(sng_config);
+    case 1: return (int)sizeof(sng_layout);
+    case 2: return (int)sizeof(sng_buffers);
+    case 3: return (int)sizeof(sng_schedule_view);
+    default: return -1;
+    }
+}
+
+const char *sng_last_error(void) { return g_last_error.c_str(); }
+
+int sng_query_layout(const sng_config *cfg, sng_layout *out)
+{
+    if (!cfg || !out || cfg->struct_size != sizeof(sng_config)) return fail(SNG_ERR_ARG, "sng_query_layout: bad struct_size");
+    if (cfg->precision != SNG_F32 && cfg->precision != SNG_F64) return fail(SNG_ERR_ARG, "precision must be 32 or 64");
+    const bool f64 = cfg->precision == SNG_F64;
+    const int pv = cfg->pv != 0, b = cfg->batt != 0;
+    out->struct_size = sizeof(sng_layout);
+    out->act_dim = cfg->n_spots + b;
+    out->obs_dim = (1 + pv) * (1 + cfg->horizon) + 2 * cfg->n_spots + b;
+    out->real_bytes = f64 ? 8 : 4;
+    out->rec_bytes = f64 ? (int)sizeof(sng::Rec<double>) : (int)sizeof(sng::Rec<float>);
+    out->envst_bytes = f64 ? (int)sizeof(sng::EnvSt<double>) : (int)sizeof(sng::EnvSt<float>);
+    out->plan_slots = SNG_MAX_VEHICLES;
+    out->diag_count = SNG_D_COUNT;
+    out->env_align = 128;
+    return SNG_OK;
+}
+
+int sng_create(const sng_config *cfg, int device, sng_env **out)
+{
+    if (!cfg || !out || cfg->struct_size != sizeof(sng_config)) return fail(SNG_ERR_ARG, "sng_create: bad struct_size");
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev < 1)
+        return fail(SNG_ERR_CUDA, "sng_create: no CUDA device (this library has no CPU fallback)");
+    if (device < 0 || device >= n_dev) return fail(SNG_ERR_ARG, "sng_create: bad device index");
+    std::string err;
+    sng::EngineBase *eng = nullptr;
+    if (cfg->precision == SNG_F32) eng = sng::make_engine_f32(*cfg, device, err);
+    else if (cfg->precision == SNG_F64) eng = sng::make_engine_f64(*cfg, device, err);
+    else return fail(SNG_ERR_ARG, "sng_create: precision must be 32 or 64");
+    if (!eng) return fail(SNG_ERR_ARG, err.empty() ? "sng_create failed" : err);
+    *out = new sng_env{eng};
+    return SNG_OK;
+}
+
+void sng_destroy(sng_env *env)
+{
+    if (!env) return;
+    delete env->eng;
+    delete env;
+}
+
+#define SNG_ENV_CHECK(env) \
+    if (!(env) || !(env)->eng) return fail(SNG_ERR_ARG, "null environment handle")
+
+int sng_bind(sng_env *env, const sng_buffers *buffers)
+{
+    SNG_ENV_CHECK(env);
+    return done(env, env->eng->bind(buffers));
+}
+
+int sng_reset(sng_env *env, uint64_t seed, const uint8_t *mask, int reset_battery, void *stream)
+{
+    SNG_ENV_CHECK(env);
+    return done(env, env->eng->reset(seed, mask, reset_battery, (cudaStream_t)stream));
+}
+
+int sng_load_schedule(sng_env *env, const sng_schedule_view *view, void *stream)
+{
+    SNG_ENV_CHECK(env);
+    return done(env, env->eng->load_schedule(view, (cudaStream_t)stream));
+}
+
+int sng_step(sng_env *env, void *stream)
+{
+    SNG_ENV_CHECK(env);
+    return done(env, env->eng->step((cudaStream_t)stream));
+}
+
+int sng_rollout(sng_env *env, const void *actions, float *obs, void *reward, uint8_t *done_, int n_steps, void *stream)
+{
+    SNG_ENV_CHECK(env);
+    return done(env, env->eng->rollout(actions, obs, reward, done_, n_steps, (cudaStream_t)stream));
+}
+
+int sng_step_host(sng_env *env, const void *actions_host, float *obs_host, void *reward_host, uint8_t *done_host,
+                  void *stream)
+{
+    SNG_ENV_CHECK(env);
+    return done(env, env->eng->step_host(actions_host, obs_host, reward_host, done_host, (cudaStream_t)stream));
+}
+
+int sng_sample_plan(sng_env *env, void *stream)
+{
+    SNG_ENV_CHECK(env);
+    return done(env, env->eng->sample_plan((cudaStream_t)stream));
+}
+
+int sng_error_flags(sng_env *env, uint32_t *host_out, void *stream)
+{
+    SNG_ENV_CHECK(env);
+    return done(env, env->eng->error_flags(host_out, (cudaStream_t)stream));
+}
+
+int64_t sng_launch_count(const sng_env *env) { return (env && env->eng) ? env->eng->launches : 0; }
+
+int sng_set_tuning(sng_env *env, int lanes_per_env, int envs_per_tile, int use_bulk_copy)
+{
+    SNG_ENV_CHECK(env);
+    return done(env, env->eng->set_tuning(lanes_per_env, envs_per_tile, use_bulk_copy));
+}
+
+}  // extern "C"

@@ -1,0 +1,61 @@
+"""Shared helpers of the parity tests (CUDA path vs the float64 oracle)."""
+import numpy as np
+
+from oracle.oracle import OracleBatch
+from smart_nanogrid_gym_b200.schedule import ScheduleRecords
+
+DEFAULT = dict(charging_mode="bounded", vehicle_uncharged_penalty_mode="sparse", time_interval="1h")
+
+
+def records_from_oracle(ob: OracleBatch) -> ScheduleRecords:
+    """Compact records of the oracle's current (pristine) dense schedule."""
+    E, N, V = ob.arr.shape
+    k = np.arange(V)[None, None, :]
+    valid = k < ob.n_veh[:, :, None]
+    arr = np.where(valid, ob.arr, 0).astype(np.int32)
+    dep = np.where(valid, ob.dep, 0).astype(np.int32)
+    a64 = arr.astype(np.int64)
+    cap = np.where(valid, np.take_along_axis(ob.cap, a64, axis=2), 0).astype(np.int32)
+    soc0 = np.where(valid, np.take_along_axis(ob.soc, a64, axis=2), 0.0)
+    req = np.where(valid, np.take_along_axis(ob.req, a64, axis=2), 0.0)
+    return ScheduleRecords(arr, dep, cap, soc0, req, ob.n_veh.copy())
+
+
+def branchy_actions(rng, lo, hi, shape):
+    """U(low, high) with exact zeros and saturated bounds sprinkled in."""
+    a = rng.uniform(lo, hi, size=shape + lo.shape)
+    z = rng.random(a.shape)
+    a[z < 0.15] = 0.0
+    hi_b = np.broadcast_to(hi, a.shape)
+    lo_b = np.broadcast_to(lo, a.shape)
+    m = (z >= 0.15) & (z < 0.20)
+    a[m] = hi_b[m]
+    m = (z >= 0.20) & (z < 0.25)
+    a[m] = lo_b[m]
+    return a
+
+
+def penalty_margin_distance(ob: OracleBatch):
+    """For the step the oracle is ABOUT to take: per env, the smallest |s - (r - 0.05 r)| over the vehicles
+    in the penalty-check set (inf when the set is empty).  The undercharge penalty jumps by 0.25 r^2 there
+    (penaliser.py:72-79), so float32 and float64 may legitimately land on different sides."""
+    E, N, W = ob.soc.shape
+    col = np.where(ob.t == 0, W - 1, ob.t - 1).astype(np.int64)[:, None, None]
+    s = np.take_along_axis(ob.soc, col, axis=2)[:, :, 0]
+    r = np.take_along_axis(ob.req, col, axis=2)[:, :, 0]
+    d = np.abs(s - (r - ob.cfg.soc_margin_ratio * r))
+    d = np.where(ob.check.astype(bool), d, np.inf)
+    return d.min(axis=1)
+
+
+def assert_close_f32(name, got, want, rtol=1e-5, atol=0.0, mask=None):
+    """|got - want| <= atol + rtol * |want| (the north-star tolerance: 1e-5 relative in float32)."""
+    got = np.asarray(got, np.float64)
+    want = np.asarray(want, np.float64)
+    bad = np.abs(got - want) > (atol + rtol * np.abs(want))
+    if mask is not None:
+        bad &= mask
+    if bad.any():
+        idx = np.argwhere(bad)[0]
+        raise AssertionError("%s: %d mismatches, first at %s: got %r want %r" %
+                             (name, bad.sum(), tuple(idx), got[tuple(idx)], want[tuple(idx)]))

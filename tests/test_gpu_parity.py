@@ -1,0 +1,380 @@
+"""Parity of the CUDA step (through the C ABI) against the float64 oracle and the golden vectors
+recorded from the live reference.  Needs a B200: run with `-m gpu`.
+
+Bars (BASELINE.json north_star): termination flags bit-exact; float32 build within 1e-5 relative
+(absolute floor 1e-5 on reward, 1e-6 on observations, because both cross zero); float64
+validation build bit-exact on SoC / observations / flags and within 4 ulp on reward (the reference
+squares penalties with libm pow(x, 2.0), which is not always the correctly rounded x*x).
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from parity_utils import DEFAULT, assert_close_f32, branchy_actions, penalty_margin_distance, records_from_oracle
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+REC_FIELDS = ("arr", "dep", "cap", "soc0", "req", "n_veh")
+
+
+def _env(n_envs, precision="float32", auto_reset=True, **kw):
+    from smart_nanogrid_gym_b200 import BatchedSmartNanogridEnv
+    full = dict(DEFAULT)
+    full.update(kw)
+    return BatchedSmartNanogridEnv(n_envs, device="cuda:0", precision=precision, want_diagnostics=True,
+                                   want_terminal_obs=True, auto_reset=auto_reset, **full)
+
+
+def _records(z, prefix):
+    from smart_nanogrid_gym_b200.schedule import ScheduleRecords
+    return ScheduleRecords(*[z[prefix + f] for f in REC_FIELDS])
+
+
+def _ulp_diff(a, b):
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    return np.abs(a - b) / np.maximum(np.spacing(np.maximum(np.abs(a), np.abs(b))), 5e-324)
+
+
+# ------------------------------------------------------------------------------------------
+# golden vectors of the live reference
+# ------------------------------------------------------------------------------------------
+def _replay_golden(z, prefix, kw, precision):
+    from smart_nanogrid_gym_b200.config import NanogridConfig
+    cfg = NanogridConfig(**kw)
+    rec = _records(z, prefix + "sched_")
+    g = lambda k: z[prefix + k]  # noqa: E731
+    E = rec.arr.shape[0]
+    env = _env(E, precision, auto_reset=False, **kw)
+    obs0 = env.load_schedule(rec, pv_shift=g("pv_shift"), soc_b=g("soc_b0") if cfg.batt else None)
+    f64 = precision == "float64"
+    if f64:
+        assert np.array_equal(obs0.cpu().numpy(), g("obs0"))
+    else:
+        assert_close_f32("obs0", obs0.cpu().numpy(), g("obs0"), atol=1e-6)
+    worst_ulp = 0.0
+    for t in range(cfg.n_steps):
+        a = torch.tensor(g("actions")[:, t], device="cuda:0", dtype=env.real)
+        obs, rew, done, trunc, info = env.step(a)
+        obs, rew, done = obs.cpu().numpy(), rew.cpu().numpy(), done.cpu().numpy()
+        diag = env.diag.cpu().numpy()
+        assert np.array_equal(done, g("done")[:, t]), t
+        assert not trunc.any().item() and info == {}
+        gd = g("diag")[:, t]
+        if f64:
+            assert np.array_equal(obs, g("obs")[:, t]), (prefix, t)
+            assert np.array_equal(diag[:, 4], gd[:, 0]), "grid power"     # bit-exact energy balance
+            assert np.array_equal(diag[:, 5], gd[:, 1]), "grid cost"
+            u = _ulp_diff(rew, g("reward")[:, t]).max()
+            worst_ulp = max(worst_ulp, u)
+            assert u <= 4, (prefix, t, u)
+            no_pen = (gd[:, 2] == 0) & (gd[:, 3] == 0)
+            assert np.array_equal(rew[no_pen], g("reward")[:, t][no_pen])  # exact whenever no pow() is involved
+        else:
+            assert_close_f32("obs", obs, g("obs")[:, t], atol=1e-6)
+            assert_close_f32("grid_power", diag[:, 4], gd[:, 0], atol=1e-4)
+            assert_close_f32("reward", rew, g("reward")[:, t], atol=1e-5)
+    assert env.error_flags() == 0
+    env.close()
+    return worst_ulp
+
+
+@pytest.mark.parametrize("precision", ["float64", "float32"])
+def test_golden_variants(precision):
+    z = np.load(os.path.join(GOLD, "ref_variants.npz"))
+    meta = json.loads(str(z["meta_json"]))
+    for idx, kw in enumerate(meta):
+        _replay_golden(z, "v%02d_" % idx, kw, precision)
+
+
+@pytest.mark.parametrize("precision", ["float64", "float32"])
+def test_golden_c1_rbc_and_c2(precision):
+    kw = dict(number_of_chargers=10, **DEFAULT)
+    _replay_golden(np.load(os.path.join(GOLD, "ref_c1_rbc_n10.npz")), "", kw, precision)
+    _replay_golden(np.load(os.path.join(GOLD, "ref_c2_n10_e256.npz")), "", kw, precision)
+
+
+def test_rbc_rule_matches_recorded_actions():
+    z = np.load(os.path.join(GOLD, "ref_c1_rbc_n10.npz"))
+    env = _env(3, "float64", number_of_chargers=10)
+    obs_seq = np.concatenate([z["obs0"][:, None], z["obs"][:, :-1]], axis=1)
+    for t in range(24):
+        a = env.rbc_actions(torch.tensor(obs_seq[:, t], device="cuda:0"))
+        assert np.array_equal(a.cpu().numpy(), z["actions"][:, t])
+    env.close()
+
+
+# ------------------------------------------------------------------------------------------
+# BASELINE config 2 at full size: in-kernel sampling + fused auto-reset vs the oracle
+# ------------------------------------------------------------------------------------------
+def _lockstep(env, ob, cfg, n_steps, rng, seed, check_soc=True, f64=False):
+    """Step the CUDA env and the oracle side by side for n_steps (across auto-resets)."""
+    lo, hi = cfg.action_bounds()
+    E = env.num_envs
+    episode = np.zeros(E, np.uint32)
+    worst = dict(obs=0.0, reward=0.0)
+    skipped = 0
+    for s in range(n_steps):
+        a = branchy_actions(rng, lo, hi, (E,))
+        a32 = a.astype(np.float32)
+        a_or = a if f64 else a32.astype(np.float64)      # the oracle sees exactly what the kernel sees
+        near = penalty_margin_distance(ob) < (0 if f64 else 1e-5)
+        skipped += int(near.sum())
+        o_ref, r_ref, d_ref = ob.step(a_or)
+        obs, rew, done, _, _ = env.step(torch.tensor(a if f64 else a32, device="cuda:0", dtype=env.real))
+        obs, rew, done = obs.cpu().numpy(), rew.cpu().numpy(), done.cpu().numpy()
+        assert np.array_equal(done, d_ref), s
+        if d_ref.any():  # auto-reset: the oracle starts the next sampled episode of those envs
+            assert d_ref.all()
+            tob = env.terminal_obs.cpu().numpy()
+            episode += 1
+            ob.sample(seed, env.env_gid0, episode)
+            o_term, o_ref = o_ref, ob.observe()
+            if f64:
+                assert np.array_equal(tob, o_term)
+            else:
+                assert_close_f32("terminal_obs", tob, o_term, atol=1e-6)
+        if f64:
+            assert np.array_equal(obs, o_ref), s
+            assert _ulp_diff(rew, r_ref).max() <= 4, s
+        else:
+            assert_close_f32("obs", obs, o_ref, atol=1e-6)
+            assert_close_f32("reward", rew, r_ref, atol=1e-5, mask=~near)
+            worst["obs"] = max(worst["obs"], float(np.abs(obs - o_ref).max()))
+            worst["reward"] = max(worst["reward"], float((np.abs(rew - r_ref) / np.maximum(np.abs(r_ref), 1.0))[~near].max()))
+    st = env.env_state()
+    assert np.array_equal(st["t"], ob.t) and np.array_equal(st["episode"], episode)
+    if f64:
+        assert np.array_equal(st["soc_b"], ob.soc_b)
+    else:
+        assert_close_f32("soc_b", st["soc_b"], ob.soc_b, atol=1e-6)
+    return worst, skipped
+
+
+@pytest.mark.parametrize("precision,n_envs", [("float32", 4096), ("float64", 1024)])
+def test_config2_sampled_episodes_with_auto_reset(precision, n_envs):
+    from oracle.oracle import OracleBatch
+    seed = 20240607
+    env = _env(n_envs, precision, number_of_chargers=10, seed=seed)
+    cfg = env.cfg
+    ob = OracleBatch(cfg, n_envs, n_threads=8)
+    obs0 = env.reset().cpu().numpy()
+    ob.sample(seed, 0, 0)
+    o_ref = ob.observe()
+    assert np.array_equal(obs0, o_ref) if precision == "float64" else np.allclose(obs0, o_ref, rtol=1e-5, atol=1e-6)
+    worst, skipped = _lockstep(env, ob, cfg, 3 * 24 + 5, np.random.default_rng(1234), seed, f64=precision == "float64")
+    assert skipped < 50
+    assert env.error_flags() == 0
+    env.close()
+
+
+@pytest.mark.parametrize("kw", [
+    dict(number_of_chargers=10, vehicle_to_everything=True, enable_requested_state_of_charge=True,
+         vehicle_uncharged_penalty_mode="dense"),
+    dict(number_of_chargers=4, pv_system_available_in_model=False, vehicle_uncharged_penalty_mode="on_departure"),
+    dict(number_of_chargers=7, battery_system_available_in_model=False, enable_different_vehicle_battery_capacities=False),
+    dict(number_of_chargers=33, price_model=3, vehicle_uncharged_penalty_mode="no_penalty"),
+    dict(number_of_chargers=64, time_interval="15min", enable_requested_state_of_charge=True),   # BASELINE config 5
+    dict(number_of_chargers=1, time_interval="2h"),
+])
+@pytest.mark.parametrize("precision", ["float32", "float64"])
+def test_variants_sampled_vs_oracle(kw, precision):
+    from oracle.oracle import OracleBatch
+    seed, E = 77, 512
+    env = _env(E, precision, seed=seed, **kw)
+    cfg = env.cfg
+    ob = OracleBatch(cfg, E, n_threads=8)
+    env.reset()
+    ob.sample(seed, 0, 0)
+    ob.observe()
+    _lockstep(env, ob, cfg, cfg.n_steps + 7, np.random.default_rng(5), seed, f64=precision == "float64")
+    flags = env.error_flags()
+    assert flags == int(np.bitwise_or.reduce(ob.err))
+    env.close()
+
+
+def test_sampler_matches_cpu_mirror_bit_exact():
+    """sng_sample_plan (GPU, Philox4x32-10) == oracle mirror, record for record; and the in-step lazy
+    sampler follows the same plan (covered by the lockstep tests)."""
+    from oracle.oracle import OracleBatch
+    for kw in (dict(number_of_chargers=10), dict(number_of_chargers=64, time_interval="15min",
+                                                 enable_requested_state_of_charge=True),
+               dict(number_of_chargers=5, enable_different_vehicle_battery_capacities=False)):
+        env = _env(2048, "float32", seed=99, env_gid0=123456789, **kw)
+        env.reset()
+        rec = env.sample_plan()
+        ob = OracleBatch(env.cfg, 2048, n_threads=8)
+        ob.sample(99, 123456789, 0)
+        ref = records_from_oracle(ob)
+        for f in REC_FIELDS:
+            assert np.array_equal(getattr(rec, f), getattr(ref, f)), f
+        assert np.array_equal(env.env_state()["pv_shift"], ob.pv_shift)
+        rec.validate(env.cfg.n_steps)
+        env.close()
+
+
+# ------------------------------------------------------------------------------------------
+# structural properties of the CUDA path
+# ------------------------------------------------------------------------------------------
+def test_lane_mappings_agree():
+    """Any lanes-per-env mapping computes the same step (sums differ only in association order)."""
+    outs = []
+    for lanes in (1, 2, 4, 8, 16, 32):
+        env = _env(1000, "float32", number_of_chargers=10, seed=3)
+        env.set_tuning(lanes_per_env=lanes)
+        env.reset()
+        g = torch.Generator(device="cuda:0").manual_seed(0)
+        acc = []
+        for _ in range(30):
+            o, r, d, _, _ = env.step(env.sample_actions(g))
+            acc.append((o.cpu().numpy().copy(), r.cpu().numpy().copy(), d.cpu().numpy().copy()))
+        outs.append(acc)
+        env.close()
+    for acc in outs[1:]:
+        for (o, r, d), (o0, r0, d0) in zip(acc, outs[0]):
+            assert np.array_equal(d, d0)
+            assert np.allclose(o, o0, rtol=1e-6, atol=1e-6) and np.allclose(r, r0, rtol=1e-5, atol=1e-5)
+
+
+def test_rollout_equals_repeated_step_and_step_host():
+    E, n = 777, 30
+    env_a = _env(E, "float32", number_of_chargers=10, seed=11)
+    env_b = _env(E, "float32", number_of_chargers=10, seed=11)
+    env_c = _env(E, "float32", number_of_chargers=10, seed=11)
+    for e in (env_a, env_b, env_c):
+        e.reset()
+    g = torch.Generator(device="cuda:0").manual_seed(1)
+    actions = torch.stack([env_a.sample_actions(g) for _ in range(n)])
+    obs_r, rew_r, done_r = env_a.rollout(actions)
+    ah = torch.zeros(E, 11).pin_memory()
+    oh, rh, dh = torch.zeros(E, 29).pin_memory(), torch.zeros(E).pin_memory(), torch.zeros(E, dtype=torch.uint8).pin_memory()
+    for s in range(n):
+        o, r, d, _, _ = env_b.step(actions[s])
+        assert torch.equal(o, obs_r[s]) and torch.equal(r, rew_r[s]) and torch.equal(d, done_r[s])
+        ah.copy_(actions[s])
+        env_c.step_host(ah, oh, rh, dh)
+        assert torch.equal(oh, o.cpu()) and torch.equal(rh, r.cpu()) and torch.equal(dh, d.cpu())
+    assert done_r[23].all() and done_r.sum().item() == E
+    for e in (env_a, env_b, env_c):
+        e.close()
+
+
+def test_zero_copy_out_buffers_and_state_dict():
+    E = 256
+    env = _env(E, "float32", number_of_chargers=10, seed=5)
+    env.reset()
+    buf_o = torch.zeros(4, E, 29, device="cuda:0")
+    buf_r = torch.zeros(4, E, device="cuda:0")
+    buf_d = torch.zeros(4, E, device="cuda:0", dtype=torch.uint8)
+    g = torch.Generator(device="cuda:0").manual_seed(2)
+    acts = [env.sample_actions(g) for _ in range(4)]
+    sd = env.state_dict()
+    for s in range(4):
+        env.step(acts[s], out=(buf_o[s], buf_r[s], buf_d[s]))
+    env.load_state_dict(sd)
+    for s in range(4):
+        o, r, d, _, _ = env.step(acts[s])
+        assert torch.equal(o, buf_o[s]) and torch.equal(r, buf_r[s]) and torch.equal(d, buf_d[s])
+    env.close()
+
+
+def test_shard_equivalence():
+    """Env e of a 2-way split equals env e of the unsplit batch (streams keyed by global env id)."""
+    E = 600
+    full = _env(E, "float32", number_of_chargers=10, seed=8)
+    lo = _env(E // 2, "float32", number_of_chargers=10, seed=8, env_gid0=0)
+    hi = _env(E // 2, "float32", number_of_chargers=10, seed=8, env_gid0=E // 2)
+    o = full.reset().clone()
+    assert torch.equal(o[:E // 2], lo.reset()) and torch.equal(o[E // 2:], hi.reset())
+    g = torch.Generator(device="cuda:0").manual_seed(4)
+    for _ in range(50):
+        a = full.sample_actions(g)
+        of, rf, df, _, _ = full.step(a)
+        ol, rl, dl, _, _ = lo.step(a[:E // 2].contiguous())
+        oh, rh, dh, _, _ = hi.step(a[E // 2:].contiguous())
+        assert torch.equal(of, torch.cat([ol, oh])) and torch.equal(rf, torch.cat([rl, rh]))
+        assert torch.equal(df, torch.cat([dl, dh]))
+    for e in (full, lo, hi):
+        e.close()
+
+
+def test_error_flags_mirror_reference_raises():
+    env = _env(64, "float32", number_of_chargers=4)
+    env.reset()
+    a = torch.zeros(64, 5, device="cuda:0")
+    env.step(a)
+    assert env.error_flags() == 0
+    for _ in range(8):          # discharge EVs without V2X -> negative demand (reference: ValueError)
+        a[:, :4] = -1.0
+        env.step(a)
+    assert env.error_flags() & 1
+    with pytest.raises(ValueError):
+        env.check_errors()
+    a[:] = float("nan")
+    env.step(a)
+    assert env.error_flags() & 4
+    env.close()
+
+
+def test_mode_validation_matches_reference_defaults():
+    """The reference constructor accepts the default '' modes and fails at reset / first use (Q10)."""
+    from smart_nanogrid_gym_b200 import BatchedSmartNanogridEnv
+    env = BatchedSmartNanogridEnv(8, number_of_chargers=4)
+    with pytest.raises(ValueError):
+        env.reset()
+    env.close()
+
+
+def test_full_size_properties_config4_slice():
+    """Size-independent properties at the per-GPU size of BASELINE config 4 (131,072 envs):
+    SoC in [0, 1], every env terminates exactly every 24 steps, battery SoC carries over resets,
+    finite rewards <= 0, observation layout."""
+    E = 131072
+    env = _env(E, "float32", number_of_chargers=10, seed=1)
+    env.reset()
+    g = torch.Generator(device="cuda:0").manual_seed(9)
+    ret = torch.zeros(E, device="cuda:0")
+    for s in range(48):
+        sb_prev = torch.tensor(env.env_state()["soc_b"], device="cuda:0") if s in (23,) else None
+        o, r, d, _, _ = env.step(env.sample_actions(g))
+        ret += r
+        assert bool(d.all().item()) == (s % 24 == 23) and (bool(d.any().item()) == bool(d.all().item()))
+        assert torch.isfinite(r).all() and (r <= 0).all()
+        soc = o[:, 8:18]
+        assert (soc >= 0).all() and (soc <= 1).all() and (o[:, 28] >= 0).all() and (o[:, 28] <= 1).all()
+        if s == 23:
+            assert torch.allclose(env.last_return, ret, rtol=1e-4, atol=1e-3)
+            ret.zero_()
+    mean_ret = env.last_return.mean().item()
+    assert -440 < mean_ret < -360, mean_ret     # live reference, random policy: -398.8 +- 93 (ref_return_stats.json)
+    assert env.error_flags() == 0
+    env.close()
+
+
+def test_single_env_gym_adapter_matches_reference_recording():
+    """The drop-in single-env API replays fixture G1 like the reference does."""
+    from smart_nanogrid_gym_b200 import SmartNanogridEnv, load_initial_values_json
+    env = SmartNanogridEnv(number_of_chargers=4, **DEFAULT)
+    assert env.observation_space.shape == (17,) and env.action_space.shape == (5,)
+    assert env.action_space.low.tolist() == [0, 0, 0, 0, -1]
+    rec = load_initial_values_json(os.path.join(GOLD, "g1_initial_values.json"))
+    with open(os.path.join(GOLD, "g1_prediction_results.json")) as fp:
+        p = json.load(fp)
+    obs, info = env.load_schedule(rec, pv_shift=0.02, soc_b=p["Initial_battery_state_of_charge"])
+    assert obs.dtype == np.float32 and obs.shape == (17,) and info == {}
+    ret = 0.0
+    for t in range(24):
+        a = np.array(p["Charger_actions"][t] + [p["Battery_action"][t]], dtype=np.float32)
+        obs, r, term, trunc, info = env.step(a)
+        assert isinstance(r, float) and isinstance(term, bool) and trunc is False and info == {}
+        assert abs(obs[16] - p["Battery_state_of_charge"][t]) < 1e-6
+        ret += r
+        assert term == (t == 23)
+    assert abs(ret - (-102.3448)) < 1e-3      # episode return per current code
+    obs, info = env.reset()
+    assert obs.shape == (17,)
+    env.close()
