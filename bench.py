@@ -1,0 +1,338 @@
+#!/usr/bin/env python
+"""bench.py -- batched env-steps/sec of the nanogrid step on B200 (BASELINE.json metric).
+
+    python bench.py --gpus 1 --steps 240 --warmup 24
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference            # the CPU restatement of the reference on the host cores
+
+Workload (BASELINE config 4 per GPU): N = 10 charging spots, PV + battery, bounded / sparse, 1 h
+steps (24 per episode), fused step + auto-reset + in-kernel Philox schedule sampling,
+`--envs` environments per GPU (default 1,048,576: the working set of one step, ~0.4 GB, is larger
+than the 126 MB L2, so no flush is needed between iterations).  One "step" = one sng_step launch
+over all envs of the rank.  Envs shard trivially: rank r owns global env ids [r*E, (r+1)*E) and
+there is no collective on the step path (scaling = weak).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ENV_KW = dict(number_of_chargers=10, charging_mode="bounded", vehicle_uncharged_penalty_mode="sparse",
+              time_interval="1h")
+METRIC = "batched env-steps/sec"
+UNIT = "env-steps/s"
+
+
+def algorithmic_bytes_per_env_step(n_spots, batt, pv):
+    """4A + 4D + 4 + 1 + 8N + 8b + 4 + 12N (float32 build)."""
+    a = n_spots + batt
+    d = 4 * (1 + pv) + 2 * n_spots + batt
+    return 4 * a + 4 * d + 4 + 1 + 8 * n_spots + 8 * batt + 4 + 12 * n_spots
+
+
+def measured_peak_gbs():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as fp:
+            return float(json.load(fp)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:  # noqa: BLE001
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic_bytes(n_envs):
+    """dram read+write bytes per launch from the committed ncu capture, if it matches this size."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as fp:
+            t = json.load(fp)
+        if int(t.get("n_envs", -1)) == int(n_envs):
+            return float(t["dram_bytes_per_launch"])
+    except Exception:  # noqa: BLE001
+        pass
+    return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+            out = ""
+        sm, smax, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_port_throughput(n_envs, seconds, threads):
+    """The float64 oracle (a C port of the reference step, oracle/) stepped on the host cores on a
+    bounded sample of the workload: `n_envs` envs, full episodes with re-sampling at every episode end."""
+    import numpy as np
+    from oracle.oracle import OracleBatch
+    from smart_nanogrid_gym_b200.config import NanogridConfig
+    cfg = NanogridConfig(**ENV_KW)
+    ob = OracleBatch(cfg, n_envs, n_threads=threads)
+    lo, hi = cfg.action_bounds()
+    rng = np.random.default_rng(0)
+    a = rng.uniform(lo, hi, size=(n_envs, cfg.act_dim))
+    obs = np.empty((n_envs, cfg.obs_dim), np.float32)
+    rew = np.empty(n_envs)
+    done = np.empty(n_envs, np.uint8)
+    ob.sample(0, 0, 0)
+    ob.observe()
+    episode, steps = 0, 0
+    for _ in range(cfg.n_steps):  # warm-up episode
+        ob.step_noalloc(a, obs, rew, done)
+    t0 = time.perf_counter()
+    while True:
+        episode += 1
+        ob.sample(0, 0, episode)
+        ob.observe()
+        for _ in range(cfg.n_steps):
+            ob.step_noalloc(a, obs, rew, done)
+        steps += cfg.n_steps
+        el = time.perf_counter() - t0
+        if el >= seconds:
+            break
+    return n_envs * steps / el, el, steps
+
+
+def run_reference_arm(args):
+    """--impl reference: the reference's own algorithm on the host CPU.  The reference is pure Python and
+    cannot be installed on the GPU box (no gym, read-only tree absent), so this times the oracle port
+    (oracle/nanogrid_oracle.c, pinned bit-exactly to the live reference) on all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as orc
+    orc.build()
+    threads = os.cpu_count() or 1
+    n_envs = args.ref_envs
+    # each "step" is one step of a bounded sample (n_envs envs) of the workload
+    import numpy as np
+    from oracle.oracle import OracleBatch
+    from smart_nanogrid_gym_b200.config import NanogridConfig
+    cfg = NanogridConfig(**ENV_KW)
+    ob = OracleBatch(cfg, n_envs, n_threads=threads)
+    lo, hi = cfg.action_bounds()
+    a = np.random.default_rng(0).uniform(lo, hi, size=(n_envs, cfg.act_dim))
+    obs = np.empty((n_envs, cfg.obs_dim), np.float32)
+    rew = np.empty(n_envs)
+    done = np.empty(n_envs, np.uint8)
+    episode = 0
+    ob.sample(0, 0, 0)
+    ob.observe()
+
+    def one_step():
+        nonlocal episode
+        ob.step_noalloc(a, obs, rew, done)
+        if done[0]:
+            episode += 1
+            ob.sample(0, 0, episode)
+            ob.observe()
+
+    for _ in range(args.warmup):
+        one_step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        one_step()
+    el = time.perf_counter() - t0
+    value = n_envs * args.steps / el
+    sample = "%d envs x %d steps (fused re-sampling at episode ends), float64 C port of the reference step" % (
+        n_envs, args.steps)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "C4 station (N=10 spots, PV+battery, 24-step episodes), CPU sample of %d envs" % n_envs},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=240)
+    ap.add_argument("--warmup", type=int, default=24)
+    ap.add_argument("--envs", type=int, default=1048576, help="environments per GPU")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--ref-envs", type=int, default=65536, help="sample size of the CPU reference arm")
+    ap.add_argument("--cpu-seconds", type=float, default=10.0, help="wall time of the cpu_baseline leg")
+    ap.add_argument("--e2e-steps", type=int, default=24)
+    ap.add_argument("--lanes", type=int, default=0, help="tuning: lanes per env (0 = auto)")
+    ap.add_argument("--tile", type=int, default=0, help="tuning: envs per tile (0 = auto)")
+    ap.add_argument("--no-bulk", action="store_true", help="tuning: disable the TMA bulk-copy path")
+    ap.add_argument("--in-stages", type=int, default=0)
+    ap.add_argument("--out-stages", type=int, default=0)
+    ap.add_argument("--ctas", type=int, default=0, help="tuning: cap on resident CTAs per SM")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from smart_nanogrid_gym_b200 import BatchedSmartNanogridEnv
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    n_gpus = world if world > 1 else 1
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+
+    E = args.envs
+    env = BatchedSmartNanogridEnv(E, device=dev, seed=0, env_gid0=rank * E, precision="float32", auto_reset=True,
+                                  **ENV_KW)
+    env.set_tuning(args.lanes, args.tile, 0 if args.no_bulk else 1)
+    env.set_pipeline(args.in_stages, args.out_stages, args.ctas)
+    cfg = env.cfg
+    env.reset()
+    # actions: a pre-filled U(low, high) tensor re-read from HBM every step
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    actions = env.sample_actions(g).contiguous()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(args.warmup):
+        env.step(actions)
+    barrier()
+
+    # ---- device-resident throughput: K launches bracketed by CUDA events on the launching stream ----
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = env.launch_count
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        env.step(actions)
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = env.launch_count - launches0
+    clocks = sampler.stop()
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    total_envs = E * n_gpus
+    value = total_envs * args.steps / (ms_max * 1e-3)
+    assert env.error_flags() == 0
+
+    # ---- end to end through the C ABI with HOST buffers (pinned): H2D actions, step, D2H obs/reward/done ----
+    a_h = actions.cpu().pin_memory()
+    o_h = torch.empty(E, cfg.obs_dim, dtype=torch.float32).pin_memory()
+    r_h = torch.empty(E, dtype=torch.float32).pin_memory()
+    d_h = torch.empty(E, dtype=torch.uint8).pin_memory()
+    for _ in range(3):
+        env.step_host(a_h, o_h, r_h, d_h)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        env.step_host(a_h, o_h, r_h, d_h)     # synchronises the stream before returning
+    torch.cuda.synchronize(dev)
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = total_envs * args.e2e_steps / float(te.item())
+    h2d = a_h.numel() * a_h.element_size()
+    d2h = o_h.numel() * 4 + r_h.numel() * 4 + d_h.numel()
+
+    # ---- optional episode-return statistics: the only collective, off the step path ----
+    stats = torch.stack([env.last_return.double().sum(), (env.last_return.double() ** 2).sum(),
+                         torch.tensor(float(E), device=dev, dtype=torch.float64)])
+    if world > 1:
+        dist.all_reduce(stats)
+    mean_ret = float(stats[0] / stats[2])
+
+    if rank == 0:
+        bytes_step = algorithmic_bytes_per_env_step(cfg.n_spots, int(cfg.batt), int(cfg.pv))
+        kernel_ms = ms / max(launches, 1)
+        achieved = bytes_step * E / (kernel_ms * 1e-3) / 1e9
+        peak, how = measured_peak_gbs()
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "C4: fused step + auto-reset + in-kernel EV schedule sampling, N=10 spots, PV+battery, "
+                                   "24-step episodes, %d envs per GPU" % E,
+                       "envs_per_gpu": E, "total_envs": total_envs, "parallelism": "env-sharded x%d, no collective" % n_gpus,
+                       "l2": "inputs larger than L2 (%.0f MB touched per step), no flush" % (bytes_step * E / 1e6),
+                       "mean_episode_return": mean_ret},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": args.e2e_steps, "path": "sng_step_host: pinned host buffers, H2D + step + D2H + sync"},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": ncu_traffic_bytes(E), "peak_source": how,
+                         "algorithmic_bytes_per_env_step": bytes_step, "kernel_ms": kernel_ms},
+        }
+        if not args.no_cpu and n_gpus == 1:
+            from oracle import oracle as orc
+            orc.build()
+            threads = os.cpu_count() or 1
+            v, el, steps = cpu_port_throughput(args.ref_envs, args.cpu_seconds, threads)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                                    "sample": "%d envs x %d steps in %.1f s, float64 C port of the reference step "
+                                              "(oracle/), all host threads" % (args.ref_envs, steps, el)}
+        print(json.dumps(line), flush=True)
+    env.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -174,6 +174,9 @@ int64_t sng_launch_count(const sng_env *env);
 
 /* Tuning knob for experiments: lanes per env (0 = auto) and envs per tile (0 = auto). */
 int sng_set_tuning(sng_env *env, int lanes_per_env, int envs_per_tile, int use_bulk_copy);
+/* Tuning knob: depth of the shared-memory input / output rings of the bulk-copy kernel and a cap
+ * on resident CTAs per SM (0 = auto for each). */
+int sng_set_pipeline(sng_env *env, int in_stages, int out_stages, int ctas_per_sm);
 
 #ifdef __cplusplus
 }

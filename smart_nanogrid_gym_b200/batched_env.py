@@ -125,6 +125,9 @@ class BatchedSmartNanogridEnv:
     def set_tuning(self, lanes_per_env=0, envs_per_tile=0, use_bulk_copy=1):
         nat.check(self._lib.sng_set_tuning(self._h, lanes_per_env, envs_per_tile, use_bulk_copy))
 
+    def set_pipeline(self, in_stages=0, out_stages=0, ctas_per_sm=0):
+        nat.check(self._lib.sng_set_pipeline(self._h, in_stages, out_stages, ctas_per_sm))
+
     @property
     def launch_count(self) -> int:
         return int(self._lib.sng_launch_count(self._h))

@@ -151,4 +151,10 @@ int sng_set_tuning(sng_env *env, int lanes_per_env, int envs_per_tile, int use_b
     return done(env, env->eng->set_tuning(lanes_per_env, envs_per_tile, use_bulk_copy));
 }
 
+int sng_set_pipeline(sng_env *env, int in_stages, int out_stages, int ctas_per_sm)
+{
+    SNG_ENV_CHECK(env);
+    return done(env, env->eng->set_pipeline(in_stages, out_stages, ctas_per_sm));
+}
+
 }  // extern "C"

@@ -60,6 +60,19 @@ template <typename real> struct Params {
     real *last_ret;
 };
 
+// Shared read-only tables (global memory in the direct kernels, a shared-memory copy in the tiled one).
+template <typename real> struct Tables {
+    const real *pv_power, *irr_norm, *price, *price_norm;  // [table_len]
+    const float *dep_norm;                                 // [kDepTab]
+};
+template <typename real> __device__ __forceinline__ Tables<real> global_tables(const Params<real> &p)
+{
+    Tables<real> tb;
+    tb.pv_power = p.pv_power; tb.irr_norm = p.irr_norm; tb.price = p.price; tb.price_norm = p.price_norm;
+    tb.dep_norm = p.dep_norm;
+    return tb;
+}
+
 // ------------------------------------------------------------------------------------------
 // Philox4x32-10 (Salmon, Moraes, Dror, Shaw: "Parallel random numbers: as easy as 1, 2, 3", SC'11)
 // ------------------------------------------------------------------------------------------
@@ -196,17 +209,18 @@ template <int L> __device__ __forceinline__ void group_sync()
 // Env-level part of the observation (envs/smart_nanogrid_environment.py:197-205,
 // central_management_system.py:53-60): disturbances now and `H` steps ahead, battery SoC.
 template <typename real>
-__device__ __forceinline__ void write_obs_env(const Params<real> &p, float *obs, int t, real shift, real soc_b)
+__device__ __forceinline__ void write_obs_env(const Params<real> &p, const Tables<real> &tb, float *obs, int t,
+                                              real shift, real soc_b)
 {
     int k = 0;
     if (p.pv) {
-        obs[k++] = (float)(p.irr_norm[t] * shift);
-        obs[k++] = (float)p.price_norm[t];
-        for (int j = 1; j <= p.H; ++j) obs[k++] = (float)(p.irr_norm[t + j] * shift);
-        for (int j = 1; j <= p.H; ++j) obs[k++] = (float)p.price_norm[t + j];
+        obs[k++] = (float)(tb.irr_norm[t] * shift);
+        obs[k++] = (float)tb.price_norm[t];
+        for (int j = 1; j <= p.H; ++j) obs[k++] = (float)(tb.irr_norm[t + j] * shift);
+        for (int j = 1; j <= p.H; ++j) obs[k++] = (float)tb.price_norm[t + j];
     } else {
-        obs[k++] = (float)p.price_norm[t];
-        for (int j = 1; j <= p.H; ++j) obs[k++] = (float)p.price_norm[t + j];
+        obs[k++] = (float)tb.price_norm[t];
+        for (int j = 1; j <= p.H; ++j) obs[k++] = (float)tb.price_norm[t + j];
     }
     if (p.batt) obs[p.off_batt] = (float)soc_b;
 }
@@ -216,8 +230,9 @@ __device__ __forceinline__ void write_obs_env(const Params<real> &p, float *obs,
 // planned vehicle; per-spot SoC state is cleared (clear_initialisation_variables,
 // charging_station.py:138-150) and the reset observation is written.
 template <typename real, int L>
-__device__ __forceinline__ void begin_episode(const Params<real> &p, long long e, int lane, uint32_t episode,
-                                              real shift, real soc_b, real *soc, Rec<real> *rec, float *obs)
+__device__ __forceinline__ void begin_episode(const Params<real> &p, const Tables<real> &tb, long long e, int lane,
+                                              uint32_t episode, real shift, real soc_b, real *soc, Rec<real> *rec,
+                                              float *obs)
 {
     const int N = p.N;
     for (int i = lane; i < N; i += L) {
@@ -237,22 +252,25 @@ __device__ __forceinline__ void begin_episode(const Params<real> &p, long long e
         const int arr = (int)(r.hdr & 0xFFu), dep = (int)((r.hdr >> 8) & 0xFFu);
         const bool present = ((uint32_t)arr != kNoVehicle) && arr == 0 && 0 < dep;
         obs[p.off_soc + i] = present ? (float)r.soc0 : 0.0f;
-        obs[p.off_dep + i] = present ? p.dep_norm[dep] : 0.0f;
+        obs[p.off_dep + i] = present ? tb.dep_norm[dep] : 0.0f;
     }
-    if (lane == 0) write_obs_env(p, obs, 0, shift, soc_b);   // battery SoC survives resets (quirk Q8)
+    if (lane == 0) write_obs_env(p, tb, obs, 0, shift, soc_b);   // battery SoC survives resets (quirk Q8)
 }
 
 // ------------------------------------------------------------------------------------------
 // The step of ONE environment, executed cooperatively by L lanes (lane l owns spots
 // l, l+L, ...).  All row pointers may point to global or shared memory.
-//   act  [A]  in      soc [N] in/out      rec [N] in/out     es in/out (same value in all lanes)
-//   obs  [D]  out     tobs [D] out or null
+//   act [A] in     soc [N] in -> soc_out [N]     rec [N] in -> rec_out [N] (written only when a
+//   vehicle arrives)     es in/out (same value in all lanes)     obs [D] out     tobs [D] out or null
+// In the direct kernels soc == soc_out and rec == rec_out; the tiled kernel reads from the staged
+// input tile and writes SoC to the output tile and changed records straight to global memory.
 // EXACT (double, L == 1 only): reproduces numpy's summation order.
 // ------------------------------------------------------------------------------------------
 template <typename real, int L, bool EXACT>
-__device__ __forceinline__ void env_step(const Params<real> &p, long long e, int lane, const real *act, real *soc,
-                                         Rec<real> *rec, EnvSt<real> &es, float *obs, float *tobs, real &reward_out,
-                                         uint8_t &done_out, uint32_t &err_out, real *diag)
+__device__ __forceinline__ void env_step(const Params<real> &p, const Tables<real> &tb, long long e, int lane,
+                                         const real *act, const real *soc, real *soc_out, const Rec<real> *rec,
+                                         Rec<real> *rec_out, EnvSt<real> &es, float *obs, float *tobs,
+                                         real &reward_out, uint8_t &done_out, uint32_t &err_out, real *diag)
 {
     const int N = p.N;
     const int t = (int)(es.t_ep & 0xFFu);
@@ -314,9 +332,9 @@ __device__ __forceinline__ void env_step(const Params<real> &p, long long e, int
             if (P < 0) neg += P;
             if (P > 0) pos += P;
         }
-        soc[i] = s_new;
+        soc_out[i] = s_new;
         obs[p.off_soc + i] = (float)s_new;                               // charging_station.py:114-117
-        obs[p.off_dep + i] = present ? p.dep_norm[dep - t] : 0.0f;       // :92-112, "/ 24" env:208
+        obs[p.off_dep + i] = present ? tb.dep_norm[dep - t] : 0.0f;       // :92-112, "/ 24" env:208
     }
     if (EXACT) {
         neg = (real)numpy_sum(cneg, nneg);
@@ -331,7 +349,7 @@ __device__ __forceinline__ void env_step(const Params<real> &p, long long e, int
     // ---- env-level phase: CentralManagementSystem.manage_nanogrid (central_management_system.py:99-113) ----
     const real total_power = pos + neg;                                   // :105
     if (total_power < (real)0 && !p.v2x) err |= FLAG_NEG_DEMAND;          // reference raises, :158-159
-    const real solar = p.pv ? p.pv_power[t] * es.pv_shift : (real)0;      // :99-103
+    const real solar = p.pv ? tb.pv_power[t] * es.pv_shift : (real)0;      // :99-103
     real rem = total_power - solar;                                       // :167
     real soc_b = es.soc_b, batt_power = 0, pen_b = 0;
     if (p.batt) {                                                         // battery_energy_storage_system.py:30-106
@@ -359,14 +377,14 @@ __device__ __forceinline__ void env_step(const Params<real> &p, long long e, int
         }
     }
     const real energy = rem * p.dt;                                       // central_management_system.py:107
-    const real price = p.price[t];
+    const real price = tb.price[t];
     const real cost = (energy < (real)0) ? energy * p.sell * price : energy * price;   // accountant.py:26-32
     const real total_pen = p.batt_w * pen_b + pen_veh;                    // penaliser.py:181
     const real total_cost = p.cost_w * fabs(cost) + total_pen;            // accountant.py:35
     const real reward = -total_cost;                                      // ...environment.py:183
 
     if (lane == 0) {
-        write_obs_env(p, obs, t, es.pv_shift, soc_b);                     // obs at the pre-increment t, :173
+        write_obs_env(p, tb, obs, t, es.pv_shift, soc_b);                 // obs at the pre-increment t, :173
         if (diag) {
             diag[D_TOTAL_CH] = pos; diag[D_TOTAL_DIS] = neg; diag[D_SOLAR] = solar;
             diag[D_BATT_POWER] = batt_power; diag[D_GRID_POWER] = rem; diag[D_GRID_COST] = cost;
@@ -382,7 +400,7 @@ __device__ __forceinline__ void env_step(const Params<real> &p, long long e, int
     if (!is_done) {
         for (int i = lane; i < N; i += L) {
             Rec<real> r = rec[i];
-            if (advance_spot(p, e, i, episode, tn, r)) rec[i] = r;
+            if (advance_spot(p, e, i, episode, tn, r)) rec_out[i] = r;
         }
         es.t_ep = (episode << 8) | (uint32_t)tn;
     } else {
@@ -396,7 +414,7 @@ __device__ __forceinline__ void env_step(const Params<real> &p, long long e, int
             }
             episode = (episode + 1u) & 0xFFFFFFu;
             if (p.mode == MODE_SAMPLE) shift = sample_pv_shift(p, p.gid0 + (unsigned long long)e, episode);
-            begin_episode<real, L>(p, e, lane, episode, shift, soc_b, soc, rec, obs);
+            begin_episode<real, L>(p, tb, e, lane, episode, shift, soc_b, soc_out, rec_out, obs);
         }
         es.t_ep = (episode << 8);                                         // t wraps to 0, :178
     }

@@ -11,6 +11,7 @@
 
 #include "../../include/sng.h"
 #include "sng_device.cuh"
+#include "sng_tiled.cuh"
 
 namespace sng {
 
@@ -25,6 +26,7 @@ struct EngineBase {
     virtual int sample_plan(cudaStream_t st) = 0;
     virtual int error_flags(uint32_t *out, cudaStream_t st) = 0;
     virtual int set_tuning(int lanes, int tile, int bulk) = 0;
+    virtual int set_pipeline(int in_stages, int out_stages, int ctas_per_sm) = 0;
     int64_t launches = 0;
     std::string error;
 };
@@ -55,9 +57,10 @@ __global__ void __launch_bounds__(256) step_direct_kernel(const Params<real> p)
     real reward;
     uint8_t done;
     uint32_t err;
-    env_step<real, L, EXACT>(p, e, lane, p.actions + (size_t)e * p.A, p.soc + (size_t)e * p.N,
-                             p.rec + (size_t)e * p.N, es, p.obs + (size_t)e * p.D,
-                             p.tobs ? p.tobs + (size_t)e * p.D : nullptr, reward, done, err,
+    real *soc = p.soc + (size_t)e * p.N;
+    Rec<real> *rec = p.rec + (size_t)e * p.N;
+    env_step<real, L, EXACT>(p, global_tables(p), e, lane, p.actions + (size_t)e * p.A, soc, soc, rec, rec, es,
+                             p.obs + (size_t)e * p.D, p.tobs ? p.tobs + (size_t)e * p.D : nullptr, reward, done, err,
                              p.diag ? p.diag + (size_t)e * D_COUNT : nullptr);
     if (lane == 0) {
         p.envst[e] = es;
@@ -82,7 +85,9 @@ __global__ void __launch_bounds__(256) rollout_direct_kernel(const Params<real> 
         real r;
         uint8_t d;
         uint32_t err;
-        env_step<real, L, EXACT>(p, e, lane, actions + row * p.A, p.soc + (size_t)e * p.N, p.rec + (size_t)e * p.N, es,
+        real *soc = p.soc + (size_t)e * p.N;
+        Rec<real> *rec = p.rec + (size_t)e * p.N;
+        env_step<real, L, EXACT>(p, global_tables(p), e, lane, actions + row * p.A, soc, soc, rec, rec, es,
                                  obs + row * p.D, nullptr, r, d, err, nullptr);
         group_sync<L>();
         err_all |= err;
@@ -117,8 +122,8 @@ __global__ void __launch_bounds__(256) reset_kernel(const Params<real> p, const 
     }
     if (init || reset_battery) soc_b = p.batt ? p.b_soc0 : (real)0;
     if (p.mode == MODE_SAMPLE) shift = sample_pv_shift(p, p.gid0 + (unsigned long long)e, episode);
-    begin_episode<real, L>(p, e, lane, episode, shift, soc_b, p.soc + (size_t)e * p.N, p.rec + (size_t)e * p.N,
-                           p.obs + (size_t)e * p.D);
+    begin_episode<real, L>(p, global_tables(p), e, lane, episode, shift, soc_b, p.soc + (size_t)e * p.N,
+                           p.rec + (size_t)e * p.N, p.obs + (size_t)e * p.D);
     if (lane == 0) {
         es.soc_b = soc_b;
         es.pv_shift = shift;
@@ -183,6 +188,9 @@ public:
     int device = 0;
     int lanes = 0;  // 0 = auto
     int tile = 0, bulk = 1;
+    int in_stages = 0, out_stages = 0, ctas_per_sm = 0;  // 0 = auto
+    int num_sms = 148;
+    size_t smem_optin = 0;
     void *d_tables = nullptr;
     uint32_t *d_flag = nullptr;
 
@@ -201,6 +209,13 @@ public:
             return SNG_ERR_UNSUPPORTED;
         }
         SNG_CUDA(cudaSetDevice(dev));
+        {
+            int v = 0;
+            SNG_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev));
+            num_sms = v;
+            SNG_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+            smem_optin = (size_t)v;
+        }
         memset(&p, 0, sizeof(p));
         p.n_envs = c.n_envs;
         p.gid0 = (unsigned long long)c.env_gid0;
@@ -392,17 +407,97 @@ public:
         return arr | (dep << 8) | (cap << 16) | (next << 24);
     }
 
-    int step(cudaStream_t st) override
+    // Parameters with every per-env pointer advanced by e0 envs (tail of a tiled launch).
+    Params<real> offset_params(long long e0) const
     {
-        int rc = check_ready(true);
-        if (rc) return rc;
+        Params<real> q = p;
+        q.n_envs = p.n_envs - e0;
+        q.gid0 = p.gid0 + (unsigned long long)e0;
+        q.actions += (size_t)e0 * p.A; q.obs += (size_t)e0 * p.D; q.reward += e0; q.done += e0;
+        if (q.tobs) q.tobs += (size_t)e0 * p.D;
+        q.soc += (size_t)e0 * p.N; q.rec += (size_t)e0 * p.N; q.envst += e0;
+        if (q.plan) q.plan += (size_t)e0 * p.N * kMaxVehicles;
+        if (q.err) q.err += e0;
+        if (q.diag) q.diag += (size_t)e0 * D_COUNT;
+        if (q.last_ret) q.last_ret += e0;
+        return q;
+    }
+
+    int launch_direct(const Params<real> &q, cudaStream_t st)
+    {
         return dispatch_lanes([&](auto lc) -> int {
             constexpr int L = decltype(lc)::value;
-            step_direct_kernel<real, L, EXACT><<<grid_for(p.n_envs * L), 256, 0, st>>>(p);
+            step_direct_kernel<real, L, EXACT><<<grid_for(q.n_envs * L), 256, 0, st>>>(q);
             ++launches;
             SNG_CUDA(cudaGetLastError());
             return (int)SNG_OK;
         });
+    }
+
+    static bool aligned16(const void *q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; }
+
+    template <int L, int OS> int launch_tiled(int epb, int num_tiles, int is, cudaStream_t st)
+    {
+        auto kern = step_tiled_kernel<real, L, OS>;
+        const TileLayout lay = make_tile_layout<real>(epb, p.N, p.A, p.D, cfg.table_len, is, OS);
+        SNG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total));
+        int per_sm = 0;
+        SNG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, epb * L, lay.total));
+        if (per_sm < 1) { error = "tiled kernel does not fit on an SM"; return SNG_ERR_CUDA; }
+        if (ctas_per_sm > 0 && per_sm > ctas_per_sm) per_sm = ctas_per_sm;
+        long long grid = (long long)num_sms * per_sm;
+        if (grid > num_tiles) grid = num_tiles;
+        kern<<<(unsigned)grid, epb * L, lay.total, st>>>(p, epb, num_tiles, is, cfg.table_len);
+        ++launches;
+        SNG_CUDA(cudaGetLastError());
+        return SNG_OK;
+    }
+
+    // Tile geometry of the bulk-copy path; returns false when the direct kernel must be used.
+    bool plan_tiles(int &L, int &epb, int &is, int &os) const
+    {
+        if (EXACT || !bulk) return false;
+        if (!aligned16(p.actions) || !aligned16(p.obs) || !aligned16(p.reward) || !aligned16(p.done) ||
+            !aligned16(p.soc) || !aligned16(p.rec) || !aligned16(p.envst))
+            return false;
+        L = lanes > 0 ? lanes : 1;
+        epb = tile > 0 ? tile : (L == 1 ? 128 : (L <= 4 ? 64 : (L <= 16 ? 32 : 16)));
+        if (epb % 16 != 0 || epb * L > 1024 || epb * L < 32) return false;
+        if (p.n_envs < epb) return false;
+        os = out_stages > 0 ? out_stages : 1;
+        if (os > 2) os = 2;
+        is = in_stages > 0 ? in_stages : 2;
+        while (is > 1 && make_tile_layout<real>(epb, p.N, p.A, p.D, cfg.table_len, is, os).total > smem_optin) --is;
+        return make_tile_layout<real>(epb, p.N, p.A, p.D, cfg.table_len, is, os).total <= smem_optin;
+    }
+
+    int step(cudaStream_t st) override
+    {
+        int rc = check_ready(true);
+        if (rc) return rc;
+        if constexpr (!EXACT) {
+            int L, epb, is, os;
+            if (plan_tiles(L, epb, is, os)) {
+                const int num_tiles = (int)(p.n_envs / epb);
+                auto go = [&](auto lc) -> int {
+                    constexpr int LL = decltype(lc)::value;
+                    return os == 2 ? launch_tiled<LL, 2>(epb, num_tiles, is, st) : launch_tiled<LL, 1>(epb, num_tiles, is, st);
+                };
+                switch (L) {
+                case 1: rc = go(std::integral_constant<int, 1>()); break;
+                case 2: rc = go(std::integral_constant<int, 2>()); break;
+                case 4: rc = go(std::integral_constant<int, 4>()); break;
+                case 8: rc = go(std::integral_constant<int, 8>()); break;
+                case 16: rc = go(std::integral_constant<int, 16>()); break;
+                default: rc = go(std::integral_constant<int, 32>()); break;
+                }
+                if (rc) return rc;
+                const long long done_envs = (long long)num_tiles * epb;
+                if (done_envs < p.n_envs) return launch_direct(offset_params(done_envs), st);
+                return SNG_OK;
+            }
+        }
+        return launch_direct(p, st);
     }
 
     int rollout(const void *actions, float *obs, void *reward, uint8_t *done, int n_steps, cudaStream_t st) override
@@ -471,6 +566,13 @@ public:
             return SNG_ERR_ARG;
         }
         lanes = l; tile = t; bulk = b;
+        return SNG_OK;
+    }
+
+    int set_pipeline(int is, int os, int cps) override
+    {
+        if (is < 0 || is > 8 || os < 0 || os > 2 || cps < 0) { error = "sng_set_pipeline: bad arguments"; return SNG_ERR_ARG; }
+        in_stages = is; out_stages = os; ctas_per_sm = cps;
         return SNG_OK;
     }
 };
