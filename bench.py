@@ -201,12 +201,10 @@ def main():
     ap.add_argument("--ref-envs", type=int, default=65536, help="sample size of the CPU reference arm")
     ap.add_argument("--cpu-seconds", type=float, default=10.0, help="wall time of the cpu_baseline leg")
     ap.add_argument("--e2e-steps", type=int, default=24)
-    ap.add_argument("--lanes", type=int, default=0, help="tuning: lanes per env (0 = auto)")
-    ap.add_argument("--tile", type=int, default=0, help="tuning: envs per tile (0 = auto)")
-    ap.add_argument("--no-bulk", action="store_true", help="tuning: disable the TMA bulk-copy path")
-    ap.add_argument("--in-stages", type=int, default=0)
-    ap.add_argument("--out-stages", type=int, default=0)
-    ap.add_argument("--ctas", type=int, default=0, help="tuning: cap on resident CTAs per SM")
+    ap.add_argument("--warps", type=int, default=0, help="tuning: warps (blocks of 32 envs) per CTA (0 = auto)")
+    ap.add_argument("--generic", action="store_true", help="tuning: use the generic runtime-N kernel")
+    ap.add_argument("--no-bulk", action="store_true", help="tuning: stage rows with plain loads instead of the copy engine")
+    ap.add_argument("--host-chunks", type=int, default=0, help="tuning: env chunks of the pipelined host path")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -232,8 +230,7 @@ def main():
     E = args.envs
     env = BatchedSmartNanogridEnv(E, device=dev, seed=0, env_gid0=rank * E, precision="float32", auto_reset=True,
                                   **ENV_KW)
-    env.set_tuning(args.lanes, args.tile, 0 if args.no_bulk else 1)
-    env.set_pipeline(args.in_stages, args.out_stages, args.ctas)
+    env.set_tuning(args.warps, int(args.generic), 0 if args.no_bulk else 1, args.host_chunks)
     cfg = env.cfg
     env.reset()
     # actions: a pre-filled U(low, high) tensor re-read from HBM every step

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define SNG_ABI_VERSION 1
+#define SNG_ABI_VERSION 2
 #define SNG_MAX_VEHICLES 8   /* schedule slots per spot and day */
 #define SNG_MAX_SPOTS 255
 #define SNG_MAX_TABLE 512    /* entries of the shared PV / price tables (two days) */
@@ -84,15 +84,18 @@ typedef struct {
 typedef struct {
     uint32_t struct_size;
     int32_t act_dim, obs_dim;
-    int32_t real_bytes;     /* 4 or 8: element size of actions / reward / soc */
-    int32_t rec_bytes;      /* one current-vehicle record (12 or 24) */
+    int32_t real_bytes;     /* 4 or 8: element size of actions / reward / soc / req */
+    int32_t plan_rec_bytes; /* one planned-vehicle record of `plan` (12 or 24) */
     int32_t envst_bytes;    /* one per-env scalar block (16 or 32) */
     int32_t plan_slots;     /* SNG_MAX_VEHICLES */
     int32_t diag_count;     /* reals per env in the optional diagnostics row */
-    int32_t env_align;      /* n_envs granularity for which the fast (bulk-copy) path applies */
+    int32_t env_block;      /* 32: per-spot state arrays are blocked [ceil(E/32)][n_spots][32] (see sng_buffers) */
 } sng_layout;
 
-/* Device buffers.  `real` = float (SNG_F32) or double (SNG_F64).  Optional pointers may be NULL. */
+/* Device buffers.  `real` = float (SNG_F32) or double (SNG_F64).  Optional pointers may be NULL.
+ * Per-spot state (soc, hdr, req) is a structure of arrays blocked by env_block = 32 envs: element
+ * (env e, spot i) lives at index (e / 32) * n_spots * 32 + i * 32 + e % 32, so the caller allocates
+ * ceil(E / 32) * n_spots * 32 elements per array.  Contents are opaque between calls. */
 typedef struct {
     uint32_t struct_size;
     uint32_t _pad;
@@ -101,10 +104,11 @@ typedef struct {
     void *reward;           /* out  [E] real */
     uint8_t *done;          /* out  [E] terminated flag (truncated is always 0 in the reference) */
     float *terminal_obs;    /* out, optional [E][obs_dim]: last obs of the finished episode (auto_reset) */
-    void *soc;              /* state [E][n_spots] real: SoC of the vehicle at each spot after the last step */
-    void *rec;              /* state [E][n_spots] x rec_bytes: current / last vehicle record per spot */
+    void *soc;              /* state, blocked real: SoC column the next step starts from */
+    uint32_t *hdr;          /* state, blocked u32: arrival | departure << 8 | capacity << 16 | next arrival << 24 */
+    void *req;              /* state, blocked real: requested SoC of the current vehicle */
     void *envst;            /* state [E] x envst_bytes: battery SoC, pv_shift, episode return, (episode, t) */
-    void *plan;             /* optional [E][n_spots][SNG_MAX_VEHICLES] x rec_bytes: full-day schedule */
+    void *plan;             /* optional [E][n_spots][SNG_MAX_VEHICLES] x plan_rec_bytes: full-day schedule */
     uint32_t *err;          /* optional [E] sticky SNG_FLAG_* bits */
     void *diag;             /* optional [E][diag_count] real per-step diagnostics */
     void *last_return;      /* optional [E] real: return of the most recently finished episode */
@@ -172,11 +176,11 @@ int sng_error_flags(sng_env *env, uint32_t *host_out, void *stream);
 /* Kernels launched by this handle so far (bench.py's gpu_launches claim). */
 int64_t sng_launch_count(const sng_env *env);
 
-/* Tuning knob for experiments: lanes per env (0 = auto) and envs per tile (0 = auto). */
-int sng_set_tuning(sng_env *env, int lanes_per_env, int envs_per_tile, int use_bulk_copy);
-/* Tuning knob: depth of the shared-memory input / output rings of the bulk-copy kernel and a cap
- * on resident CTAs per SM (0 = auto for each). */
-int sng_set_pipeline(sng_env *env, int in_stages, int out_stages, int ctas_per_sm);
+/* Tuning knobs for experiments and tests: warps (= blocks of 32 envs) per CTA (0 = auto); force the
+ * generic runtime-N kernel instead of the specialised one; stage action / observation rows with the
+ * copy engine (1, default) or with plain loads / stores (0); number of env chunks sng_step_host
+ * pipelines over PCIe (0 = auto). */
+int sng_set_tuning(sng_env *env, int warps_per_cta, int use_generic_kernel, int use_bulk_copy, int host_chunks);
 
 #ifdef __cplusplus
 }

@@ -317,8 +317,22 @@ void ngo_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t ou
 }
 
 /* Sampler spec shared with the CUDA kernel (DESIGN.md "Sampling"): the arrival process of
- * ChargingStation.generate_initial_vehicle_presence_per_charger (charging_station.py:200-255)
- * with draws keyed by (seed, global env id, spot, episode, timestep). */
+ * ChargingStation.generate_initial_vehicle_presence_per_charger (charging_station.py:200-255):
+ * one Bernoulli(0.4) arrival trial per free spot and step (:213-214), none on the departure step
+ * itself (:239-251).  Sampled per VEHICLE: the count of failed trials before the next arrival is
+ * geometric, so the Philox block keyed by (seed, global env id, spot, episode, arrival step)
+ * yields the vehicle and the step its successor arrives at (dep + 1 + gap); the block keyed
+ * 0xFFFFFFFE yields the first arrival of the day. */
+static uint32_t geometric_gap(uint32_t x)
+{
+    uint32_t g = 0, th = 0x99999999u; /* floor(0.6 * 2^32); th_{k+1} = floor(th_k * 0x9999999A / 2^32) */
+    while (x < th) {
+        g++;
+        th = (uint32_t)(((uint64_t)th * 0x9999999Aull) >> 32);
+    }
+    return g;
+}
+
 void ngo_sample_episode(const ngo_config *c, ngo_state *s, int64_t e, uint64_t seed, uint64_t env_gid,
                         uint32_t episode)
 {
@@ -334,44 +348,40 @@ void ngo_sample_episode(const ngo_config *c, ngo_state *s, int64_t e, uint64_t s
         memset(soc, 0, sizeof(double) * W);
         memset(cap, 0, sizeof(double) * W);
         memset(req, 0, sizeof(double) * W);
-        int nv = 0, present = 0, dep_cur = 0;
-        double cap_cur = 0, req_cur = 0;
+        int nv = 0;
         const uint64_t stream = env_gid * (uint64_t)N + (uint64_t)i;
-        for (int t = 0; t < T; t++) {
-            if (!present) { /* :213-237 */
-                const uint32_t ctr[4] = {(uint32_t)stream, (uint32_t)(stream >> 32), episode, (uint32_t)t};
-                uint32_t x[4];
-                ngo_philox4x32_10(ctr, key, x);
-                if (x[0] > 0x99999999u && nv < NGO_MAX_VEHICLES) { /* round(rand() - 0.1) == 1 <=> u > 0.6, :214 */
-                    present = 1;
-                    const float u1 = (float)(x[1] >> 8) * 5.9604644775390625e-08f;
-                    const float soc0 = fmaf(0.8f, u1, 0.1f); /* uniform(0.1, 0.9), :257-259 */
-                    float rq = 1.0f;
-                    if (c->req_soc) { /* :227-229, 261-265 */
-                        const float u2 = (float)(x[2] >> 8) * 5.9604644775390625e-08f;
-                        const float lo = (soc0 <= 0.9f) ? soc0 + 0.1f : 1.0f;
-                        rq = fmaf(1.0f - lo, u2, lo);
-                    }
-                    const int cp = c->diff_cap ? 15 + (int)(((x[3] >> 16) * 105u) >> 16) : 40; /* :267-269 */
-                    const int low = t + i4; /* :271-279 */
-                    const int up = (t + i10 < T + i1) ? t + i10 : T + i1;
-                    const int dp = (low >= up) ? low : low + (int)(((x[3] & 0xFFFFu) * (uint32_t)(up - low)) >> 16);
-                    soc[t] = (double)soc0;
-                    cap_cur = cp;
-                    req_cur = (double)rq;
-                    dep_cur = dp;
-                    arr[nv] = t;
-                    dep[nv] = dp;
-                    nv++;
-                }
+        uint32_t x[4];
+        {
+            const uint32_t ctr[4] = {(uint32_t)stream, (uint32_t)(stream >> 32), episode, 0xFFFFFFFEu};
+            ngo_philox4x32_10(ctr, key, x);
+        }
+        uint32_t next = geometric_gap(x[0]); /* failed trials at t = 0, 1, ... before the first arrival */
+        while (next < (uint32_t)T && nv < NGO_MAX_VEHICLES) {
+            const int t = (int)next;
+            const uint32_t ctr[4] = {(uint32_t)stream, (uint32_t)(stream >> 32), episode, (uint32_t)t};
+            ngo_philox4x32_10(ctr, key, x);
+            const float u1 = (float)(x[1] >> 8) * 5.9604644775390625e-08f;
+            const float soc0 = fmaf(0.8f, u1, 0.1f); /* uniform(0.1, 0.9), :257-259 */
+            float rq = 1.0f;
+            if (c->req_soc) { /* :227-229, 261-265 */
+                const float u2 = (float)(x[2] >> 8) * 5.9604644775390625e-08f;
+                const float lo = (soc0 <= 0.9f) ? soc0 + 0.1f : 1.0f;
+                rq = fmaf(1.0f - lo, u2, lo);
             }
-            if (present && t < dep_cur) { /* :239-242 */
-                occ[t] = 1;
-                cap[t] = cap_cur;
-                req[t] = req_cur;
-            } else { /* :243-251 */
-                present = 0;
+            const int cp = c->diff_cap ? 15 + (int)(((x[3] >> 16) * 105u) >> 16) : 40; /* :267-269 */
+            const int low = t + i4; /* :271-279 */
+            const int up = (t + i10 < T + i1) ? t + i10 : T + i1;
+            const int dp = (low >= up) ? low : low + (int)(((x[3] & 0xFFFFu) * (uint32_t)(up - low)) >> 16);
+            soc[t] = (double)soc0;
+            for (int q = t; q < dp && q < T; q++) { /* :239-242 */
+                occ[q] = 1;
+                cap[q] = cp;
+                req[q] = (double)rq;
             }
+            arr[nv] = t;
+            dep[nv] = dp;
+            nv++;
+            next = (uint32_t)dp + 1u + geometric_gap(x[0]); /* no trial on the departure step, :243-251 */
         }
         s->n_veh[e * N + i] = nv;
     }

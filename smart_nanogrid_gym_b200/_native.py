@@ -21,7 +21,7 @@ DIAG = ("total_ch", "total_dis", "solar", "batt_power", "grid_power", "grid_cost
 
 EXPORTS = ("sng_abi_version", "sng_sizeof", "sng_last_error", "sng_query_layout", "sng_create", "sng_destroy", "sng_bind",
            "sng_reset", "sng_load_schedule", "sng_step", "sng_rollout", "sng_step_host", "sng_sample_plan",
-           "sng_error_flags", "sng_launch_count", "sng_set_tuning", "sng_set_pipeline")
+           "sng_error_flags", "sng_launch_count", "sng_set_tuning")
 
 
 class SngConfig(C.Structure):
@@ -39,13 +39,13 @@ class SngConfig(C.Structure):
 
 class SngLayout(C.Structure):
     _fields_ = [("struct_size", C.c_uint32), ("act_dim", C.c_int32), ("obs_dim", C.c_int32), ("real_bytes", C.c_int32),
-                ("rec_bytes", C.c_int32), ("envst_bytes", C.c_int32), ("plan_slots", C.c_int32),
-                ("diag_count", C.c_int32), ("env_align", C.c_int32)]
+                ("plan_rec_bytes", C.c_int32), ("envst_bytes", C.c_int32), ("plan_slots", C.c_int32),
+                ("diag_count", C.c_int32), ("env_block", C.c_int32)]
 
 
 class SngBuffers(C.Structure):
     _fields_ = [("struct_size", C.c_uint32), ("_pad", C.c_uint32)] + [(n, C.c_void_p) for n in (
-        "actions", "obs", "reward", "done", "terminal_obs", "soc", "rec", "envst", "plan", "err", "diag",
+        "actions", "obs", "reward", "done", "terminal_obs", "soc", "hdr", "req", "envst", "plan", "err", "diag",
         "last_return")]
 
 
@@ -99,9 +99,8 @@ def lib():
         L.sng_error_flags.argtypes = [C.c_void_p, C.POINTER(C.c_uint32), C.c_void_p]
         L.sng_launch_count.argtypes = [C.c_void_p]
         L.sng_launch_count.restype = C.c_int64
-        L.sng_set_tuning.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
-        L.sng_set_pipeline.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
-        if L.sng_abi_version() != 1:
+        L.sng_set_tuning.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
+        if L.sng_abi_version() != 2:
             raise NativeError("libsng.so ABI version mismatch")
         for which, st in enumerate((SngConfig, SngLayout, SngBuffers, SngScheduleView)):
             if L.sng_sizeof(which) != C.sizeof(st):

@@ -66,8 +66,12 @@ class BatchedSmartNanogridEnv:
         self.reward = z(E, dtype=self.real)
         self.done = z(E, dtype=torch.uint8)
         self.terminal_obs = z(E, D, dtype=torch.float32) if want_terminal_obs else None
-        self.soc = z(E, N, dtype=self.real)
-        self._rec = z(E * N * self.layout.rec_bytes, dtype=torch.uint8)
+        # per-spot state: structure of arrays blocked by 32 envs, [ceil(E/32)][N][32] (include/sng.h)
+        B = self.layout.env_block
+        self._blocks = (E + B - 1) // B
+        self._soc = z(self._blocks, N, B, dtype=self.real)
+        self._hdr = z(self._blocks, N, B, dtype=torch.int32)
+        self._req = z(self._blocks, N, B, dtype=self.real)
         self._envst = z(E * self.layout.envst_bytes, dtype=torch.uint8)
         self._plan = None
         self.err = z(E, dtype=torch.int32)
@@ -96,13 +100,14 @@ class BatchedSmartNanogridEnv:
         b.struct_size = C.sizeof(nat.SngBuffers)
         obs, rew, done = self._bound_out
         b.actions, b.obs, b.reward, b.done = (_ptr(self._bound_actions), _ptr(obs), _ptr(rew), _ptr(done))
-        b.terminal_obs, b.soc, b.rec, b.envst = _ptr(self.terminal_obs), _ptr(self.soc), _ptr(self._rec), _ptr(self._envst)
+        b.terminal_obs, b.soc, b.hdr, b.req = _ptr(self.terminal_obs), _ptr(self._soc), _ptr(self._hdr), _ptr(self._req)
+        b.envst = _ptr(self._envst)
         b.plan, b.err, b.diag, b.last_return = _ptr(self._plan), _ptr(self.err), _ptr(self.diag), _ptr(self.last_return)
         nat.check(self._lib.sng_bind(self._h, C.byref(b)))
 
     def _ensure_plan(self):
         if self._plan is None:
-            n = self.num_envs * self.cfg.n_spots * MAX_VEHICLES * self.layout.rec_bytes
+            n = self.num_envs * self.cfg.n_spots * MAX_VEHICLES * self.layout.plan_rec_bytes
             self._plan = torch.zeros(n, dtype=torch.uint8, device=self.device)
             self._bind()
 
@@ -122,11 +127,27 @@ class BatchedSmartNanogridEnv:
         except Exception:  # noqa: BLE001
             pass
 
-    def set_tuning(self, lanes_per_env=0, envs_per_tile=0, use_bulk_copy=1):
-        nat.check(self._lib.sng_set_tuning(self._h, lanes_per_env, envs_per_tile, use_bulk_copy))
+    def set_tuning(self, warps_per_cta=0, use_generic_kernel=0, use_bulk_copy=1, host_chunks=0):
+        """Experiment / test knobs of the step launch (include/sng.h sng_set_tuning)."""
+        nat.check(self._lib.sng_set_tuning(self._h, warps_per_cta, use_generic_kernel, use_bulk_copy, host_chunks))
 
-    def set_pipeline(self, in_stages=0, out_stages=0, ctas_per_sm=0):
-        nat.check(self._lib.sng_set_pipeline(self._h, in_stages, out_stages, ctas_per_sm))
+    def _unblock(self, x):
+        """Blocked per-spot state [E/32][N][32] -> [E][N]."""
+        return x.permute(0, 2, 1).reshape(-1, self.cfg.n_spots)[:self.num_envs]
+
+    @property
+    def soc(self):
+        """[E, N] SoC column the next step starts from (a de-blocked copy of the kernel state)."""
+        return self._unblock(self._soc)
+
+    def spot_state(self):
+        """Decoded per-spot state as numpy arrays [E, N]: arrival, departure, capacity, next arrival
+        (255 = none), requested SoC, SoC."""
+        h = self._unblock(self._hdr).cpu().numpy().astype(np.uint32)
+        return dict(arr=(h & 0xFF).astype(np.int32), dep=((h >> 8) & 0xFF).astype(np.int32),
+                    cap=((h >> 16) & 0xFF).astype(np.int32), next=(h >> 24).astype(np.int32),
+                    req=self._unblock(self._req).cpu().numpy().astype(np.float64),
+                    soc=self.soc.cpu().numpy().astype(np.float64))
 
     @property
     def launch_count(self) -> int:
@@ -289,7 +310,8 @@ class BatchedSmartNanogridEnv:
                     episode=(r["t_ep"] >> 8).astype(np.int64))
 
     def state_dict(self):
-        sd = dict(soc=self.soc.clone(), rec=self._rec.clone(), envst=self._envst.clone(), err=self.err.clone(),
+        sd = dict(soc=self._soc.clone(), hdr=self._hdr.clone(), req=self._req.clone(), envst=self._envst.clone(),
+                  err=self.err.clone(),
                   last_return=self.last_return.clone(), seed=self.seed_value, obs=self.obs.clone())
         if self._plan is not None:
             sd["plan"] = self._plan.clone()
@@ -298,8 +320,9 @@ class BatchedSmartNanogridEnv:
     def load_state_dict(self, sd):
         """Restores a state captured by state_dict() on an env that has been reset() / load_schedule()d
         in the same mode (sampling vs replay)."""
-        self.soc.copy_(sd["soc"])
-        self._rec.copy_(sd["rec"])
+        self._soc.copy_(sd["soc"])
+        self._hdr.copy_(sd["hdr"])
+        self._req.copy_(sd["req"])
         self._envst.copy_(sd["envst"])
         self.err.copy_(sd["err"])
         self.last_return.copy_(sd["last_return"])

@@ -59,11 +59,11 @@ int sng_query_layout(const sng_config *cfg, sng_layout *out)
     out->act_dim = cfg->n_spots + b;
     out->obs_dim = (1 + pv) * (1 + cfg->horizon) + 2 * cfg->n_spots + b;
     out->real_bytes = f64 ? 8 : 4;
-    out->rec_bytes = f64 ? (int)sizeof(sng::Rec<double>) : (int)sizeof(sng::Rec<float>);
+    out->plan_rec_bytes = f64 ? (int)sizeof(sng::PlanRec<double>) : (int)sizeof(sng::PlanRec<float>);
     out->envst_bytes = f64 ? (int)sizeof(sng::EnvSt<double>) : (int)sizeof(sng::EnvSt<float>);
     out->plan_slots = SNG_MAX_VEHICLES;
     out->diag_count = SNG_D_COUNT;
-    out->env_align = 128;
+    out->env_block = sng::kBlock;
     return SNG_OK;
 }
 
@@ -145,16 +145,10 @@ int sng_error_flags(sng_env *env, uint32_t *host_out, void *stream)
 
 int64_t sng_launch_count(const sng_env *env) { return (env && env->eng) ? env->eng->launches : 0; }
 
-int sng_set_tuning(sng_env *env, int lanes_per_env, int envs_per_tile, int use_bulk_copy)
+int sng_set_tuning(sng_env *env, int warps_per_cta, int use_generic_kernel, int use_bulk_copy, int host_chunks)
 {
     SNG_ENV_CHECK(env);
-    return done(env, env->eng->set_tuning(lanes_per_env, envs_per_tile, use_bulk_copy));
-}
-
-int sng_set_pipeline(sng_env *env, int in_stages, int out_stages, int ctas_per_sm)
-{
-    SNG_ENV_CHECK(env);
-    return done(env, env->eng->set_pipeline(in_stages, out_stages, ctas_per_sm));
+    return done(env, env->eng->set_tuning(warps_per_cta, use_generic_kernel, use_bulk_copy, host_chunks));
 }
 
 }  // extern "C"

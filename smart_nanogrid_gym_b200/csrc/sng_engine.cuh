@@ -1,5 +1,5 @@
 // sng_engine.cuh -- kernels and host-side launch logic, templated on the arithmetic type.
-// Instantiated as Engine<float,false> (sng_f32.cu) and Engine<double,true> (sng_f64.cu, built
+// Instantiated as Engine<float,false> (sng_api.cu) and Engine<double,true> (sng_f64.cu, built
 // with -fmad=false so that no multiply-add is contracted).
 #pragma once
 #include <cmath>
@@ -11,7 +11,7 @@
 
 #include "../../include/sng.h"
 #include "sng_device.cuh"
-#include "sng_tiled.cuh"
+#include "sng_tma.cuh"
 
 namespace sng {
 
@@ -25,8 +25,7 @@ struct EngineBase {
     virtual int step_host(const void *a, float *obs, void *rew, uint8_t *done, cudaStream_t st) = 0;
     virtual int sample_plan(cudaStream_t st) = 0;
     virtual int error_flags(uint32_t *out, cudaStream_t st) = 0;
-    virtual int set_tuning(int lanes, int tile, int bulk) = 0;
-    virtual int set_pipeline(int in_stages, int out_stages, int ctas_per_sm) = 0;
+    virtual int set_tuning(int warps_per_cta, int use_generic, int use_bulk, int host_chunks) = 0;
     int64_t launches = 0;
     std::string error;
 };
@@ -44,71 +43,88 @@ EngineBase *make_engine_f64(const sng_config &cfg, int device, std::string &err)
     } while (0)
 
 // ------------------------------------------------------------------------------------------
-// Kernels, direct-global variant: L lanes per env, rows addressed in global memory.
+// The step kernel.  One warp = one block of 32 consecutive envs, one thread per env; warps are
+// independent (no CTA-wide barrier).  Per warp and step:
+//   lane 0: cp.async.bulk  actions[32 rows] HBM -> shared (mbarrier complete_tx)
+//   all   : coalesced loads of the blocked state, wait for the actions, env_step() out of shared
+//           memory, observation rows written to shared memory
+//   lane 0: cp.async.bulk  obs[32 rows] shared -> HBM
+// `n_steps` > 1 is the rollout: the same warp advances its envs n_steps times, one action / obs /
+// reward / done slab per step (slab strides in rows: E).
+// use_bulk == 0 (or a partial last block, or unaligned bases) stages the rows with plain coalesced
+// loads / stores instead of the copy engine; both paths run the identical env_step().
 // ------------------------------------------------------------------------------------------
-template <typename real, int L, bool EXACT>
-__global__ void __launch_bounds__(256) step_direct_kernel(const Params<real> p)
+template <typename real, int NCT, bool EXACT>
+__global__ void __launch_bounds__(256) step_kernel(const Params<real> p, const real *actions, float *obs_out,
+                                                  real *reward, uint8_t *done, int n_steps, int use_bulk)
 {
-    const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long e = gtid / L;
-    const int lane = (int)(gtid % L);
-    if (e >= p.n_envs) return;
-    EnvSt<real> es = p.envst[e];
-    real reward;
-    uint8_t done;
-    uint32_t err;
-    real *soc = p.soc + (size_t)e * p.N;
-    Rec<real> *rec = p.rec + (size_t)e * p.N;
-    env_step<real, L, EXACT>(p, global_tables(p), e, lane, p.actions + (size_t)e * p.A, soc, soc, rec, rec, es,
-                             p.obs + (size_t)e * p.D, p.tobs ? p.tobs + (size_t)e * p.D : nullptr, reward, done, err,
-                             p.diag ? p.diag + (size_t)e * D_COUNT : nullptr);
-    if (lane == 0) {
-        p.envst[e] = es;
-        p.reward[e] = reward;
-        p.done[e] = done;
-        if (err && p.err) atomicOr(p.err + e, err);
-    }
-}
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const long long blk = (long long)blockIdx.x * wpb + warp;   // state block = 32 envs
+    const long long e0 = blk * kBlock;
+    if (e0 >= p.n_envs) return;                                  // whole warp leaves; no CTA barrier below
+    const int N = NCT ? NCT : p.N;
+    const int A = p.A, D = p.D;
+    const uint32_t act_bytes = (uint32_t)(kBlock * A * sizeof(real)), obs_bytes = (uint32_t)(kBlock * D * sizeof(float));
+    const uint32_t per_warp = align128(act_bytes) + align128(obs_bytes);
+    real *act_s = reinterpret_cast<real *>(smem + (size_t)warp * per_warp);
+    float *obs_s = reinterpret_cast<float *>(smem + (size_t)warp * per_warp + align128(act_bytes));
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + (size_t)wpb * per_warp) + warp;
 
-template <typename real, int L, bool EXACT>
-__global__ void __launch_bounds__(256) rollout_direct_kernel(const Params<real> p, const real *actions, float *obs,
-                                                            real *reward, uint8_t *done, int n_steps)
-{
-    const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long e = gtid / L;
-    const int lane = (int)(gtid % L);
-    if (e >= p.n_envs) return;
-    EnvSt<real> es = p.envst[e];
-    uint32_t err_all = 0;
-    for (int s = 0; s < n_steps; ++s) {
-        const size_t row = (size_t)s * p.n_envs + e;
-        real r;
-        uint8_t d;
-        uint32_t err;
-        real *soc = p.soc + (size_t)e * p.N;
-        Rec<real> *rec = p.rec + (size_t)e * p.N;
-        env_step<real, L, EXACT>(p, global_tables(p), e, lane, actions + row * p.A, soc, soc, rec, rec, es,
-                                 obs + row * p.D, nullptr, r, d, err, nullptr);
-        group_sync<L>();
-        err_all |= err;
+    const long long left = p.n_envs - e0;
+    const int n_valid = left < kBlock ? (int)left : kBlock;
+    const bool bulk = use_bulk && n_valid == kBlock;
+    const bool valid = lane < n_valid;
+    const long long e = e0 + lane;
+    const size_t sbase = (size_t)blk * N * kBlock + lane;
+
+    if (bulk) {
         if (lane == 0) {
-            reward[row] = r;
-            done[row] = d;
+            mbar_init(bar, 1);
+            fence_mbar_init();
+        }
+        __syncwarp();
+    }
+    for (int s = 0; s < n_steps; ++s) {
+        const size_t slab = (size_t)s * (size_t)p.n_envs;        // row offset of this step's slab
+        const real *act_g = actions + (slab + (size_t)e0) * A;
+        float *obs_g = obs_out + (slab + (size_t)e0) * D;
+        if (bulk) {
+            if (lane == 0) {
+                if (s > 0) bulk_wait_read<0>();                   // the previous obs store has left shared memory
+                mbar_expect_tx(bar, act_bytes);
+                bulk_g2s(act_s, act_g, act_bytes, bar);
+            }
+            __syncwarp();
+        } else {
+            for (int k = lane; k < n_valid * A; k += 32) act_s[k] = act_g[k];
+            __syncwarp();
+        }
+        if (valid) {
+            env_step<real, NCT, EXACT>(p, e, sbase, act_s + lane * A, obs_s + lane * D, reward + slab, done + slab,
+                                       [&]() { if (bulk) mbar_wait(bar, (uint32_t)(s & 1)); });
+        }
+        if (bulk) {
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+                bulk_s2g(obs_g, obs_s, obs_bytes);
+                bulk_commit();
+            }
+        } else {
+            __syncwarp();
+            for (int k = lane; k < n_valid * D; k += 32) obs_g[k] = obs_s[k];
+            __syncwarp();
         }
     }
-    if (lane == 0) {
-        p.envst[e] = es;
-        if (err_all && p.err) atomicOr(p.err + e, err_all);
-    }
+    if (bulk && lane == 0) bulk_wait_read<0>();   // shared memory must stay valid until the store has read it
 }
 
-template <typename real, int L>
+template <typename real>
 __global__ void __launch_bounds__(256) reset_kernel(const Params<real> p, const uint8_t *mask, int init,
                                                    int new_episode, int reset_battery)
 {
-    const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long e = gtid / L;
-    const int lane = (int)(gtid % L);
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= p.n_envs) return;
     if (mask && !mask[e]) return;
     EnvSt<real> es = p.envst[e];
@@ -121,48 +137,42 @@ __global__ void __launch_bounds__(256) reset_kernel(const Params<real> p, const 
         episode = (episode + 1u) & 0xFFFFFFu;
     }
     if (init || reset_battery) soc_b = p.batt ? p.b_soc0 : (real)0;
-    if (p.mode == MODE_SAMPLE) shift = sample_pv_shift(p, p.gid0 + (unsigned long long)e, episode);
-    begin_episode<real, L>(p, global_tables(p), e, lane, episode, shift, soc_b, p.soc + (size_t)e * p.N,
-                           p.rec + (size_t)e * p.N, p.obs + (size_t)e * p.D);
-    if (lane == 0) {
-        es.soc_b = soc_b;
-        es.pv_shift = shift;
-        es.ep_ret = 0;
-        es.t_ep = episode << 8;
-        p.envst[e] = es;
-        if (init && p.err) p.err[e] = 0;
-    }
+    if (p.mode == MODE_SAMPLE) shift = sample_pv_shift(p, p.N, p.gid0 + (unsigned long long)e, episode);
+    const size_t sbase = (size_t)(e / kBlock) * p.N * kBlock + (size_t)(e % kBlock);
+    begin_episode(p, p.N, e, sbase, episode, shift, soc_b, p.obs + (size_t)e * p.D);
+    es.soc_b = soc_b;
+    es.pv_shift = shift;
+    es.ep_ret = 0;
+    es.t_ep = episode << 8;
+    p.envst[e] = es;
+    if (init && p.err) p.err[e] = 0;
 }
 
-// Whole-day schedule of the current episode, one thread per (env, spot): the reference's
-// generator loop (charging_station.py:200-255) over the same Philox trials the lazy sampler uses.
+// Whole-day schedule of the current episode, one thread per (env, spot): walks the same chain of
+// Philox blocks the in-step sampler follows (first arrival, then vehicle -> next arrival).
 template <typename real>
-__global__ void __launch_bounds__(256) sample_plan_kernel(const Params<real> p, Rec<real> *plan)
+__global__ void __launch_bounds__(256) sample_plan_kernel(const Params<real> p, PlanRec<real> *plan)
 {
     const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (gtid >= p.n_envs * p.N) return;
     const long long e = gtid / p.N;
     const int i = (int)(gtid % p.N);
     const uint32_t episode = p.envst[e].t_ep >> 8;
-    Rec<real> *pl = plan + (size_t)gtid * kMaxVehicles;
-    Rec<real> cur;
-    cur.hdr = make_hdr(kNoVehicle, 0, 0, kNoVehicle);
-    cur.soc0 = 0;
-    cur.req = 0;
+    PlanRec<real> *pl = plan + (size_t)gtid * kMaxVehicles;
     int nv = 0;
-    for (int t = 0; t < p.T; ++t) {
-        Rec<real> r = cur;
-        if (advance_spot(p, e, i, episode, t, r) && nv < kMaxVehicles) {
-            if (nv > 0) pl[nv - 1].hdr = (pl[nv - 1].hdr & 0x00FFFFFFu) | ((uint32_t)t << 24);
-            pl[nv++] = r;
-            cur = r;
-        }
+    uint32_t next = first_arrival(p, p.N, e, i, episode);
+    while (next != kNoVehicle && nv < kMaxVehicles) {
+        const Vehicle<real> v = fetch_vehicle(p, p.N, e, i, episode, (int)next);
+        PlanRec<real> r;
+        memset(&r, 0, sizeof(r));
+        r.hdr = v.hdr; r.soc0 = v.soc0; r.req = v.req;
+        pl[nv++] = r;
+        next = v.hdr >> 24;
     }
     for (int v = nv; v < kMaxVehicles; ++v) {
-        Rec<real> z;
+        PlanRec<real> z;
+        memset(&z, 0, sizeof(z));
         z.hdr = make_hdr(kNoVehicle, 0, 0, kNoVehicle);
-        z.soc0 = 0;
-        z.req = 0;
         pl[v] = z;
     }
 }
@@ -186,19 +196,21 @@ public:
     sng_buffers buf;
     bool bound = false, started = false;
     int device = 0;
-    int lanes = 0;  // 0 = auto
-    int tile = 0, bulk = 1;
-    int in_stages = 0, out_stages = 0, ctas_per_sm = 0;  // 0 = auto
+    int warps_per_cta = 0;   // 0 = auto
+    int use_generic = 0, use_bulk = 1, host_chunks = 0;
     int num_sms = 148;
     size_t smem_optin = 0;
     void *d_tables = nullptr;
     uint32_t *d_flag = nullptr;
+    cudaStream_t copy_in = nullptr, copy_out = nullptr;      // sng_step_host pipeline
+    std::vector<cudaEvent_t> ev_in, ev_step;
 
     int init(const sng_config &c, int dev)
     {
         cfg = c;
         device = dev;
-        if (c.n_spots < 1 || c.n_spots > SNG_MAX_SPOTS || c.n_steps < 1 || c.n_steps > 250 || c.n_envs < 1 ||
+        if (c.n_spots < 1 || c.n_spots > SNG_MAX_SPOTS || c.n_steps < 1 || c.n_envs < 1 ||
+            c.n_steps + (int)(4.0 / c.dt) > 250 ||
             c.table_len < c.n_steps + c.horizon || c.table_len > SNG_MAX_TABLE || !c.price || !c.price_norm ||
             (c.pv && (!c.pv_power || !c.irr_norm)) || c.penalty_mode < 0 || c.penalty_mode > 3 || c.horizon < 0) {
             error = "sng_create: invalid configuration";
@@ -226,12 +238,14 @@ public:
         p.off_soc = nd; p.off_dep = nd + p.N; p.off_batt = nd + 2 * p.N;
         p.D = nd + 2 * p.N + p.batt;
         p.pen_mode = c.penalty_mode; p.diff_cap = c.diff_cap != 0; p.req_soc = c.req_soc != 0;
+        p.max_togo = c.penalty_mode == PEN_DENSE ? (1 << 20) : (c.penalty_mode == PEN_SPARSE ? 3 : (c.penalty_mode == PEN_ON_DEPARTURE ? 1 : 0));
         p.default_cap = c.default_cap; p.auto_reset = c.auto_reset != 0; p.mode = MODE_SAMPLE;
         p.i4 = (int)(4.0 / c.dt); p.i10 = (int)(10.0 / c.dt); p.i1 = (int)(1.0 / c.dt);
         p.dt = (real)c.dt; p.ev_pmax = (real)c.ev_pmax; p.ev_eff = (real)c.ev_eff;
         p.b_cap = (real)c.b_cap; p.b_pmax = (real)c.b_pmax; p.b_eff = (real)c.b_eff; p.b_dod = (real)c.b_dod;
         p.b_soc0 = (real)c.b_soc0; p.sell = (real)c.sell_coeff; p.cost_w = (real)c.cost_weight;
         p.batt_w = (real)c.batt_pen_w; p.margin = (real)c.margin;
+        if (c.default_cap < 1 || c.default_cap > 255) { error = "sng_create: default_cap must be in 1..255"; return SNG_ERR_ARG; }
         // shared tables: 4 x table_len reals + the departure-normalisation table
         const int n = c.table_len;
         std::vector<real> h(4 * (size_t)n, (real)0);
@@ -258,47 +272,26 @@ public:
     {
         if (d_tables) cudaFree(d_tables);
         if (d_flag) cudaFree(d_flag);
+        for (auto e : ev_in) cudaEventDestroy(e);
+        for (auto e : ev_step) cudaEventDestroy(e);
+        if (copy_in) cudaStreamDestroy(copy_in);
+        if (copy_out) cudaStreamDestroy(copy_out);
     }
 
     int bind(const sng_buffers *b) override
     {
         if (!b || b->struct_size != sizeof(sng_buffers)) { error = "sng_bind: bad struct_size"; return SNG_ERR_ARG; }
-        if (!b->actions || !b->obs || !b->reward || !b->done || !b->soc || !b->rec || !b->envst) {
-            error = "sng_bind: actions, obs, reward, done, soc, rec and envst are required";
+        if (!b->actions || !b->obs || !b->reward || !b->done || !b->soc || !b->hdr || !b->req || !b->envst) {
+            error = "sng_bind: actions, obs, reward, done, soc, hdr, req and envst are required";
             return SNG_ERR_ARG;
         }
         buf = *b;
         p.actions = (const real *)b->actions; p.obs = b->obs; p.reward = (real *)b->reward; p.done = b->done;
-        p.tobs = b->terminal_obs; p.soc = (real *)b->soc; p.rec = (Rec<real> *)b->rec;
-        p.envst = (EnvSt<real> *)b->envst; p.plan = (const Rec<real> *)b->plan; p.err = b->err;
+        p.tobs = b->terminal_obs; p.soc = (real *)b->soc; p.hdr = b->hdr; p.req = (real *)b->req;
+        p.envst = (EnvSt<real> *)b->envst; p.plan = (const PlanRec<real> *)b->plan; p.err = b->err;
         p.diag = (real *)b->diag; p.last_ret = (real *)b->last_return;
         bound = true;
         return SNG_OK;
-    }
-
-    int auto_lanes() const
-    {
-        if (EXACT) return 1;
-        if (lanes > 0) return lanes;
-        int l = 1;
-        while (l < p.N && l < 32) l <<= 1;  // one (sub-)warp per env, spots on lanes
-        return l;
-    }
-
-    template <typename F> int dispatch_lanes(F &&f)
-    {
-        if constexpr (EXACT) {
-            return f(std::integral_constant<int, 1>());
-        } else {
-            switch (auto_lanes()) {
-            case 1: return f(std::integral_constant<int, 1>());
-            case 2: return f(std::integral_constant<int, 2>());
-            case 4: return f(std::integral_constant<int, 4>());
-            case 8: return f(std::integral_constant<int, 8>());
-            case 16: return f(std::integral_constant<int, 16>());
-            default: return f(std::integral_constant<int, 32>());
-            }
-        }
     }
 
     static unsigned grid_for(long long threads) { return (unsigned)((threads + 255) / 256); }
@@ -312,13 +305,10 @@ public:
 
     int launch_reset(const uint8_t *mask, int init, int new_episode, int reset_battery, cudaStream_t st)
     {
-        return dispatch_lanes([&](auto lc) -> int {
-            constexpr int L = decltype(lc)::value;
-            reset_kernel<real, L><<<grid_for(p.n_envs * L), 256, 0, st>>>(p, mask, init, new_episode, reset_battery);
-            ++launches;
-            SNG_CUDA(cudaGetLastError());
-            return (int)SNG_OK;
-        });
+        reset_kernel<real><<<grid_for(p.n_envs), 256, 0, st>>>(p, mask, init, new_episode, reset_battery);
+        ++launches;
+        SNG_CUDA(cudaGetLastError());
+        return SNG_OK;
     }
 
     int reset(uint64_t seed, const uint8_t *mask, int reset_battery, cudaStream_t st) override
@@ -349,7 +339,7 @@ public:
         SNG_CUDA(cudaSetDevice(device));
         const long long E = p.n_envs;
         const int N = p.N, V = v->n_slots;
-        std::vector<Rec<real>> plan((size_t)E * N * kMaxVehicles);
+        std::vector<PlanRec<real>> plan((size_t)E * N * kMaxVehicles);
         for (long long e = 0; e < E; ++e)
             for (int i = 0; i < N; ++i) {
                 const size_t sp = (size_t)e * N + i;
@@ -357,9 +347,9 @@ public:
                 if (nv < 0 || nv > V) { error = "sng_load_schedule: n_veh out of range"; return SNG_ERR_ARG; }
                 int prev_dep = -1;
                 for (int k = 0; k < kMaxVehicles; ++k) {
-                    Rec<real> r;
+                    PlanRec<real> r;
                     memset(&r, 0, sizeof(r));
-                    r.hdr = make_hdr_host(kNoVehicle, 0, 0, kNoVehicle);
+                    r.hdr = make_hdr(kNoVehicle, 0, 0, kNoVehicle);
                     if (k < nv) {
                         const size_t q = sp * V + k;
                         const int a = v->arr[q], d = v->dep[q], c = v->cap[q];
@@ -370,14 +360,14 @@ public:
                         }
                         prev_dep = d;
                         const uint32_t nxt = (k + 1 < nv) ? (uint32_t)v->arr[q + 1] : kNoVehicle;
-                        r.hdr = make_hdr_host((uint32_t)a, (uint32_t)d, (uint32_t)c, nxt);
+                        r.hdr = make_hdr((uint32_t)a, (uint32_t)d, (uint32_t)c, nxt);
                         r.soc0 = (real)v->soc0[q];
                         r.req = (real)v->req[q];
                     }
                     plan[sp * kMaxVehicles + k] = r;
                 }
             }
-        SNG_CUDA(cudaMemcpyAsync(buf.plan, plan.data(), plan.size() * sizeof(Rec<real>), cudaMemcpyHostToDevice, st));
+        SNG_CUDA(cudaMemcpyAsync(buf.plan, plan.data(), plan.size() * sizeof(PlanRec<real>), cudaMemcpyHostToDevice, st));
         if (!started || v->pv_shift || v->soc_b) {
             std::vector<EnvSt<real>> es((size_t)E);
             if (started) {
@@ -402,102 +392,65 @@ public:
         return rc;
     }
 
-    static uint32_t make_hdr_host(uint32_t arr, uint32_t dep, uint32_t cap, uint32_t next)
-    {
-        return arr | (dep << 8) | (cap << 16) | (next << 24);
-    }
-
-    // Parameters with every per-env pointer advanced by e0 envs (tail of a tiled launch).
-    Params<real> offset_params(long long e0) const
-    {
-        Params<real> q = p;
-        q.n_envs = p.n_envs - e0;
-        q.gid0 = p.gid0 + (unsigned long long)e0;
-        q.actions += (size_t)e0 * p.A; q.obs += (size_t)e0 * p.D; q.reward += e0; q.done += e0;
-        if (q.tobs) q.tobs += (size_t)e0 * p.D;
-        q.soc += (size_t)e0 * p.N; q.rec += (size_t)e0 * p.N; q.envst += e0;
-        if (q.plan) q.plan += (size_t)e0 * p.N * kMaxVehicles;
-        if (q.err) q.err += e0;
-        if (q.diag) q.diag += (size_t)e0 * D_COUNT;
-        if (q.last_ret) q.last_ret += e0;
-        return q;
-    }
-
-    int launch_direct(const Params<real> &q, cudaStream_t st)
-    {
-        return dispatch_lanes([&](auto lc) -> int {
-            constexpr int L = decltype(lc)::value;
-            step_direct_kernel<real, L, EXACT><<<grid_for(q.n_envs * L), 256, 0, st>>>(q);
-            ++launches;
-            SNG_CUDA(cudaGetLastError());
-            return (int)SNG_OK;
-        });
-    }
-
     static bool aligned16(const void *q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; }
 
-    template <int L, int OS> int launch_tiled(int epb, int num_tiles, int is, cudaStream_t st)
+    // Launch geometry of step_kernel: warps per CTA so that a CTA's shared memory fits, and the
+    // dynamic shared memory size.
+    int geometry(int &wpb, size_t &smem) const
     {
-        auto kern = step_tiled_kernel<real, L, OS>;
-        const TileLayout lay = make_tile_layout<real>(epb, p.N, p.A, p.D, cfg.table_len, is, OS);
-        SNG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total));
-        int per_sm = 0;
-        SNG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, epb * L, lay.total));
-        if (per_sm < 1) { error = "tiled kernel does not fit on an SM"; return SNG_ERR_CUDA; }
-        if (ctas_per_sm > 0 && per_sm > ctas_per_sm) per_sm = ctas_per_sm;
-        long long grid = (long long)num_sms * per_sm;
-        if (grid > num_tiles) grid = num_tiles;
-        kern<<<(unsigned)grid, epb * L, lay.total, st>>>(p, epb, num_tiles, is, cfg.table_len);
+        const size_t per_warp = align128((uint32_t)(kBlock * p.A * sizeof(real))) + align128((uint32_t)(kBlock * p.D * sizeof(float)));
+        wpb = warps_per_cta > 0 ? warps_per_cta : 4;
+        while (wpb > 1 && (size_t)wpb * (per_warp + 8) > smem_optin) wpb >>= 1;
+        smem = (size_t)wpb * (per_warp + 8);
+        return smem <= smem_optin ? SNG_OK : SNG_ERR_UNSUPPORTED;
+    }
+
+    template <int NCT>
+    int launch_step_n(const Params<real> &q, const real *actions, float *obs, real *reward, uint8_t *done, int n_steps,
+                      int bulk, cudaStream_t st)
+    {
+        int wpb;
+        size_t smem;
+        if (geometry(wpb, smem) != SNG_OK) { error = "step kernel: one warp's action/observation rows do not fit in shared memory"; return SNG_ERR_UNSUPPORTED; }
+        auto kern = step_kernel<real, NCT, EXACT>;
+        SNG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const long long blocks = (q.n_envs + kBlock - 1) / kBlock;
+        const unsigned grid = (unsigned)((blocks + wpb - 1) / wpb);
+        kern<<<grid, wpb * 32, smem, st>>>(q, actions, obs, reward, done, n_steps, bulk);
         ++launches;
         SNG_CUDA(cudaGetLastError());
         return SNG_OK;
     }
 
-    // Tile geometry of the bulk-copy path; returns false when the direct kernel must be used.
-    bool plan_tiles(int &L, int &epb, int &is, int &os) const
+    // q: parameters (possibly of a slice of envs starting at a multiple of 32)
+    int launch_step(const Params<real> &q, const real *actions, float *obs, real *reward, uint8_t *done, int n_steps,
+                    cudaStream_t st)
     {
-        if (EXACT || !bulk) return false;
-        if (!aligned16(p.actions) || !aligned16(p.obs) || !aligned16(p.reward) || !aligned16(p.done) ||
-            !aligned16(p.soc) || !aligned16(p.rec) || !aligned16(p.envst))
-            return false;
-        L = lanes > 0 ? lanes : 1;
-        epb = tile > 0 ? tile : (L == 1 ? 128 : (L <= 4 ? 64 : (L <= 16 ? 32 : 16)));
-        if (epb % 16 != 0 || epb * L > 1024 || epb * L < 32) return false;
-        if (p.n_envs < epb) return false;
-        os = out_stages > 0 ? out_stages : 1;
-        if (os > 2) os = 2;
-        is = in_stages > 0 ? in_stages : 2;
-        while (is > 1 && make_tile_layout<real>(epb, p.N, p.A, p.D, cfg.table_len, is, os).total > smem_optin) --is;
-        return make_tile_layout<real>(epb, p.N, p.A, p.D, cfg.table_len, is, os).total <= smem_optin;
+        // the copy engine needs 16-byte aligned row slabs: bases aligned and, for rollouts, slab strides too
+        int bulk = use_bulk && aligned16(actions) && aligned16(obs);
+        if (n_steps > 1 && (((size_t)q.n_envs * q.A * sizeof(real)) % 16 != 0 || ((size_t)q.n_envs * q.D * sizeof(float)) % 16 != 0))
+            bulk = 0;
+        if constexpr (EXACT) {
+            return launch_step_n<0>(q, actions, obs, reward, done, n_steps, bulk, st);
+        } else {
+            if (!use_generic) {
+                switch (q.N) {
+                case 4: return launch_step_n<4>(q, actions, obs, reward, done, n_steps, bulk, st);
+                case 8: return launch_step_n<8>(q, actions, obs, reward, done, n_steps, bulk, st);
+                case 10: return launch_step_n<10>(q, actions, obs, reward, done, n_steps, bulk, st);
+                case 64: return launch_step_n<64>(q, actions, obs, reward, done, n_steps, bulk, st);
+                default: break;
+                }
+            }
+            return launch_step_n<0>(q, actions, obs, reward, done, n_steps, bulk, st);
+        }
     }
 
     int step(cudaStream_t st) override
     {
         int rc = check_ready(true);
         if (rc) return rc;
-        if constexpr (!EXACT) {
-            int L, epb, is, os;
-            if (plan_tiles(L, epb, is, os)) {
-                const int num_tiles = (int)(p.n_envs / epb);
-                auto go = [&](auto lc) -> int {
-                    constexpr int LL = decltype(lc)::value;
-                    return os == 2 ? launch_tiled<LL, 2>(epb, num_tiles, is, st) : launch_tiled<LL, 1>(epb, num_tiles, is, st);
-                };
-                switch (L) {
-                case 1: rc = go(std::integral_constant<int, 1>()); break;
-                case 2: rc = go(std::integral_constant<int, 2>()); break;
-                case 4: rc = go(std::integral_constant<int, 4>()); break;
-                case 8: rc = go(std::integral_constant<int, 8>()); break;
-                case 16: rc = go(std::integral_constant<int, 16>()); break;
-                default: rc = go(std::integral_constant<int, 32>()); break;
-                }
-                if (rc) return rc;
-                const long long done_envs = (long long)num_tiles * epb;
-                if (done_envs < p.n_envs) return launch_direct(offset_params(done_envs), st);
-                return SNG_OK;
-            }
-        }
-        return launch_direct(p, st);
+        return launch_step(p, p.actions, p.obs, p.reward, p.done, 1, st);
     }
 
     int rollout(const void *actions, float *obs, void *reward, uint8_t *done, int n_steps, cudaStream_t st) override
@@ -506,28 +459,81 @@ public:
         if (rc) return rc;
         if (!actions) { error = "sng_rollout: in-kernel random actions are not implemented yet"; return SNG_ERR_UNSUPPORTED; }
         if (!obs || !reward || !done || n_steps < 1) { error = "sng_rollout: bad arguments"; return SNG_ERR_ARG; }
-        return dispatch_lanes([&](auto lc) -> int {
-            constexpr int L = decltype(lc)::value;
-            rollout_direct_kernel<real, L, EXACT><<<grid_for(p.n_envs * L), 256, 0, st>>>(
-                p, (const real *)actions, obs, (real *)reward, done, n_steps);
-            ++launches;
-            SNG_CUDA(cudaGetLastError());
-            return (int)SNG_OK;
-        });
+        return launch_step(p, (const real *)actions, obs, (real *)reward, done, n_steps, st);
     }
 
+    // Parameters with every per-env pointer advanced by e0 envs (e0 a multiple of 32).
+    Params<real> slice_params(long long e0, long long n) const
+    {
+        Params<real> q = p;
+        q.n_envs = n;
+        q.gid0 = p.gid0 + (unsigned long long)e0;
+        q.actions += (size_t)e0 * p.A; q.obs += (size_t)e0 * p.D; q.reward += e0; q.done += e0;
+        if (q.tobs) q.tobs += (size_t)e0 * p.D;
+        q.soc += (size_t)e0 * p.N; q.hdr += (size_t)e0 * p.N; q.req += (size_t)e0 * p.N; q.envst += e0;
+        if (q.plan) q.plan += (size_t)e0 * p.N * kMaxVehicles;
+        if (q.err) q.err += e0;
+        if (q.diag) q.diag += (size_t)e0 * D_COUNT;
+        if (q.last_ret) q.last_ret += e0;
+        return q;
+    }
+
+    // The gym-facing call with host buffers.  The batch is cut into chunks of envs that flow through
+    // a three-stage pipeline on three streams (H2D actions | step kernel | D2H obs/reward/done), so the
+    // two PCIe directions and the kernel overlap; with one chunk it degenerates to copy-step-copy.
     int step_host(const void *a, float *obs, void *rew, uint8_t *done, cudaStream_t st) override
     {
         int rc = check_ready(true);
         if (rc) return rc;
         if (!a || !obs || !rew || !done) { error = "sng_step_host: null host buffer"; return SNG_ERR_ARG; }
-        const size_t E = (size_t)p.n_envs;
-        SNG_CUDA(cudaMemcpyAsync((void *)buf.actions, a, E * p.A * sizeof(real), cudaMemcpyHostToDevice, st));
-        rc = step(st);
-        if (rc) return rc;
-        SNG_CUDA(cudaMemcpyAsync(obs, buf.obs, E * p.D * sizeof(float), cudaMemcpyDeviceToHost, st));
-        SNG_CUDA(cudaMemcpyAsync(rew, buf.reward, E * sizeof(real), cudaMemcpyDeviceToHost, st));
-        SNG_CUDA(cudaMemcpyAsync(done, buf.done, E, cudaMemcpyDeviceToHost, st));
+        const long long E = p.n_envs;
+        int chunks = host_chunks > 0 ? host_chunks : (E >= (1 << 16) ? 8 : 1);
+        long long per = ((E + chunks - 1) / chunks + 1023) / 1024 * 1024;      // multiple of 32 (and of the TMA slab alignment)
+        if (per >= E) { chunks = 1; per = E; }
+        chunks = (int)((E + per - 1) / per);
+        if (chunks == 1) {
+            SNG_CUDA(cudaMemcpyAsync((void *)buf.actions, a, (size_t)E * p.A * sizeof(real), cudaMemcpyHostToDevice, st));
+            rc = step(st);
+            if (rc) return rc;
+            SNG_CUDA(cudaMemcpyAsync(obs, buf.obs, (size_t)E * p.D * sizeof(float), cudaMemcpyDeviceToHost, st));
+            SNG_CUDA(cudaMemcpyAsync(rew, buf.reward, (size_t)E * sizeof(real), cudaMemcpyDeviceToHost, st));
+            SNG_CUDA(cudaMemcpyAsync(done, buf.done, (size_t)E, cudaMemcpyDeviceToHost, st));
+            SNG_CUDA(cudaStreamSynchronize(st));
+            return SNG_OK;
+        }
+        if (!copy_in) {
+            SNG_CUDA(cudaStreamCreateWithFlags(&copy_in, cudaStreamNonBlocking));
+            SNG_CUDA(cudaStreamCreateWithFlags(&copy_out, cudaStreamNonBlocking));
+        }
+        while ((int)ev_in.size() < chunks) {
+            cudaEvent_t e1, e2;
+            SNG_CUDA(cudaEventCreateWithFlags(&e1, cudaEventDisableTiming));
+            SNG_CUDA(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming));
+            ev_in.push_back(e1);
+            ev_step.push_back(e2);
+        }
+        // the copy streams start after whatever the caller queued on `st`
+        cudaEvent_t ev0 = ev_in[0];
+        SNG_CUDA(cudaEventRecord(ev0, st));
+        SNG_CUDA(cudaStreamWaitEvent(copy_in, ev0, 0));
+        SNG_CUDA(cudaStreamWaitEvent(copy_out, ev0, 0));
+        for (int c = 0; c < chunks; ++c) {
+            const long long e0 = (long long)c * per, n = (e0 + per <= E) ? per : E - e0;
+            SNG_CUDA(cudaMemcpyAsync((char *)buf.actions + (size_t)e0 * p.A * sizeof(real), (const char *)a + (size_t)e0 * p.A * sizeof(real),
+                                     (size_t)n * p.A * sizeof(real), cudaMemcpyHostToDevice, copy_in));
+            SNG_CUDA(cudaEventRecord(ev_in[c], copy_in));
+            SNG_CUDA(cudaStreamWaitEvent(st, ev_in[c], 0));
+            const Params<real> q = slice_params(e0, n);
+            rc = launch_step(q, q.actions, q.obs, q.reward, q.done, 1, st);
+            if (rc) return rc;
+            SNG_CUDA(cudaEventRecord(ev_step[c], st));
+            SNG_CUDA(cudaStreamWaitEvent(copy_out, ev_step[c], 0));
+            SNG_CUDA(cudaMemcpyAsync(obs + (size_t)e0 * p.D, buf.obs + (size_t)e0 * p.D, (size_t)n * p.D * sizeof(float), cudaMemcpyDeviceToHost, copy_out));
+            SNG_CUDA(cudaMemcpyAsync((char *)rew + (size_t)e0 * sizeof(real), (char *)buf.reward + (size_t)e0 * sizeof(real), (size_t)n * sizeof(real),
+                                     cudaMemcpyDeviceToHost, copy_out));
+            SNG_CUDA(cudaMemcpyAsync(done + e0, buf.done + e0, (size_t)n, cudaMemcpyDeviceToHost, copy_out));
+        }
+        SNG_CUDA(cudaStreamSynchronize(copy_out));
         SNG_CUDA(cudaStreamSynchronize(st));
         return SNG_OK;
     }
@@ -538,7 +544,7 @@ public:
         if (rc) return rc;
         if (!buf.plan) { error = "sng_sample_plan: no `plan` buffer bound"; return SNG_ERR_STATE; }
         if (p.mode != MODE_SAMPLE) { error = "sng_sample_plan: handle is in replay mode"; return SNG_ERR_STATE; }
-        sample_plan_kernel<real><<<grid_for(p.n_envs * p.N), 256, 0, st>>>(p, (Rec<real> *)buf.plan);
+        sample_plan_kernel<real><<<grid_for(p.n_envs * p.N), 256, 0, st>>>(p, (PlanRec<real> *)buf.plan);
         ++launches;
         SNG_CUDA(cudaGetLastError());
         return SNG_OK;
@@ -559,20 +565,14 @@ public:
         return SNG_OK;
     }
 
-    int set_tuning(int l, int t, int b) override
+    int set_tuning(int w, int g, int b, int hc) override
     {
-        if (l != 0 && l != 1 && l != 2 && l != 4 && l != 8 && l != 16 && l != 32) {
-            error = "sng_set_tuning: lanes_per_env must be 0 or a power of two <= 32";
+        if (w != 0 && w != 1 && w != 2 && w != 4 && w != 8) {
+            error = "sng_set_tuning: warps_per_cta must be 0, 1, 2, 4 or 8";
             return SNG_ERR_ARG;
         }
-        lanes = l; tile = t; bulk = b;
-        return SNG_OK;
-    }
-
-    int set_pipeline(int is, int os, int cps) override
-    {
-        if (is < 0 || is > 8 || os < 0 || os > 2 || cps < 0) { error = "sng_set_pipeline: bad arguments"; return SNG_ERR_ARG; }
-        in_stages = is; out_stages = os; ctas_per_sm = cps;
+        if (hc < 0 || hc > 64) { error = "sng_set_tuning: host_chunks must be in 0..64"; return SNG_ERR_ARG; }
+        warps_per_cta = w; use_generic = g; use_bulk = b; host_chunks = hc;
         return SNG_OK;
     }
 };

@@ -220,64 +220,47 @@ def test_sampler_matches_cpu_mirror_bit_exact():
 # ------------------------------------------------------------------------------------------
 # structural properties of the CUDA path
 # ------------------------------------------------------------------------------------------
-def test_lane_mappings_agree():
-    """Any lanes-per-env mapping computes the same step (sums differ only in association order)."""
-    outs = []
-    for lanes in (1, 2, 4, 8, 16, 32):
-        env = _env(1000, "float32", number_of_chargers=10, seed=3)
-        env.set_tuning(lanes_per_env=lanes)
-        env.reset()
-        g = torch.Generator(device="cuda:0").manual_seed(0)
-        acc = []
-        for _ in range(30):
-            o, r, d, _, _ = env.step(env.sample_actions(g))
-            acc.append((o.cpu().numpy().copy(), r.cpu().numpy().copy(), d.cpu().numpy().copy()))
-        outs.append(acc)
-        env.close()
-    for acc in outs[1:]:
-        for (o, r, d), (o0, r0, d0) in zip(acc, outs[0]):
-            assert np.array_equal(d, d0)
-            assert np.allclose(o, o0, rtol=1e-6, atol=1e-6) and np.allclose(r, r0, rtol=1e-5, atol=1e-5)
-
-
-@pytest.mark.parametrize("kw,lanes,tile", [
-    (dict(number_of_chargers=10), 1, 128), (dict(number_of_chargers=10), 1, 256), (dict(number_of_chargers=10), 16, 32),
-    (dict(number_of_chargers=4, vehicle_to_everything=True, vehicle_uncharged_penalty_mode="dense"), 4, 64),
-    (dict(number_of_chargers=64, time_interval="15min"), 32, 16), (dict(number_of_chargers=64, time_interval="15min"), 1, 32),
-    (dict(number_of_chargers=7, battery_system_available_in_model=False, pv_system_available_in_model=False), 1, 128),
+@pytest.mark.parametrize("kw", [
+    dict(number_of_chargers=10),
+    dict(number_of_chargers=4, vehicle_to_everything=True, vehicle_uncharged_penalty_mode="dense"),
+    dict(number_of_chargers=64, time_interval="15min", enable_requested_state_of_charge=True),
+    dict(number_of_chargers=8, battery_system_available_in_model=False, pv_system_available_in_model=False),
+    dict(number_of_chargers=7),
 ])
-def test_bulk_copy_kernel_is_bit_identical_to_direct_kernel(kw, lanes, tile):
-    """The TMA-staged kernel and the direct-global kernel run the same body: with the same lane mapping
-    their outputs are bit-identical, including the ragged tail (E not a multiple of the tile)."""
-    E = 5 * 256 + 104
+def test_kernel_variants_are_bit_identical(kw):
+    """The specialised (compile-time N) and the generic kernel, the copy-engine and the plain-load staging
+    of action / observation rows, and every CTA shape run the same per-env body: outputs and state are
+    bit-identical, including the ragged last block (E not a multiple of 32)."""
+    E = 5 * 256 + 104 + 13
+    variants = [dict(), dict(use_generic_kernel=1), dict(use_bulk_copy=0), dict(warps_per_cta=1),
+                dict(warps_per_cta=8, use_generic_kernel=1, use_bulk_copy=0)]
     envs = []
-    for bulk, stages in ((1, (2, 1)), (1, (3, 2)), (0, (0, 0))):
+    for v in variants:
         env = _env(E, "float32", seed=21, **kw)
-        env.set_tuning(lanes_per_env=lanes, envs_per_tile=tile, use_bulk_copy=bulk)
-        env.set_pipeline(stages[0], stages[1], 0)
+        env.set_tuning(**v)
         env.reset()
         envs.append(env)
     g = torch.Generator(device="cuda:0").manual_seed(3)
     for s in range(envs[0].cfg.n_steps + 9):
         a = envs[0].sample_actions(g)
         outs = [e.step(a) for e in envs]
-        for o in outs[1:]:
+        for e, o in zip(envs[1:], outs[1:]):
             assert torch.equal(o[0], outs[0][0]) and torch.equal(o[1], outs[0][1]) and torch.equal(o[2], outs[0][2]), s
-        assert torch.equal(envs[0].soc, envs[2].soc) and torch.equal(envs[0]._rec, envs[2]._rec)
-        assert torch.equal(envs[0]._envst, envs[2]._envst) and torch.equal(envs[0].terminal_obs, envs[2].terminal_obs)
-        assert torch.equal(envs[0].diag, envs[2].diag)
+            assert torch.equal(envs[0]._soc, e._soc) and torch.equal(envs[0]._hdr, e._hdr) and torch.equal(envs[0]._req, e._req)
+            assert torch.equal(envs[0]._envst, e._envst) and torch.equal(envs[0].terminal_obs, e.terminal_obs)
+            assert torch.equal(envs[0].diag, e.diag)
     for e in envs:
         assert e.error_flags() == 0
         e.close()
 
 
 def test_rollout_equals_repeated_step_and_step_host():
-    E, n = 777, 30
+    E, n = 2777, 30
     env_a = _env(E, "float32", number_of_chargers=10, seed=11)
     env_b = _env(E, "float32", number_of_chargers=10, seed=11)
     env_c = _env(E, "float32", number_of_chargers=10, seed=11)
+    env_c.set_tuning(host_chunks=3)    # pipelined host path: chunks of envs, ragged last chunk
     for e in (env_a, env_b, env_c):
-        e.set_tuning(lanes_per_env=16, use_bulk_copy=0)    # same lane mapping => bit-identical sums
         e.reset()
     g = torch.Generator(device="cuda:0").manual_seed(1)
     actions = torch.stack([env_a.sample_actions(g) for _ in range(n)])
