@@ -89,13 +89,17 @@ typedef struct {
     int32_t envst_bytes;    /* one per-env scalar block (16 or 32) */
     int32_t plan_slots;     /* SNG_MAX_VEHICLES */
     int32_t diag_count;     /* reals per env in the optional diagnostics row */
-    int32_t env_block;      /* 32: per-spot state arrays are blocked [ceil(E/32)][n_spots][32] (see sng_buffers) */
+    int32_t env_block;      /* 32: the per-spot state array is blocked by 32 envs (see sng_buffers.spot) */
+    int32_t spot_planes;    /* 3: planes of the per-spot state (header word, requested SoC, SoC) */
 } sng_layout;
 
 /* Device buffers.  `real` = float (SNG_F32) or double (SNG_F64).  Optional pointers may be NULL.
- * Per-spot state (soc, hdr, req) is a structure of arrays blocked by env_block = 32 envs: element
- * (env e, spot i) lives at index (e / 32) * n_spots * 32 + i * 32 + e % 32, so the caller allocates
- * ceil(E / 32) * n_spots * 32 elements per array.  Contents are opaque between calls. */
+ * The per-spot state `spot` is ONE array of real-sized words, a structure of arrays blocked by
+ * env_block = 32 envs: word (env e, spot i, plane f) lives at index
+ *     (((e / 32) * n_spots + i) * 3 + f) * 32 + e % 32
+ * with plane 0 = header word (arrival | departure << 8 | capacity << 16 | next arrival << 24, zero
+ * extended), plane 1 = requested SoC, plane 2 = SoC column the next step starts from (both `real`
+ * bit patterns).  The caller allocates ceil(E / 32) * n_spots * 3 * 32 words of real_bytes bytes. */
 typedef struct {
     uint32_t struct_size;
     uint32_t _pad;
@@ -104,9 +108,7 @@ typedef struct {
     void *reward;           /* out  [E] real */
     uint8_t *done;          /* out  [E] terminated flag (truncated is always 0 in the reference) */
     float *terminal_obs;    /* out, optional [E][obs_dim]: last obs of the finished episode (auto_reset) */
-    void *soc;              /* state, blocked real: SoC column the next step starts from */
-    uint32_t *hdr;          /* state, blocked u32: arrival | departure << 8 | capacity << 16 | next arrival << 24 */
-    void *req;              /* state, blocked real: requested SoC of the current vehicle */
+    void *spot;             /* state, blocked words (see above) */
     void *envst;            /* state [E] x envst_bytes: battery SoC, pv_shift, episode return, (episode, t) */
     void *plan;             /* optional [E][n_spots][SNG_MAX_VEHICLES] x plan_rec_bytes: full-day schedule */
     uint32_t *err;          /* optional [E] sticky SNG_FLAG_* bits */

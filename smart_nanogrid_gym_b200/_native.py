@@ -40,12 +40,12 @@ class SngConfig(C.Structure):
 class SngLayout(C.Structure):
     _fields_ = [("struct_size", C.c_uint32), ("act_dim", C.c_int32), ("obs_dim", C.c_int32), ("real_bytes", C.c_int32),
                 ("plan_rec_bytes", C.c_int32), ("envst_bytes", C.c_int32), ("plan_slots", C.c_int32),
-                ("diag_count", C.c_int32), ("env_block", C.c_int32)]
+                ("diag_count", C.c_int32), ("env_block", C.c_int32), ("spot_planes", C.c_int32)]
 
 
 class SngBuffers(C.Structure):
     _fields_ = [("struct_size", C.c_uint32), ("_pad", C.c_uint32)] + [(n, C.c_void_p) for n in (
-        "actions", "obs", "reward", "done", "terminal_obs", "soc", "hdr", "req", "envst", "plan", "err", "diag",
+        "actions", "obs", "reward", "done", "terminal_obs", "spot", "envst", "plan", "err", "diag",
         "last_return")]
 
 

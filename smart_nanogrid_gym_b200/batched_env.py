@@ -66,12 +66,12 @@ class BatchedSmartNanogridEnv:
         self.reward = z(E, dtype=self.real)
         self.done = z(E, dtype=torch.uint8)
         self.terminal_obs = z(E, D, dtype=torch.float32) if want_terminal_obs else None
-        # per-spot state: structure of arrays blocked by 32 envs, [ceil(E/32)][N][32] (include/sng.h)
+        # per-spot state: one array of real-sized words, a structure of arrays blocked by 32 envs:
+        # [ceil(E/32)][N][3 planes: header | requested SoC | SoC][32] (include/sng.h sng_buffers.spot)
         B = self.layout.env_block
         self._blocks = (E + B - 1) // B
-        self._soc = z(self._blocks, N, B, dtype=self.real)
-        self._hdr = z(self._blocks, N, B, dtype=torch.int32)
-        self._req = z(self._blocks, N, B, dtype=self.real)
+        self._word = torch.int32 if self.precision == nat.SNG_F32 else torch.int64
+        self._spot = z(self._blocks, N, self.layout.spot_planes, B, dtype=self._word)
         self._envst = z(E * self.layout.envst_bytes, dtype=torch.uint8)
         self._plan = None
         self.err = z(E, dtype=torch.int32)
@@ -100,8 +100,7 @@ class BatchedSmartNanogridEnv:
         b.struct_size = C.sizeof(nat.SngBuffers)
         obs, rew, done = self._bound_out
         b.actions, b.obs, b.reward, b.done = (_ptr(self._bound_actions), _ptr(obs), _ptr(rew), _ptr(done))
-        b.terminal_obs, b.soc, b.hdr, b.req = _ptr(self.terminal_obs), _ptr(self._soc), _ptr(self._hdr), _ptr(self._req)
-        b.envst = _ptr(self._envst)
+        b.terminal_obs, b.spot, b.envst = _ptr(self.terminal_obs), _ptr(self._spot), _ptr(self._envst)
         b.plan, b.err, b.diag, b.last_return = _ptr(self._plan), _ptr(self.err), _ptr(self.diag), _ptr(self.last_return)
         nat.check(self._lib.sng_bind(self._h, C.byref(b)))
 
@@ -131,22 +130,22 @@ class BatchedSmartNanogridEnv:
         """Experiment / test knobs of the step launch (include/sng.h sng_set_tuning)."""
         nat.check(self._lib.sng_set_tuning(self._h, warps_per_cta, use_generic_kernel, use_bulk_copy, host_chunks))
 
-    def _unblock(self, x):
-        """Blocked per-spot state [E/32][N][32] -> [E][N]."""
-        return x.permute(0, 2, 1).reshape(-1, self.cfg.n_spots)[:self.num_envs]
+    def _plane(self, f):
+        """Plane f of the blocked per-spot state -> a de-blocked [E, N] copy (words)."""
+        return self._spot[:, :, f, :].permute(0, 2, 1).reshape(-1, self.cfg.n_spots)[:self.num_envs].contiguous()
 
     @property
     def soc(self):
         """[E, N] SoC column the next step starts from (a de-blocked copy of the kernel state)."""
-        return self._unblock(self._soc)
+        return self._plane(2).view(self.real)
 
     def spot_state(self):
         """Decoded per-spot state as numpy arrays [E, N]: arrival, departure, capacity, next arrival
         (255 = none), requested SoC, SoC."""
-        h = self._unblock(self._hdr).cpu().numpy().astype(np.uint32)
+        h = self._plane(0).cpu().numpy().astype(np.int64)
         return dict(arr=(h & 0xFF).astype(np.int32), dep=((h >> 8) & 0xFF).astype(np.int32),
-                    cap=((h >> 16) & 0xFF).astype(np.int32), next=(h >> 24).astype(np.int32),
-                    req=self._unblock(self._req).cpu().numpy().astype(np.float64),
+                    cap=((h >> 16) & 0xFF).astype(np.int32), next=((h >> 24) & 0xFF).astype(np.int32),
+                    req=self._plane(1).view(self.real).cpu().numpy().astype(np.float64),
                     soc=self.soc.cpu().numpy().astype(np.float64))
 
     @property
@@ -310,8 +309,7 @@ class BatchedSmartNanogridEnv:
                     episode=(r["t_ep"] >> 8).astype(np.int64))
 
     def state_dict(self):
-        sd = dict(soc=self._soc.clone(), hdr=self._hdr.clone(), req=self._req.clone(), envst=self._envst.clone(),
-                  err=self.err.clone(),
+        sd = dict(spot=self._spot.clone(), envst=self._envst.clone(), err=self.err.clone(),
                   last_return=self.last_return.clone(), seed=self.seed_value, obs=self.obs.clone())
         if self._plan is not None:
             sd["plan"] = self._plan.clone()
@@ -320,9 +318,7 @@ class BatchedSmartNanogridEnv:
     def load_state_dict(self, sd):
         """Restores a state captured by state_dict() on an env that has been reset() / load_schedule()d
         in the same mode (sampling vs replay)."""
-        self._soc.copy_(sd["soc"])
-        self._hdr.copy_(sd["hdr"])
-        self._req.copy_(sd["req"])
+        self._spot.copy_(sd["spot"])
         self._envst.copy_(sd["envst"])
         self.err.copy_(sd["err"])
         self.last_return.copy_(sd["last_return"])

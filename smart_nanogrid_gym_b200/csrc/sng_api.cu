@@ -64,6 +64,7 @@ int sng_query_layout(const sng_config *cfg, sng_layout *out)
     out->plan_slots = SNG_MAX_VEHICLES;
     out->diag_count = SNG_D_COUNT;
     out->env_block = sng::kBlock;
+    out->spot_planes = sng::kPlanes;
     return SNG_OK;
 }
 

@@ -2,8 +2,9 @@
 // step body.
 //
 // Thread mapping: ONE THREAD PER ENVIRONMENT, 32 consecutive envs per warp.  Per-spot state is a
-// structure of arrays blocked by 32 envs ([E/32][N][32]), so lane l of a warp reads spot i of its env
-// from word  block*N*32 + i*32 + l : every state load / store of a warp is one full 128-byte line.
+// structure of arrays blocked by 32 envs ([E/32][N][3 planes][32]), so lane l of a warp reads plane f
+// of spot i of its env from word  ((block*N + i)*3 + f)*32 + l : every state load / store of a warp is
+// one full 128-byte line, and all of a thread's accesses are constant offsets from one base pointer.
 // Spots are walked sequentially inside the thread (no shuffles, sums in spot order, results do not
 // depend on how envs are split over GPUs).  DESIGN.md "Thread mapping" has the measurements behind
 // this choice (a warp-per-env mapping leaves 22 of 32 lanes idle at 10 spots and is issue-bound).
@@ -20,6 +21,17 @@ namespace sng {
 // State layout in HBM (DESIGN.md "Data layout")
 // ------------------------------------------------------------------------------------------
 constexpr int kBlock = 32;          // envs per state block = lanes of a warp
+constexpr int kPlanes = 3;          // per-spot state planes: header word, requested SoC, SoC
+enum : int { PL_HDR = 0, PL_REQ = 1, PL_SOC = 2 };
+
+// State words are as wide as `real` (uint32 / uint64) so that one array holds all three planes.
+template <typename real> struct WordOf;
+template <> struct WordOf<float> { typedef uint32_t type; };
+template <> struct WordOf<double> { typedef unsigned long long type; };
+__device__ __forceinline__ float word_to_real(uint32_t w, float) { return __uint_as_float(w); }
+__device__ __forceinline__ double word_to_real(unsigned long long w, double) { return __longlong_as_double((long long)w); }
+__device__ __forceinline__ uint32_t real_to_word(float x) { return __float_as_uint(x); }
+__device__ __forceinline__ unsigned long long real_to_word(double x) { return (unsigned long long)__double_as_longlong(x); }
 constexpr uint32_t kNoVehicle = 0xFFu;
 constexpr int kMaxVehicles = 8;
 constexpr int kDepTab = 256;
@@ -69,9 +81,7 @@ template <typename real> struct Params {
     real *reward;          // [E]
     uint8_t *done;         // [E]
     float *tobs;           // [E][D] or null
-    real *soc;             // [E/32][N][32] SoC column the next step starts from
-    uint32_t *hdr;         // [E/32][N][32]
-    real *req;             // [E/32][N][32] requested SoC of the current vehicle
+    typename WordOf<real>::type *spot;  // [E/32][N][3][32]: header word | requested SoC | SoC column the next step starts from
     EnvSt<real> *envst;    // [E]
     const PlanRec<real> *plan;  // [E][N][kMaxVehicles] or null
     uint32_t *err;
@@ -196,6 +206,15 @@ __device__ __forceinline__ Vehicle<real> fetch_vehicle(const Params<real> &p, in
     return v;
 }
 
+// Install vehicle `v` at the spot whose plane-0 word is *sp (planes are kBlock words apart).
+template <typename real>
+__device__ __forceinline__ void store_vehicle(typename WordOf<real>::type *sp, const Vehicle<real> &v)
+{
+    sp[PL_HDR * kBlock] = v.hdr;
+    sp[PL_REQ * kBlock] = real_to_word(v.req);
+    sp[PL_SOC * kBlock] = real_to_word(v.soc0);   // the step at `arr` starts from the arrival SoC (charger.py:62-67)
+}
+
 // numpy's pairwise float64 sum (n <= 128 branch) for the bit-faithful double build:
 // charger_power_values[mask].sum(), utils/charging_station.py:293-294.
 __device__ inline double numpy_sum(const double *a, int n)
@@ -216,36 +235,61 @@ __device__ inline double numpy_sum(const double *a, int n)
     return res;
 }
 
-// (power * dt) / capacity: IEEE division in the float64 validation build, MUFU.RCP-based fast
-// division (<= 2 ulp, capacity is an integer in 1..255) in the float32 production build.
-__device__ __forceinline__ float div_cap(float x, float cap) { return __fdividef(x, cap); }
+// (power * dt) / capacity: IEEE division in the float64 validation build; in the float32 production
+// build one MUFU.RCP (rcp.approx, <= 1 ulp; the capacity is an integer in 1..255) and a multiply.
+__device__ __forceinline__ float div_cap(float x, float cap)
+{
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(cap));
+    return x * r;
+}
 __device__ __forceinline__ double div_cap(double x, double cap) { return x / cap; }
+
+// Observation offsets: ND = number of disturbance entries = (1 + pv) * (1 + H) when known at compile
+// time (0 = read the offsets from the parameters).
+template <int NCT, int ND> struct Offsets {
+    template <typename real> static __device__ __forceinline__ int soc(const Params<real> &p) { return (NCT && ND) ? ND : p.off_soc; }
+    template <typename real> static __device__ __forceinline__ int dep(const Params<real> &p) { return (NCT && ND) ? ND + NCT : p.off_dep; }
+    template <typename real> static __device__ __forceinline__ int batt(const Params<real> &p) { return (NCT && ND) ? ND + 2 * NCT : p.off_batt; }
+};
 
 // Env-level part of the observation (envs/smart_nanogrid_environment.py:197-205,
 // central_management_system.py:53-60): disturbances now and `H` steps ahead, battery SoC.
-template <typename real>
+// ND == 8 is the reference's own shape (PV on, NUMBER_OF_HOURS_AHEAD = 3).
+template <typename real, int NCT, int ND>
 __device__ __forceinline__ void write_obs_env(const Params<real> &p, float *obs, int t, real shift, real soc_b)
 {
-    int k = 0;
-    if (p.pv) {
-        obs[k++] = (float)(__ldg(p.irr_norm + t) * shift);
-        obs[k++] = (float)__ldg(p.price_norm + t);
-        for (int j = 1; j <= p.H; ++j) obs[k++] = (float)(__ldg(p.irr_norm + t + j) * shift);
-        for (int j = 1; j <= p.H; ++j) obs[k++] = (float)__ldg(p.price_norm + t + j);
+    if (NCT && ND == 8) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) obs[j == 0 ? 0 : 1 + j] = (float)(__ldg(p.irr_norm + t + j) * shift);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) obs[j == 0 ? 1 : 4 + j] = (float)__ldg(p.price_norm + t + j);
     } else {
-        obs[k++] = (float)__ldg(p.price_norm + t);
-        for (int j = 1; j <= p.H; ++j) obs[k++] = (float)__ldg(p.price_norm + t + j);
+        int k = 0;
+        if (p.pv) {
+            obs[k++] = (float)(__ldg(p.irr_norm + t) * shift);
+            obs[k++] = (float)__ldg(p.price_norm + t);
+            for (int j = 1; j <= p.H; ++j) obs[k++] = (float)(__ldg(p.irr_norm + t + j) * shift);
+            for (int j = 1; j <= p.H; ++j) obs[k++] = (float)__ldg(p.price_norm + t + j);
+        } else {
+            obs[k++] = (float)__ldg(p.price_norm + t);
+            for (int j = 1; j <= p.H; ++j) obs[k++] = (float)__ldg(p.price_norm + t + j);
+        }
     }
-    if (p.batt) obs[p.off_batt] = (float)soc_b;
+    if (p.batt) obs[Offsets<NCT, ND>::batt(p)] = (float)soc_b;
 }
 
 // Begin an episode at t = 0 (SmartNanogridEnv.reset, envs/smart_nanogrid_environment.py:311-351):
 // per spot, schedule the first arrival of the day (and admit it when it is at step 0), clear the SoC
 // state (clear_initialisation_variables, charging_station.py:138-150) and write the reset observation.
-template <typename real>
-__device__ __forceinline__ void begin_episode(const Params<real> &p, int N, long long e, size_t sbase, uint32_t episode,
-                                              real shift, real soc_b, float *obs)
+// `spot` points at (this env, spot 0, plane 0); dep_tab is the departure-normalisation table.
+template <typename real, int NCT, int ND>
+__device__ __forceinline__ void begin_episode(const Params<real> &p, int N, long long e,
+                                              typename WordOf<real>::type *spot, uint32_t episode, real shift,
+                                              real soc_b, float *obs, const float *dep_tab)
 {
+    const int off_soc = Offsets<NCT, ND>::soc(p), off_dep = Offsets<NCT, ND>::dep(p);
+#pragma unroll 1
     for (int i = 0; i < N; ++i) {
         const uint32_t next = first_arrival(p, N, e, i, episode);
         Vehicle<real> v;
@@ -253,96 +297,110 @@ __device__ __forceinline__ void begin_episode(const Params<real> &p, int N, long
         v.soc0 = 0;
         v.req = 0;
         if (next == 0u) v = fetch_vehicle(p, N, e, i, episode, 0);
-        const size_t idx = sbase + (size_t)i * kBlock;
-        p.hdr[idx] = v.hdr;
-        p.req[idx] = v.req;
         // the dense SoC array holds the arrival SoC at slot `arr` (charging_station.py:257-259),
         // so the reset observation shows it for vehicles arriving at t = 0
-        p.soc[idx] = v.soc0;
+        store_vehicle<real>(spot + (size_t)i * (kPlanes * kBlock), v);
         const bool present = (v.hdr & 0xFFu) == 0u;
-        obs[p.off_soc + i] = present ? (float)v.soc0 : 0.0f;
-        obs[p.off_dep + i] = present ? __ldg(p.dep_norm + ((v.hdr >> 8) & 0xFFu)) : 0.0f;
+        obs[off_soc + i] = present ? (float)v.soc0 : 0.0f;
+        obs[off_dep + i] = present ? dep_tab[(v.hdr >> 8) & 0xFFu] : 0.0f;
     }
-    write_obs_env(p, obs, 0, shift, soc_b);   // battery SoC survives resets (quirk Q8)
+    write_obs_env<real, NCT, ND>(p, obs, 0, shift, soc_b);   // battery SoC survives resets (quirk Q8)
+}
+
+// Discharging an EV (V2X) -- Charger.discharge_vehicle, charger.py:108-140.  Kept out of line: the
+// default action space has no negative charger actions, so this is cold code in the hot loop.
+template <typename real> struct PowerSoc { real P, soc; };
+template <typename real>
+__device__ __noinline__ PowerSoc<real> discharge_vehicle(real power, real dt, real s_prev, real cap)
+{
+    const real calc = s_prev + div_cap(power * dt, cap);
+    PowerSoc<real> r;
+    // flag = ceil(0.5 * (1 + sign(calc))) == 1 iff calc >= 0 (quirk Q1)
+    r.P = (calc >= (real)0) ? -((s_prev * cap) / dt) : power;
+    r.soc = (calc > (real)0) ? calc : (real)0;
+    return r;
 }
 
 // ------------------------------------------------------------------------------------------
 // The step of ONE environment, executed by one thread.
-//   e       local env index          sbase   word index of (this env, spot 0) in the blocked state arrays
+//   e       local env index          spot    (this env, spot 0, plane 0) in the blocked state array
 //   act     [A] action row           obs     [D] observation row   (both in shared memory in the step kernels)
+//   dep_tab [kDepTab] float(k / 24.0) (shared memory in the step kernels)
 //   reward_out, done_out  [E] outputs of this step
 //   wait_actions()  called once, after the first state loads are in flight and before `act` is read
-// NCT: number of spots at compile time (0 = runtime p.N).  EXACT (double only): reproduces
-// numpy's summation order of the station power sums.
+// NCT: number of spots at compile time (0 = runtime p.N); ND: see Offsets.  EXACT (double only):
+// reproduces numpy's summation order of the station power sums.
 // ------------------------------------------------------------------------------------------
-template <typename real, int NCT, bool EXACT, typename WaitFn>
-__device__ __forceinline__ void env_step(const Params<real> &p, long long e, size_t sbase, const real *act, float *obs,
-                                         real *reward_out, uint8_t *done_out, WaitFn wait_actions)
+template <typename real, int NCT, int ND, bool EXACT, typename WaitFn>
+__device__ __forceinline__ void env_step(const Params<real> &p, long long e, typename WordOf<real>::type *spot,
+                                         const real *act, float *obs, const float *dep_tab, real *reward_out,
+                                         uint8_t *done_out, WaitFn wait_actions)
 {
+    typedef typename WordOf<real>::type word;
     const int N = NCT ? NCT : p.N;
     constexpr int CH = NCT == 0 ? 1 : (NCT <= 16 ? NCT : 8);   // spots whose state loads are issued together
+    constexpr int SP = kPlanes * kBlock;                       // words between consecutive spots of an env
+    const int off_soc = Offsets<NCT, ND>::soc(p), off_dep = Offsets<NCT, ND>::dep(p);
     EnvSt<real> es = p.envst[e];
     const int t = (int)(es.t_ep & 0xFFu);
     uint32_t episode = es.t_ep >> 8;
     const int tn = t + 1;
     const bool is_done = (tn == p.T);
+    const uint32_t tn_key = is_done ? 0x100u : (uint32_t)tn;   // never equals a header's `next` byte when done
     real pos = 0, neg = 0, pen_veh = 0;
     uint32_t err = 0;
     unsigned long long arrivals = 0;   // spots whose next vehicle arrives at tn (NCT > 0: N <= 64)
     double cpos[EXACT ? 256 : 1], cneg[EXACT ? 256 : 1];
     int npos = 0, nneg = 0;
+    const real kw_per_action = p.ev_pmax;
 
     // ---- per-spot phase: ChargingStation.simulate_vehicle_charging (charging_station.py:281-300),
     //      Charger.charge_or_discharge_vehicle (charger.py:37-140) and the lagged undercharge
     //      penalty (penaliser.py:39-87) ----
 #pragma unroll 1
     for (int c = 0; c < N; c += CH) {
-        uint32_t h[CH];
-        real rq[CH], sp[CH];
+        word wh[CH], wr[CH], ws[CH];
 #pragma unroll
         for (int j = 0; j < CH; ++j) {
-            const size_t idx = sbase + (size_t)(c + j) * kBlock;
-            h[j] = p.hdr[idx];
-            rq[j] = p.req[idx];
-            sp[j] = p.soc[idx];
+            const word *sp = spot + (size_t)(c + j) * SP;
+            wh[j] = sp[PL_HDR * kBlock];
+            wr[j] = sp[PL_REQ * kBlock];
+            ws[j] = sp[PL_SOC * kBlock];
         }
         if (c == 0) wait_actions();
 #pragma unroll
         for (int j = 0; j < CH; ++j) {
             const int i = c + j;
-            const uint32_t hd = h[j];
+            const uint32_t hd = (uint32_t)wh[j];
+            const real rq = word_to_real(wr[j], (real)0);
+            const real s_prev = word_to_real(ws[j], (real)0);  // SoC column t-1 (the arrival SoC when arr == t, charger.py:62-67)
             const int arr = (int)(hd & 0xFFu), dep = (int)((hd >> 8) & 0xFFu);   // arr == 0xFF: no vehicle yet
-            const real s_prev = sp[j];     // SoC column t-1 (or the arrival SoC when arr == t, charger.py:62-67)
             const real a = act[i];
             if (a != a) err |= FLAG_NAN_ACTION;
 
             // check set computed by the previous observe() at t_obs = t-1; column t-1 of soc / req
-            if (arr <= t - 1 && t - 1 < dep && dep - (t - 1) <= p.max_togo) {
-                const real lower = p.margin * rq[j];       // penaliser.py:72
-                if (s_prev < rq[j] - lower) {              // :78
-                    const real d = (rq[j] - s_prev) * (real)10;
-                    pen_veh = pen_veh + d * d;             // :79 (Python `** 2`)
-                }
+            const bool checked = arr < t && t <= dep && dep - t < p.max_togo;   // arr <= t-1 < dep, dep-(t-1) <= window
+            const real lower = p.margin * rq;                  // penaliser.py:72
+            if (checked && s_prev < rq - lower) {              // :78
+                const real d = (rq - s_prev) * (real)10;
+                pen_veh = pen_veh + d * d;                     // :79 (Python `** 2`)
             }
 
-            const bool present = arr <= t && t < dep;      // charger.occupancy[t] == 1
+            const bool present = arr <= t && t < dep;          // charger.occupancy[t] == 1
             real P = 0, s_new = 0;
-            if (present) {
+            if (a >= (real)0) {
+                // a == 0: soc[t] = soc[p], power 0 (charger.py:38-45) -- the same as charging with zero power;
+                // a > 0: charge_vehicle, charger.py:58-90: min(soc + P*dt/cap, 1); power is NOT reduced when clamped
                 const real cap = (real)((hd >> 16) & 0xFFu);
-                if (a == (real)0) {                              // charger.py:38-45
-                    s_new = s_prev;
-                } else if (a > (real)0) {                        // charge_vehicle, charger.py:58-90
-                    const real power = a * p.ev_pmax * p.ev_eff;
-                    const real calc = s_prev + div_cap(power * p.dt, cap);
-                    s_new = ((real)1 < calc) ? (real)1 : calc;   // power is NOT reduced when clamped
-                    P = power;
-                } else {                                         // discharge_vehicle, charger.py:108-140
-                    const real power = a * p.ev_pmax * p.ev_eff;
-                    const real calc = s_prev + div_cap(power * p.dt, cap);
-                    // flag = ceil(0.5 * (1 + sign(calc))) == 1 iff calc >= 0 (quirk Q1)
-                    P = (calc >= (real)0) ? -((s_prev * cap) / p.dt) : power;
-                    s_new = (calc > (real)0) ? calc : (real)0;
-                }
+                const real power = a * kw_per_action * p.ev_eff;
+                const real calc = s_prev + div_cap(power * p.dt, cap);
+                const real clamped = ((real)1 < calc) ? (real)1 : calc;
+                s_new = present ? ((a == (real)0) ? s_prev : clamped) : (real)0;
+                P = present ? power : (real)0;
+            } else if (present) {                              // a < 0 (or NaN): V2X discharge
+                const PowerSoc<real> r = discharge_vehicle(a * kw_per_action * p.ev_eff, p.dt, s_prev, (real)((hd >> 16) & 0xFFu));
+                P = r.P;
+                s_new = r.soc;
             }
             if (EXACT) {
                 if (P < 0) cneg[nneg++] = (double)P;
@@ -351,18 +409,15 @@ __device__ __forceinline__ void env_step(const Params<real> &p, long long e, siz
                 if (P < 0) neg += P;
                 if (P > 0) pos += P;
             }
-            const size_t idx = sbase + (size_t)i * kBlock;
-            p.soc[idx] = s_new;
-            obs[p.off_soc + i] = (float)s_new;                                       // charging_station.py:114-117
-            obs[p.off_dep + i] = present ? __ldg(p.dep_norm + (dep - t)) : 0.0f;     // :92-112, "/ 24" env:208
-            if (!is_done && (hd >> 24) == (uint32_t)tn) {
+            word *sp = spot + (size_t)i * SP;
+            sp[PL_SOC * kBlock] = real_to_word(s_new);
+            obs[off_soc + i] = (float)s_new;                                  // charging_station.py:114-117
+            obs[off_dep + i] = present ? dep_tab[dep - t] : 0.0f;             // :92-112, "/ 24" env:208
+            if ((hd >> 24) == tn_key) {
                 if (NCT) {
                     arrivals |= 1ull << i;
                 } else {                                   // generic kernel: admit the arriving vehicle in place
-                    const Vehicle<real> v = fetch_vehicle(p, N, e, i, episode, tn);
-                    p.hdr[idx] = v.hdr;
-                    p.req[idx] = v.req;
-                    p.soc[idx] = v.soc0;
+                    store_vehicle<real>(sp, fetch_vehicle(p, N, e, i, episode, tn));
                 }
             }
         }
@@ -409,7 +464,7 @@ __device__ __forceinline__ void env_step(const Params<real> &p, long long e, siz
     const real total_cost = p.cost_w * fabs(cost) + total_pen;            // accountant.py:35
     const real reward = -total_cost;                                      // ...environment.py:183
 
-    write_obs_env(p, obs, t, es.pv_shift, soc_b);                         // obs at the pre-increment t, :173
+    write_obs_env<real, NCT, ND>(p, obs, t, es.pv_shift, soc_b);          // obs at the pre-increment t, :173
     if (p.diag) {
         real *diag = p.diag + (size_t)e * D_COUNT;
         diag[D_TOTAL_CH] = pos; diag[D_TOTAL_DIS] = neg; diag[D_SOLAR] = solar;
@@ -425,11 +480,7 @@ __device__ __forceinline__ void env_step(const Params<real> &p, long long e, siz
         while (arrivals) {
             const int i = __ffsll((long long)arrivals) - 1;
             arrivals &= arrivals - 1;
-            const Vehicle<real> v = fetch_vehicle(p, N, e, i, episode, tn);
-            const size_t idx = sbase + (size_t)i * kBlock;
-            p.hdr[idx] = v.hdr;
-            p.req[idx] = v.req;
-            p.soc[idx] = v.soc0;
+            store_vehicle<real>(spot + (size_t)i * SP, fetch_vehicle(p, N, e, i, episode, tn));
         }
         es.t_ep = (episode << 8) | (uint32_t)tn;
     } else {
@@ -442,7 +493,7 @@ __device__ __forceinline__ void env_step(const Params<real> &p, long long e, siz
             }
             episode = (episode + 1u) & 0xFFFFFFu;
             if (p.mode == MODE_SAMPLE) shift = sample_pv_shift(p, N, p.gid0 + (unsigned long long)e, episode);
-            begin_episode(p, N, e, sbase, episode, shift, soc_b, obs);
+            begin_episode<real, NCT, ND>(p, N, e, spot, episode, shift, soc_b, obs, dep_tab);
         }
         es.t_ep = (episode << 8);                                         // t wraps to 0, :178
     }

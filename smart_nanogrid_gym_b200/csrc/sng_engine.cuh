@@ -54,29 +54,34 @@ EngineBase *make_engine_f64(const sng_config &cfg, int device, std::string &err)
 // use_bulk == 0 (or a partial last block, or unaligned bases) stages the rows with plain coalesced
 // loads / stores instead of the copy engine; both paths run the identical env_step().
 // ------------------------------------------------------------------------------------------
-template <typename real, int NCT, bool EXACT>
+template <typename real, int NCT, int ND, bool EXACT>
 __global__ void __launch_bounds__(256) step_kernel(const Params<real> p, const real *actions, float *obs_out,
                                                   real *reward, uint8_t *done, int n_steps, int use_bulk)
 {
     extern __shared__ __align__(128) unsigned char smem[];
+    typedef typename WordOf<real>::type word;
+    float *dep_tab = reinterpret_cast<float *>(smem);            // [kDepTab] at shared offset 0
+    for (int k = threadIdx.x; k < kDepTab; k += blockDim.x) dep_tab[k] = __ldg(p.dep_norm + k);
+    __syncthreads();                                             // the only CTA-wide barrier; warps are independent below
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     const long long blk = (long long)blockIdx.x * wpb + warp;   // state block = 32 envs
     const long long e0 = blk * kBlock;
-    if (e0 >= p.n_envs) return;                                  // whole warp leaves; no CTA barrier below
+    if (e0 >= p.n_envs) return;
     const int N = NCT ? NCT : p.N;
     const int A = p.A, D = p.D;
     const uint32_t act_bytes = (uint32_t)(kBlock * A * sizeof(real)), obs_bytes = (uint32_t)(kBlock * D * sizeof(float));
     const uint32_t per_warp = align128(act_bytes) + align128(obs_bytes);
-    real *act_s = reinterpret_cast<real *>(smem + (size_t)warp * per_warp);
-    float *obs_s = reinterpret_cast<float *>(smem + (size_t)warp * per_warp + align128(act_bytes));
-    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + (size_t)wpb * per_warp) + warp;
+    unsigned char *wbase = smem + kDepTab * sizeof(float) + (size_t)warp * per_warp;
+    real *act_s = reinterpret_cast<real *>(wbase);
+    float *obs_s = reinterpret_cast<float *>(wbase + align128(act_bytes));
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + kDepTab * sizeof(float) + (size_t)wpb * per_warp) + warp;
 
     const long long left = p.n_envs - e0;
     const int n_valid = left < kBlock ? (int)left : kBlock;
     const bool bulk = use_bulk && n_valid == kBlock;
     const bool valid = lane < n_valid;
     const long long e = e0 + lane;
-    const size_t sbase = (size_t)blk * N * kBlock + lane;
+    word *spot = p.spot + (size_t)blk * N * (kPlanes * kBlock) + lane;
 
     if (bulk) {
         if (lane == 0) {
@@ -101,8 +106,8 @@ __global__ void __launch_bounds__(256) step_kernel(const Params<real> p, const r
             __syncwarp();
         }
         if (valid) {
-            env_step<real, NCT, EXACT>(p, e, sbase, act_s + lane * A, obs_s + lane * D, reward + slab, done + slab,
-                                       [&]() { if (bulk) mbar_wait(bar, (uint32_t)(s & 1)); });
+            env_step<real, NCT, ND, EXACT>(p, e, spot, act_s + lane * A, obs_s + lane * D, dep_tab, reward + slab,
+                                           done + slab, [&]() { if (bulk) mbar_wait(bar, (uint32_t)(s & 1)); });
         }
         if (bulk) {
             fence_proxy_async();
@@ -138,8 +143,8 @@ __global__ void __launch_bounds__(256) reset_kernel(const Params<real> p, const 
     }
     if (init || reset_battery) soc_b = p.batt ? p.b_soc0 : (real)0;
     if (p.mode == MODE_SAMPLE) shift = sample_pv_shift(p, p.N, p.gid0 + (unsigned long long)e, episode);
-    const size_t sbase = (size_t)(e / kBlock) * p.N * kBlock + (size_t)(e % kBlock);
-    begin_episode(p, p.N, e, sbase, episode, shift, soc_b, p.obs + (size_t)e * p.D);
+    typename WordOf<real>::type *spot = p.spot + (size_t)(e / kBlock) * p.N * (kPlanes * kBlock) + (size_t)(e % kBlock);
+    begin_episode<real, 0, 0>(p, p.N, e, spot, episode, shift, soc_b, p.obs + (size_t)e * p.D, p.dep_norm);
     es.soc_b = soc_b;
     es.pv_shift = shift;
     es.ep_ret = 0;
@@ -281,13 +286,13 @@ public:
     int bind(const sng_buffers *b) override
     {
         if (!b || b->struct_size != sizeof(sng_buffers)) { error = "sng_bind: bad struct_size"; return SNG_ERR_ARG; }
-        if (!b->actions || !b->obs || !b->reward || !b->done || !b->soc || !b->hdr || !b->req || !b->envst) {
-            error = "sng_bind: actions, obs, reward, done, soc, hdr, req and envst are required";
+        if (!b->actions || !b->obs || !b->reward || !b->done || !b->spot || !b->envst) {
+            error = "sng_bind: actions, obs, reward, done, spot and envst are required";
             return SNG_ERR_ARG;
         }
         buf = *b;
         p.actions = (const real *)b->actions; p.obs = b->obs; p.reward = (real *)b->reward; p.done = b->done;
-        p.tobs = b->terminal_obs; p.soc = (real *)b->soc; p.hdr = b->hdr; p.req = (real *)b->req;
+        p.tobs = b->terminal_obs; p.spot = (typename WordOf<real>::type *)b->spot;
         p.envst = (EnvSt<real> *)b->envst; p.plan = (const PlanRec<real> *)b->plan; p.err = b->err;
         p.diag = (real *)b->diag; p.last_ret = (real *)b->last_return;
         bound = true;
@@ -399,20 +404,21 @@ public:
     int geometry(int &wpb, size_t &smem) const
     {
         const size_t per_warp = align128((uint32_t)(kBlock * p.A * sizeof(real))) + align128((uint32_t)(kBlock * p.D * sizeof(float)));
+        const size_t fixed = kDepTab * sizeof(float);
         wpb = warps_per_cta > 0 ? warps_per_cta : 4;
-        while (wpb > 1 && (size_t)wpb * (per_warp + 8) > smem_optin) wpb >>= 1;
-        smem = (size_t)wpb * (per_warp + 8);
+        while (wpb > 1 && fixed + (size_t)wpb * (per_warp + 8) > smem_optin) wpb >>= 1;
+        smem = fixed + (size_t)wpb * (per_warp + 8);
         return smem <= smem_optin ? SNG_OK : SNG_ERR_UNSUPPORTED;
     }
 
-    template <int NCT>
+    template <int NCT, int ND>
     int launch_step_n(const Params<real> &q, const real *actions, float *obs, real *reward, uint8_t *done, int n_steps,
                       int bulk, cudaStream_t st)
     {
         int wpb;
         size_t smem;
         if (geometry(wpb, smem) != SNG_OK) { error = "step kernel: one warp's action/observation rows do not fit in shared memory"; return SNG_ERR_UNSUPPORTED; }
-        auto kern = step_kernel<real, NCT, EXACT>;
+        auto kern = step_kernel<real, NCT, ND, EXACT>;
         SNG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const long long blocks = (q.n_envs + kBlock - 1) / kBlock;
         const unsigned grid = (unsigned)((blocks + wpb - 1) / wpb);
@@ -431,18 +437,20 @@ public:
         if (n_steps > 1 && (((size_t)q.n_envs * q.A * sizeof(real)) % 16 != 0 || ((size_t)q.n_envs * q.D * sizeof(float)) % 16 != 0))
             bulk = 0;
         if constexpr (EXACT) {
-            return launch_step_n<0>(q, actions, obs, reward, done, n_steps, bulk, st);
+            return launch_step_n<0, 0>(q, actions, obs, reward, done, n_steps, bulk, st);
         } else {
-            if (!use_generic) {
+            // specialised kernels: the station sizes BASELINE.json names, with the reference's observation
+            // shape (PV on, 3 steps ahead: 8 disturbance entries); everything else runs the generic kernel
+            if (!use_generic && q.off_soc == 8) {
                 switch (q.N) {
-                case 4: return launch_step_n<4>(q, actions, obs, reward, done, n_steps, bulk, st);
-                case 8: return launch_step_n<8>(q, actions, obs, reward, done, n_steps, bulk, st);
-                case 10: return launch_step_n<10>(q, actions, obs, reward, done, n_steps, bulk, st);
-                case 64: return launch_step_n<64>(q, actions, obs, reward, done, n_steps, bulk, st);
+                case 4: return launch_step_n<4, 8>(q, actions, obs, reward, done, n_steps, bulk, st);
+                case 8: return launch_step_n<8, 8>(q, actions, obs, reward, done, n_steps, bulk, st);
+                case 10: return launch_step_n<10, 8>(q, actions, obs, reward, done, n_steps, bulk, st);
+                case 64: return launch_step_n<64, 8>(q, actions, obs, reward, done, n_steps, bulk, st);
                 default: break;
                 }
             }
-            return launch_step_n<0>(q, actions, obs, reward, done, n_steps, bulk, st);
+            return launch_step_n<0, 0>(q, actions, obs, reward, done, n_steps, bulk, st);
         }
     }
 
@@ -470,7 +478,7 @@ public:
         q.gid0 = p.gid0 + (unsigned long long)e0;
         q.actions += (size_t)e0 * p.A; q.obs += (size_t)e0 * p.D; q.reward += e0; q.done += e0;
         if (q.tobs) q.tobs += (size_t)e0 * p.D;
-        q.soc += (size_t)e0 * p.N; q.hdr += (size_t)e0 * p.N; q.req += (size_t)e0 * p.N; q.envst += e0;
+        q.spot += (size_t)e0 * p.N * kPlanes; q.envst += e0;
         if (q.plan) q.plan += (size_t)e0 * p.N * kMaxVehicles;
         if (q.err) q.err += e0;
         if (q.diag) q.diag += (size_t)e0 * D_COUNT;

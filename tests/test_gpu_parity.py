@@ -246,7 +246,7 @@ def test_kernel_variants_are_bit_identical(kw):
         outs = [e.step(a) for e in envs]
         for e, o in zip(envs[1:], outs[1:]):
             assert torch.equal(o[0], outs[0][0]) and torch.equal(o[1], outs[0][1]) and torch.equal(o[2], outs[0][2]), s
-            assert torch.equal(envs[0]._soc, e._soc) and torch.equal(envs[0]._hdr, e._hdr) and torch.equal(envs[0]._req, e._req)
+            assert torch.equal(envs[0]._spot, e._spot)
             assert torch.equal(envs[0]._envst, e._envst) and torch.equal(envs[0].terminal_obs, e.terminal_obs)
             assert torch.equal(envs[0].diag, e.diag)
     for e in envs:
