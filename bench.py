@@ -203,8 +203,10 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=24)
     ap.add_argument("--warps", type=int, default=0, help="tuning: warps (blocks of 32 envs) per CTA (0 = auto)")
     ap.add_argument("--generic", action="store_true", help="tuning: use the generic runtime-N kernel")
-    ap.add_argument("--no-bulk", action="store_true", help="tuning: stage rows with plain loads instead of the copy engine")
+    ap.add_argument("--bulk", type=int, default=1, help="tuning: 0 plain loads/stores, 1 copy-engine action loads + vector obs stores, 3 copy engine both ways")
     ap.add_argument("--host-chunks", type=int, default=0, help="tuning: env chunks of the pipelined host path")
+    ap.add_argument("--pipeline", action="store_true", help="tuning: persistent pipelined kernel instead of one block per warp")
+    ap.add_argument("--ctas", type=int, default=0, help="tuning: cap on resident CTAs per SM (pipelined kernel)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -230,7 +232,8 @@ def main():
     E = args.envs
     env = BatchedSmartNanogridEnv(E, device=dev, seed=0, env_gid0=rank * E, precision="float32", auto_reset=True,
                                   **ENV_KW)
-    env.set_tuning(args.warps, int(args.generic), 0 if args.no_bulk else 1, args.host_chunks)
+    env.set_tuning(args.warps, int(args.generic), args.bulk, args.host_chunks)
+    env.set_pipeline(1 if args.pipeline else 0, args.ctas)
     cfg = env.cfg
     env.reset()
     # actions: a pre-filled U(low, high) tensor re-read from HBM every step

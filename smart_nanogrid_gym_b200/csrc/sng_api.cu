@@ -152,4 +152,10 @@ int sng_set_tuning(sng_env *env, int warps_per_cta, int use_generic_kernel, int 
     return done(env, env->eng->set_tuning(warps_per_cta, use_generic_kernel, use_bulk_copy, host_chunks));
 }
 
+int sng_set_pipeline(sng_env *env, int use_pipelined_kernel, int ctas_per_sm)
+{
+    SNG_ENV_CHECK(env);
+    return done(env, env->eng->set_pipeline(use_pipelined_kernel, ctas_per_sm));
+}
+
 }  // extern "C"

@@ -13,6 +13,7 @@
 // is the step-by-step specification.
 #pragma once
 #include <cstdint>
+#include <type_traits>
 #include <cuda_runtime.h>
 
 namespace sng {
@@ -245,6 +246,31 @@ __device__ __forceinline__ float div_cap(float x, float cap)
 }
 __device__ __forceinline__ double div_cap(double x, double cap) { return x / cap; }
 
+// Departure-time normalisation float(k / 24.0) (…environment.py:208,228): a 256-entry table, read from
+// the CTA's shared-memory copy in the step kernels (SMEM) or from global memory elsewhere.
+__device__ __forceinline__ float *dep_table_smem()
+{
+    __shared__ float tab[kDepTab];
+    return tab;
+}
+// 32-bit shared-space address of the table, made opaque so that it stays in one register instead of
+// being re-derived (S2R + LEA) at every use.
+__device__ __forceinline__ uint32_t dep_table_base()
+{
+    uint32_t a = (uint32_t)__cvta_generic_to_shared(dep_table_smem());
+    asm volatile("" : "+r"(a));
+    return a;
+}
+template <bool SMEM, typename real> __device__ __forceinline__ float dep_lookup(const Params<real> &p, uint32_t base, int k)
+{
+    if (SMEM) {
+        float v;
+        asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(base + 4u * (uint32_t)k));
+        return v;
+    }
+    return __ldg(p.dep_norm + k);
+}
+
 // Observation offsets: ND = number of disturbance entries = (1 + pv) * (1 + H) when known at compile
 // time (0 = read the offsets from the parameters).
 template <int NCT, int ND> struct Offsets {
@@ -282,13 +308,14 @@ __device__ __forceinline__ void write_obs_env(const Params<real> &p, float *obs,
 // Begin an episode at t = 0 (SmartNanogridEnv.reset, envs/smart_nanogrid_environment.py:311-351):
 // per spot, schedule the first arrival of the day (and admit it when it is at step 0), clear the SoC
 // state (clear_initialisation_variables, charging_station.py:138-150) and write the reset observation.
-// `spot` points at (this env, spot 0, plane 0); dep_tab is the departure-normalisation table.
-template <typename real, int NCT, int ND>
+// `spot` points at (this env, spot 0, plane 0).
+template <typename real, int NCT, int ND, bool SMEM>
 __device__ __forceinline__ void begin_episode(const Params<real> &p, int N, long long e,
                                               typename WordOf<real>::type *spot, uint32_t episode, real shift,
-                                              real soc_b, float *obs, const float *dep_tab)
+                                              real soc_b, float *obs)
 {
     const int off_soc = Offsets<NCT, ND>::soc(p), off_dep = Offsets<NCT, ND>::dep(p);
+    const uint32_t dep_base = SMEM ? dep_table_base() : 0u;
 #pragma unroll 1
     for (int i = 0; i < N; ++i) {
         const uint32_t next = first_arrival(p, N, e, i, episode);
@@ -302,9 +329,44 @@ __device__ __forceinline__ void begin_episode(const Params<real> &p, int N, long
         store_vehicle<real>(spot + (size_t)i * (kPlanes * kBlock), v);
         const bool present = (v.hdr & 0xFFu) == 0u;
         obs[off_soc + i] = present ? (float)v.soc0 : 0.0f;
-        obs[off_dep + i] = present ? dep_tab[(v.hdr >> 8) & 0xFFu] : 0.0f;
+        obs[off_dep + i] = present ? dep_lookup<SMEM>(p, dep_base, (int)((v.hdr >> 8) & 0xFFu)) : 0.0f;
     }
     write_obs_env<real, NCT, ND>(p, obs, 0, shift, soc_b);   // battery SoC survives resets (quirk Q8)
+}
+
+// Spots whose state loads are issued together (and, in the pipelined kernel, one block ahead).
+template <int NCT> struct Chunk {
+    static constexpr int value = NCT == 0 ? 1 : (NCT <= 16 ? NCT : 8);
+    static_assert(NCT == 0 || NCT % value == 0, "the chunk must divide the number of spots");
+};
+
+// Registers holding the per-env scalars and the first chunk of per-spot state words of one env.
+template <typename real, int NCT> struct StateRegs {
+    typedef typename WordOf<real>::type word;
+    EnvSt<real> es;
+    word h[Chunk<NCT>::value], r[Chunk<NCT>::value], s[Chunk<NCT>::value];
+};
+
+template <typename real, int CH>
+__device__ __forceinline__ void load_spots(const typename WordOf<real>::type *spot, int c, typename WordOf<real>::type (&h)[CH],
+                                           typename WordOf<real>::type (&r)[CH], typename WordOf<real>::type (&s)[CH])
+{
+#pragma unroll
+    for (int j = 0; j < CH; ++j) {
+        const typename WordOf<real>::type *sp = spot + (size_t)(c + j) * (kPlanes * kBlock);
+        h[j] = sp[PL_HDR * kBlock];
+        r[j] = sp[PL_REQ * kBlock];
+        s[j] = sp[PL_SOC * kBlock];
+    }
+}
+
+// Issue the loads of one env's scalars and first state chunk (consumed by env_step, possibly one block later).
+template <typename real, int NCT>
+__device__ __forceinline__ void load_state(const Params<real> &p, long long e, const typename WordOf<real>::type *spot,
+                                           StateRegs<real, NCT> &st)
+{
+    st.es = p.envst[e];
+    load_spots<real, Chunk<NCT>::value>(spot, 0, st.h, st.r, st.s);
 }
 
 // Discharging an EV (V2X) -- Charger.discharge_vehicle, charger.py:108-140.  Kept out of line: the
@@ -325,23 +387,23 @@ __device__ __noinline__ PowerSoc<real> discharge_vehicle(real power, real dt, re
 // The step of ONE environment, executed by one thread.
 //   e       local env index          spot    (this env, spot 0, plane 0) in the blocked state array
 //   act     [A] action row           obs     [D] observation row   (both in shared memory in the step kernels)
-//   dep_tab [kDepTab] float(k / 24.0) (shared memory in the step kernels)
+//   SMEM    the departure table is read from the CTA's shared-memory copy (step kernels)
 //   reward_out, done_out  [E] outputs of this step
-//   wait_actions()  called once, after the first state loads are in flight and before `act` is read
+//   st      the env scalars and first state chunk, loaded by load_state()
 // NCT: number of spots at compile time (0 = runtime p.N); ND: see Offsets.  EXACT (double only):
 // reproduces numpy's summation order of the station power sums.
 // ------------------------------------------------------------------------------------------
-template <typename real, int NCT, int ND, bool EXACT, typename WaitFn>
+template <typename real, int NCT, int ND, bool EXACT, bool SMEM>
 __device__ __forceinline__ void env_step(const Params<real> &p, long long e, typename WordOf<real>::type *spot,
-                                         const real *act, float *obs, const float *dep_tab, real *reward_out,
-                                         uint8_t *done_out, WaitFn wait_actions)
+                                         const StateRegs<real, NCT> &st, const real *act, float *obs,
+                                         real *reward_out, uint8_t *done_out)
 {
     typedef typename WordOf<real>::type word;
     const int N = NCT ? NCT : p.N;
-    constexpr int CH = NCT == 0 ? 1 : (NCT <= 16 ? NCT : 8);   // spots whose state loads are issued together
+    constexpr int CH = Chunk<NCT>::value;
     constexpr int SP = kPlanes * kBlock;                       // words between consecutive spots of an env
     const int off_soc = Offsets<NCT, ND>::soc(p), off_dep = Offsets<NCT, ND>::dep(p);
-    EnvSt<real> es = p.envst[e];
+    EnvSt<real> es = st.es;
     const int t = (int)(es.t_ep & 0xFFu);
     uint32_t episode = es.t_ep >> 8;
     const int tn = t + 1;
@@ -349,10 +411,18 @@ __device__ __forceinline__ void env_step(const Params<real> &p, long long e, typ
     const uint32_t tn_key = is_done ? 0x100u : (uint32_t)tn;   // never equals a header's `next` byte when done
     real pos = 0, neg = 0, pen_veh = 0;
     uint32_t err = 0;
-    unsigned long long arrivals = 0;   // spots whose next vehicle arrives at tn (NCT > 0: N <= 64)
+    // spots whose next vehicle arrives at tn (specialised kernels only: N <= 64)
+    typename std::conditional<(NCT > 32), unsigned long long, uint32_t>::type arrivals = 0, discharging = 0;
+    constexpr bool DEFER = NCT > 0 && !EXACT;   // V2X discharges are finished after the (branch-free) hot loop
     double cpos[EXACT ? 256 : 1], cneg[EXACT ? 256 : 1];
     int npos = 0, nneg = 0;
-    const real kw_per_action = p.ev_pmax;
+    // float32 build: fold the constant factors of the power (a * 22 * 0.95) and of the SoC change
+    // (power * dt) into one multiplier each (<= 1 ulp from the reference's operation order);
+    // the float64 validation build keeps the reference's order
+    const real kw = EXACT ? p.ev_pmax : p.ev_pmax * p.ev_eff;
+    const real kwh = kw * p.dt;
+    const uint32_t dep_base = SMEM ? dep_table_base() : 0u;
+    real nan_probe = 0;   // float32 build: sum of a * 0 over all actions is NaN iff some action is NaN or infinite
 
     // ---- per-spot phase: ChargingStation.simulate_vehicle_charging (charging_station.py:281-300),
     //      Charger.charge_or_discharge_vehicle (charger.py:37-140) and the lagged undercharge
@@ -360,14 +430,12 @@ __device__ __forceinline__ void env_step(const Params<real> &p, long long e, typ
 #pragma unroll 1
     for (int c = 0; c < N; c += CH) {
         word wh[CH], wr[CH], ws[CH];
+        if (c == 0) {
 #pragma unroll
-        for (int j = 0; j < CH; ++j) {
-            const word *sp = spot + (size_t)(c + j) * SP;
-            wh[j] = sp[PL_HDR * kBlock];
-            wr[j] = sp[PL_REQ * kBlock];
-            ws[j] = sp[PL_SOC * kBlock];
+            for (int j = 0; j < CH; ++j) { wh[j] = st.h[j]; wr[j] = st.r[j]; ws[j] = st.s[j]; }
+        } else {
+            load_spots<real, CH>(spot, c, wh, wr, ws);
         }
-        if (c == 0) wait_actions();
 #pragma unroll
         for (int j = 0; j < CH; ++j) {
             const int i = c + j;
@@ -376,7 +444,11 @@ __device__ __forceinline__ void env_step(const Params<real> &p, long long e, typ
             const real s_prev = word_to_real(ws[j], (real)0);  // SoC column t-1 (the arrival SoC when arr == t, charger.py:62-67)
             const int arr = (int)(hd & 0xFFu), dep = (int)((hd >> 8) & 0xFFu);   // arr == 0xFF: no vehicle yet
             const real a = act[i];
-            if (a != a) err |= FLAG_NAN_ACTION;
+            if (EXACT) {
+                if (a != a) err |= FLAG_NAN_ACTION;
+            } else {
+                nan_probe = fma(a, (real)0, nan_probe);
+            }
 
             // check set computed by the previous observe() at t_obs = t-1; column t-1 of soc / req
             const bool checked = arr < t && t <= dep && dep - t < p.max_togo;   // arr <= t-1 < dep, dep-(t-1) <= window
@@ -388,34 +460,47 @@ __device__ __forceinline__ void env_step(const Params<real> &p, long long e, typ
 
             const bool present = arr <= t && t < dep;          // charger.occupancy[t] == 1
             real P = 0, s_new = 0;
-            if (a >= (real)0) {
+            if (DEFER || a >= (real)0) {
                 // a == 0: soc[t] = soc[p], power 0 (charger.py:38-45) -- the same as charging with zero power;
                 // a > 0: charge_vehicle, charger.py:58-90: min(soc + P*dt/cap, 1); power is NOT reduced when clamped
                 const real cap = (real)((hd >> 16) & 0xFFu);
-                const real power = a * kw_per_action * p.ev_eff;
-                const real calc = s_prev + div_cap(power * p.dt, cap);
-                const real clamped = ((real)1 < calc) ? (real)1 : calc;
-                s_new = present ? ((a == (real)0) ? s_prev : clamped) : (real)0;
+                const real power = EXACT ? a * kw * p.ev_eff : a * kw;
+                const real calc = s_prev + div_cap(EXACT ? power * p.dt : a * kwh, cap);
+                const real clamped = ((real)1 < calc) ? (real)1 : calc;   // a == 0 gives calc == s_prev <= 1 exactly
+                s_new = present ? clamped : (real)0;
                 P = present ? power : (real)0;
+                if (DEFER) {
+                    // branch-free hot loop: a spot whose action is negative (V2X) or NaN keeps its SoC here
+                    // and is finished by the cold pass below
+                    const bool later = present && !(a >= (real)0);
+                    if (later) discharging |= (decltype(discharging))1 << i;
+                    s_new = later ? s_prev : s_new;
+                    P = later ? (real)0 : P;
+                }
+                if (EXACT) {
+                    if (P > 0) cpos[npos++] = (double)P;
+                } else {
+                    pos += P;                                  // P >= 0 here
+                }
             } else if (present) {                              // a < 0 (or NaN): V2X discharge
-                const PowerSoc<real> r = discharge_vehicle(a * kw_per_action * p.ev_eff, p.dt, s_prev, (real)((hd >> 16) & 0xFFu));
+                const PowerSoc<real> r = discharge_vehicle(a * p.ev_pmax * p.ev_eff, p.dt, s_prev, (real)((hd >> 16) & 0xFFu));
                 P = r.P;
                 s_new = r.soc;
-            }
-            if (EXACT) {
-                if (P < 0) cneg[nneg++] = (double)P;
-                if (P > 0) cpos[npos++] = (double)P;
-            } else {
-                if (P < 0) neg += P;
-                if (P > 0) pos += P;
+                if (EXACT) {
+                    if (P < 0) cneg[nneg++] = (double)P;
+                    if (P > 0) cpos[npos++] = (double)P;
+                } else {
+                    if (P < 0) neg += P;
+                    if (P > 0) pos += P;
+                }
             }
             word *sp = spot + (size_t)i * SP;
             sp[PL_SOC * kBlock] = real_to_word(s_new);
             obs[off_soc + i] = (float)s_new;                                  // charging_station.py:114-117
-            obs[off_dep + i] = present ? dep_tab[dep - t] : 0.0f;             // :92-112, "/ 24" env:208
+            obs[off_dep + i] = present ? dep_lookup<SMEM>(p, dep_base, dep - t) : 0.0f;   // :92-112, "/ 24" env:208
             if ((hd >> 24) == tn_key) {
                 if (NCT) {
-                    arrivals |= 1ull << i;
+                    arrivals |= (decltype(arrivals))1 << i;
                 } else {                                   // generic kernel: admit the arriving vehicle in place
                     store_vehicle<real>(sp, fetch_vehicle(p, N, e, i, episode, tn));
                 }
@@ -426,6 +511,18 @@ __device__ __forceinline__ void env_step(const Params<real> &p, long long e, typ
         neg = (real)numpy_sum(cneg, nneg);
         pos = (real)numpy_sum(cpos, npos);
     }
+    while (DEFER && discharging) {   // cold pass: V2X discharges (and NaN actions) left out of the hot loop
+        const int i = (NCT > 32) ? __ffsll((long long)discharging) - 1 : __ffs((int)discharging) - 1;
+        discharging &= discharging - 1;
+        word *sp = spot + (size_t)i * SP;
+        const uint32_t hd = (uint32_t)sp[PL_HDR * kBlock];
+        const real s_prev = word_to_real(sp[PL_SOC * kBlock], (real)0);   // the hot loop left it unchanged
+        const PowerSoc<real> r = discharge_vehicle(act[i] * p.ev_pmax * p.ev_eff, p.dt, s_prev, (real)((hd >> 16) & 0xFFu));
+        if (r.P < 0) neg += r.P;
+        if (r.P > 0) pos += r.P;
+        sp[PL_SOC * kBlock] = real_to_word(r.soc);
+        obs[off_soc + i] = (float)r.soc;
+    }
 
     // ---- env-level phase: CentralManagementSystem.manage_nanogrid (central_management_system.py:99-113) ----
     const real total_power = pos + neg;                                   // :105
@@ -435,7 +532,11 @@ __device__ __forceinline__ void env_step(const Params<real> &p, long long e, typ
     real soc_b = es.soc_b, batt_power = 0, pen_b = 0;
     if (p.batt) {                                                         // battery_energy_storage_system.py:30-106
         const real ab = act[N];                                           // actions[-1], :88-89
-        if (ab != ab) err |= FLAG_NAN_ACTION;
+        if (EXACT) {
+            if (ab != ab) err |= FLAG_NAN_ACTION;
+        } else {
+            nan_probe = fma(ab, (real)0, nan_probe);
+        }
         if (ab > (real)0) {                                               // charge, :46-74
             const real power = ab * p.b_pmax * p.b_eff;
             const real calc = soc_b + (power * p.dt) / p.b_cap;
@@ -457,6 +558,7 @@ __device__ __forceinline__ void env_step(const Params<real> &p, long long e, typ
             err |= FLAG_BATT_SOC_GT1;
         }
     }
+    if (!EXACT && nan_probe != nan_probe) err |= FLAG_NAN_ACTION;
     const real energy = rem * p.dt;                                       // central_management_system.py:107
     const real price = __ldg(p.price + t);
     const real cost = (energy < (real)0) ? energy * p.sell * price : energy * price;   // accountant.py:26-32
@@ -478,7 +580,7 @@ __device__ __forceinline__ void env_step(const Params<real> &p, long long e, typ
     if (!is_done) {
         // admit the vehicles that arrive at tn (the observation above does not show them: quirk Q5)
         while (arrivals) {
-            const int i = __ffsll((long long)arrivals) - 1;
+            const int i = (NCT > 32) ? __ffsll((long long)arrivals) - 1 : __ffs((int)arrivals) - 1;
             arrivals &= arrivals - 1;
             store_vehicle<real>(spot + (size_t)i * SP, fetch_vehicle(p, N, e, i, episode, tn));
         }
@@ -493,7 +595,7 @@ __device__ __forceinline__ void env_step(const Params<real> &p, long long e, typ
             }
             episode = (episode + 1u) & 0xFFFFFFu;
             if (p.mode == MODE_SAMPLE) shift = sample_pv_shift(p, N, p.gid0 + (unsigned long long)e, episode);
-            begin_episode<real, NCT, ND>(p, N, e, spot, episode, shift, soc_b, obs, dep_tab);
+            begin_episode<real, NCT, ND, SMEM>(p, N, e, spot, episode, shift, soc_b, obs);
         }
         es.t_ep = (episode << 8);                                         // t wraps to 0, :178
     }

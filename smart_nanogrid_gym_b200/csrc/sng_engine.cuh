@@ -26,6 +26,7 @@ struct EngineBase {
     virtual int sample_plan(cudaStream_t st) = 0;
     virtual int error_flags(uint32_t *out, cudaStream_t st) = 0;
     virtual int set_tuning(int warps_per_cta, int use_generic, int use_bulk, int host_chunks) = 0;
+    virtual int set_pipeline(int use_pipeline, int ctas_per_sm) = 0;
     int64_t launches = 0;
     std::string error;
 };
@@ -43,45 +44,132 @@ EngineBase *make_engine_f64(const sng_config &cfg, int device, std::string &err)
     } while (0)
 
 // ------------------------------------------------------------------------------------------
-// The step kernel.  One warp = one block of 32 consecutive envs, one thread per env; warps are
-// independent (no CTA-wide barrier).  Per warp and step:
-//   lane 0: cp.async.bulk  actions[32 rows] HBM -> shared (mbarrier complete_tx)
-//   all   : coalesced loads of the blocked state, wait for the actions, env_step() out of shared
-//           memory, observation rows written to shared memory
-//   lane 0: cp.async.bulk  obs[32 rows] shared -> HBM
-// `n_steps` > 1 is the rollout: the same warp advances its envs n_steps times, one action / obs /
-// reward / done slab per step (slab strides in rows: E).
-// use_bulk == 0 (or a partial last block, or unaligned bases) stages the rows with plain coalesced
-// loads / stores instead of the copy engine; both paths run the identical env_step().
+// Step kernels.  One warp = one block of 32 consecutive envs, one thread per env; warps are
+// independent (the only CTA-wide barrier publishes the departure table).  Action rows arrive and
+// observation rows leave through shared memory, moved by the copy engine (one cp.async.bulk per warp
+// and direction, mbarrier complete_tx / bulk_group); the blocked state is read and written with
+// coalesced 128-byte warp accesses; env_step() is the same body everywhere.
+//
+//   step_pipelined_kernel  the production single-step kernel: persistent warps walk the blocks
+//                          grid-stride and software-pipeline them -- while block k is computed, the
+//                          state words of block k+1 are already loading into registers and its action
+//                          rows into the other shared-memory stage, so DRAM never waits for the math.
+//   step_simple_kernel     one block per warp, no pipelining; any n_steps (the rollout: the same warp
+//                          advances its envs n_steps times, one action / obs / reward / done slab per
+//                          step), partial last block, and a plain load / store staging path for
+//                          buffers the copy engine cannot address (16-byte alignment) or use_bulk == 0.
 // ------------------------------------------------------------------------------------------
+template <typename real> __device__ __forceinline__ void publish_dep_table(const Params<real> &p)
+{
+    float4 *tab = reinterpret_cast<float4 *>(dep_table_smem());
+#pragma unroll 1
+    for (int k = threadIdx.x; k < kDepTab / 4; k += blockDim.x) tab[k] = __ldg(reinterpret_cast<const float4 *>(p.dep_norm) + k);
+    __syncthreads();
+}
+
+#ifndef SNG_PIPE_THREADS
+#define SNG_PIPE_THREADS 64
+#endif
+#ifndef SNG_PIPE_MINB
+#define SNG_PIPE_MINB 10
+#endif
 template <typename real, int NCT, int ND, bool EXACT>
-__global__ void __launch_bounds__(256) step_kernel(const Params<real> p, const real *actions, float *obs_out,
-                                                  real *reward, uint8_t *done, int n_steps, int use_bulk)
+__global__ void __launch_bounds__(SNG_PIPE_THREADS, SNG_PIPE_MINB)
+    step_pipelined_kernel(const Params<real> p, long long n_blocks)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     typedef typename WordOf<real>::type word;
-    float *dep_tab = reinterpret_cast<float *>(smem);            // [kDepTab] at shared offset 0
-    for (int k = threadIdx.x; k < kDepTab; k += blockDim.x) dep_tab[k] = __ldg(p.dep_norm + k);
-    __syncthreads();                                             // the only CTA-wide barrier; warps are independent below
+    publish_dep_table(p);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-    const long long blk = (long long)blockIdx.x * wpb + warp;   // state block = 32 envs
-    const long long e0 = blk * kBlock;
-    if (e0 >= p.n_envs) return;
+    const int N = NCT ? NCT : p.N;
+    const int A = p.A, D = p.D;
+    const uint32_t act_bytes = (uint32_t)(kBlock * A * sizeof(real)), obs_bytes = (uint32_t)(kBlock * D * sizeof(float));
+    const uint32_t act_stage = align128(act_bytes);
+    const uint32_t per_warp = 2 * act_stage + align128(obs_bytes);
+    unsigned char *wbase = smem + (size_t)warp * per_warp;
+    float *obs_s = reinterpret_cast<float *>(wbase + 2 * act_stage);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + (size_t)wpb * per_warp) + 2 * warp;   // one per action stage
+
+    const long long stride = (long long)gridDim.x * wpb;
+    long long blk = (long long)blockIdx.x * wpb + warp;
+    if (blk >= n_blocks) return;
+    if (lane == 0) {
+        mbar_init(bar, 1);
+        mbar_init(bar + 1, 1);
+        fence_mbar_init();
+    }
+    __syncwarp();
+    const size_t blk_words = (size_t)N * (kPlanes * kBlock);
+    StateRegs<real, NCT> cur, nxt;
+    load_state<real, NCT>(p, blk * kBlock + lane, p.spot + (size_t)blk * blk_words + lane, cur);
+    if (lane == 0) {
+        mbar_expect_tx(bar, act_bytes);
+        bulk_g2s(wbase, p.actions + (size_t)blk * kBlock * A, act_bytes, bar);
+    }
+    for (int it = 0; blk < n_blocks; ++it, blk += stride) {
+        const long long nblk = blk + stride;
+        const int stage = it & 1;
+        if (nblk < n_blocks) {   // warp-uniform: put block k+1 in flight
+            load_state<real, NCT>(p, nblk * kBlock + lane, p.spot + (size_t)nblk * blk_words + lane, nxt);
+            if (lane == 0) {
+                mbar_expect_tx(bar + (stage ^ 1), act_bytes);
+                bulk_g2s(wbase + (stage ^ 1) * act_stage, p.actions + (size_t)nblk * kBlock * A, act_bytes, bar + (stage ^ 1));
+            }
+        }
+        mbar_wait(bar + stage, (uint32_t)((it >> 1) & 1));
+        const long long e = blk * kBlock + lane;
+        env_step<real, NCT, ND, EXACT, true>(p, e, p.spot + (size_t)blk * blk_words + lane, cur,
+                                             reinterpret_cast<const real *>(wbase + stage * act_stage) + lane * A,
+                                             obs_s + lane * D, p.reward, p.done);
+        __syncwarp();            // obs rows complete; everyone is done reading this action stage
+        {   // 32 rows = 8 * D float4 (16-byte aligned on both sides): coalesced 512-byte warp stores.
+            // (Plain stores, not cp.async.bulk: waiting for a bulk group drains the scoreboard the
+            //  prefetched state loads sit on, which would serialise the pipeline.)
+            const float4 *src = reinterpret_cast<const float4 *>(obs_s);
+            float4 *dst = reinterpret_cast<float4 *>(p.obs + (size_t)blk * kBlock * D);
+#pragma unroll 4
+            for (int k = lane; k < 8 * D; k += 32) dst[k] = src[k];
+        }
+        __syncwarp();            // obs_s may be overwritten by the next block
+        cur = nxt;
+    }
+}
+
+#ifndef SNG_STEP_MAXT
+#define SNG_STEP_MAXT 128
+#endif
+#ifndef SNG_STEP_MINB
+#define SNG_STEP_MINB 8
+#endif
+// MULTI: n_steps > 1 (rollout); the single-step instantiation carries no slab arithmetic.
+template <typename real, int NCT, int ND, bool EXACT, bool MULTI>
+__global__ void __launch_bounds__(SNG_STEP_MAXT, EXACT ? 1 : SNG_STEP_MINB)
+    step_simple_kernel(const Params<real> p, const real *actions, float *obs_out, real *reward, uint8_t *done, int n_steps,
+                       int use_bulk)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    typedef typename WordOf<real>::type word;
+    publish_dep_table(p);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const int n_envs = (int)p.n_envs;                            // a handle owns < 2^31 envs (sng_create)
+    const int blk = blockIdx.x * wpb + warp;                     // state block = 32 envs
+    const int e0 = blk * kBlock;
+    if (e0 >= n_envs) return;
     const int N = NCT ? NCT : p.N;
     const int A = p.A, D = p.D;
     const uint32_t act_bytes = (uint32_t)(kBlock * A * sizeof(real)), obs_bytes = (uint32_t)(kBlock * D * sizeof(float));
     const uint32_t per_warp = align128(act_bytes) + align128(obs_bytes);
-    unsigned char *wbase = smem + kDepTab * sizeof(float) + (size_t)warp * per_warp;
+    unsigned char *wbase = smem + (size_t)warp * per_warp;
     real *act_s = reinterpret_cast<real *>(wbase);
     float *obs_s = reinterpret_cast<float *>(wbase + align128(act_bytes));
-    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + kDepTab * sizeof(float) + (size_t)wpb * per_warp) + warp;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + (size_t)wpb * per_warp) + warp;
 
-    const long long left = p.n_envs - e0;
-    const int n_valid = left < kBlock ? (int)left : kBlock;
-    const bool bulk = use_bulk && n_valid == kBlock;
+    const int n_valid = min(kBlock, n_envs - e0);
+    const bool bulk = (use_bulk & 1) && n_valid == kBlock;
+    const bool bulk_store = (use_bulk & 2) != 0;             // observation rows leave through the copy engine too
     const bool valid = lane < n_valid;
-    const long long e = e0 + lane;
-    word *spot = p.spot + (size_t)blk * N * (kPlanes * kBlock) + lane;
+    const int e = e0 + lane;
+    word *spot = p.spot + (size_t)blk * (size_t)(N * kPlanes * kBlock) + lane;
 
     if (bulk) {
         if (lane == 0) {
@@ -90,39 +178,53 @@ __global__ void __launch_bounds__(256) step_kernel(const Params<real> p, const r
         }
         __syncwarp();
     }
-    for (int s = 0; s < n_steps; ++s) {
-        const size_t slab = (size_t)s * (size_t)p.n_envs;        // row offset of this step's slab
+#pragma unroll 1
+    for (int s = 0; s < (MULTI ? n_steps : 1); ++s) {
+        const size_t slab = MULTI ? (size_t)s * (size_t)n_envs : 0;   // row offset of this step's slab
         const real *act_g = actions + (slab + (size_t)e0) * A;
         float *obs_g = obs_out + (slab + (size_t)e0) * D;
+        StateRegs<real, NCT> st;
         if (bulk) {
             if (lane == 0) {
-                if (s > 0) bulk_wait_read<0>();                   // the previous obs store has left shared memory
+                if (MULTI && s > 0 && bulk_store) bulk_wait_read<0>();   // the previous obs store has left shared memory
                 mbar_expect_tx(bar, act_bytes);
                 bulk_g2s(act_s, act_g, act_bytes, bar);
             }
-            __syncwarp();
+            if (MULTI) __syncwarp();
+            load_state<real, NCT>(p, e, spot, st);                // state loads fly while the actions arrive
+            mbar_wait(bar, (uint32_t)(s & 1));
         } else {
+#pragma unroll 1
             for (int k = lane; k < n_valid * A; k += 32) act_s[k] = act_g[k];
             __syncwarp();
+            if (valid) load_state<real, NCT>(p, e, spot, st);
         }
-        if (valid) {
-            env_step<real, NCT, ND, EXACT>(p, e, spot, act_s + lane * A, obs_s + lane * D, dep_tab, reward + slab,
-                                           done + slab, [&]() { if (bulk) mbar_wait(bar, (uint32_t)(s & 1)); });
-        }
-        if (bulk) {
+        if (valid)
+            env_step<real, NCT, ND, EXACT, true>(p, e, spot, st, act_s + lane * A, obs_s + lane * D, reward + slab,
+                                                 done + slab);
+        if (bulk && bulk_store) {
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) {
                 bulk_s2g(obs_g, obs_s, obs_bytes);
                 bulk_commit();
             }
+        } else if (bulk) {
+            // 32 rows = 8 * D float4 (16-byte aligned on both sides): coalesced 512-byte warp stores
+            __syncwarp();
+            const float4 *src = reinterpret_cast<const float4 *>(obs_s);
+            float4 *dst = reinterpret_cast<float4 *>(obs_g);
+#pragma unroll 4
+            for (int k = lane; k < 8 * D; k += 32) dst[k] = src[k];
+            if (MULTI) __syncwarp();
         } else {
             __syncwarp();
+#pragma unroll 1
             for (int k = lane; k < n_valid * D; k += 32) obs_g[k] = obs_s[k];
             __syncwarp();
         }
     }
-    if (bulk && lane == 0) bulk_wait_read<0>();   // shared memory must stay valid until the store has read it
+    if (bulk && bulk_store && lane == 0) bulk_wait_read<0>();   // shared memory must stay valid until the store has read it
 }
 
 template <typename real>
@@ -144,7 +246,7 @@ __global__ void __launch_bounds__(256) reset_kernel(const Params<real> p, const 
     if (init || reset_battery) soc_b = p.batt ? p.b_soc0 : (real)0;
     if (p.mode == MODE_SAMPLE) shift = sample_pv_shift(p, p.N, p.gid0 + (unsigned long long)e, episode);
     typename WordOf<real>::type *spot = p.spot + (size_t)(e / kBlock) * p.N * (kPlanes * kBlock) + (size_t)(e % kBlock);
-    begin_episode<real, 0, 0>(p, p.N, e, spot, episode, shift, soc_b, p.obs + (size_t)e * p.D, p.dep_norm);
+    begin_episode<real, 0, 0, false>(p, p.N, e, spot, episode, shift, soc_b, p.obs + (size_t)e * p.D);
     es.soc_b = soc_b;
     es.pv_shift = shift;
     es.ep_ret = 0;
@@ -202,7 +304,7 @@ public:
     bool bound = false, started = false;
     int device = 0;
     int warps_per_cta = 0;   // 0 = auto
-    int use_generic = 0, use_bulk = 1, host_chunks = 0;
+    int use_generic = 0, use_bulk = 1, host_chunks = 0, use_pipeline = 0, ctas_per_sm = 0;
     int num_sms = 148;
     size_t smem_optin = 0;
     void *d_tables = nullptr;
@@ -214,7 +316,7 @@ public:
     {
         cfg = c;
         device = dev;
-        if (c.n_spots < 1 || c.n_spots > SNG_MAX_SPOTS || c.n_steps < 1 || c.n_envs < 1 ||
+        if (c.n_spots < 1 || c.n_spots > SNG_MAX_SPOTS || c.n_steps < 1 || c.n_envs < 1 || c.n_envs > (1ll << 30) ||
             c.n_steps + (int)(4.0 / c.dt) > 250 ||
             c.table_len < c.n_steps + c.horizon || c.table_len > SNG_MAX_TABLE || !c.price || !c.price_norm ||
             (c.pv && (!c.pv_power || !c.irr_norm)) || c.penalty_mode < 0 || c.penalty_mode > 3 || c.horizon < 0) {
@@ -399,26 +501,23 @@ public:
 
     static bool aligned16(const void *q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; }
 
-    // Launch geometry of step_kernel: warps per CTA so that a CTA's shared memory fits, and the
-    // dynamic shared memory size.
-    int geometry(int &wpb, size_t &smem) const
+    size_t row_bytes(int stages) const
     {
-        const size_t per_warp = align128((uint32_t)(kBlock * p.A * sizeof(real))) + align128((uint32_t)(kBlock * p.D * sizeof(float)));
-        const size_t fixed = kDepTab * sizeof(float);
-        wpb = warps_per_cta > 0 ? warps_per_cta : 4;
-        while (wpb > 1 && fixed + (size_t)wpb * (per_warp + 8) > smem_optin) wpb >>= 1;
-        smem = fixed + (size_t)wpb * (per_warp + 8);
-        return smem <= smem_optin ? SNG_OK : SNG_ERR_UNSUPPORTED;
+        return (size_t)stages * align128((uint32_t)(kBlock * p.A * sizeof(real))) + align128((uint32_t)(kBlock * p.D * sizeof(float)));
     }
+    static constexpr size_t kStaticSmem = kDepTab * sizeof(float);
 
     template <int NCT, int ND>
-    int launch_step_n(const Params<real> &q, const real *actions, float *obs, real *reward, uint8_t *done, int n_steps,
+    int launch_simple(const Params<real> &q, const real *actions, float *obs, real *reward, uint8_t *done, int n_steps,
                       int bulk, cudaStream_t st)
     {
-        int wpb;
-        size_t smem;
-        if (geometry(wpb, smem) != SNG_OK) { error = "step kernel: one warp's action/observation rows do not fit in shared memory"; return SNG_ERR_UNSUPPORTED; }
-        auto kern = step_kernel<real, NCT, ND, EXACT>;
+        const size_t per_warp = row_bytes(1) + 8;
+        int wpb = warps_per_cta > 0 ? warps_per_cta : 2;
+        if (wpb * 32 > SNG_STEP_MAXT) wpb = SNG_STEP_MAXT / 32;
+        while (wpb > 1 && kStaticSmem + (size_t)wpb * per_warp > smem_optin) wpb >>= 1;
+        const size_t smem = (size_t)wpb * per_warp;
+        if (kStaticSmem + smem > smem_optin) { error = "step kernel: one warp's action/observation rows do not fit in shared memory"; return SNG_ERR_UNSUPPORTED; }
+        auto kern = n_steps > 1 ? step_simple_kernel<real, NCT, ND, EXACT, true> : step_simple_kernel<real, NCT, ND, EXACT, false>;
         SNG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const long long blocks = (q.n_envs + kBlock - 1) / kBlock;
         const unsigned grid = (unsigned)((blocks + wpb - 1) / wpb);
@@ -428,12 +527,55 @@ public:
         return SNG_OK;
     }
 
+    // Persistent pipelined kernel over the full 32-env blocks of q; returns SNG_ERR_UNSUPPORTED (without
+    // launching) when a warp's stages do not fit in shared memory.
+    template <int NCT, int ND> int launch_pipelined(const Params<real> &q, long long n_blocks, cudaStream_t st)
+    {
+        const size_t per_warp = row_bytes(2) + 16;
+        int wpb = warps_per_cta > 0 ? warps_per_cta : 2;
+        if (wpb * 32 > SNG_PIPE_THREADS) wpb = SNG_PIPE_THREADS / 32;
+        const size_t smem = (size_t)wpb * per_warp;
+        if (kStaticSmem + smem > smem_optin) return SNG_ERR_UNSUPPORTED;
+        auto kern = step_pipelined_kernel<real, NCT, ND, EXACT>;
+        SNG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = 0;
+        SNG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, wpb * 32, smem));
+        if (per_sm < 1) return SNG_ERR_UNSUPPORTED;
+        if (ctas_per_sm > 0 && per_sm > ctas_per_sm) per_sm = ctas_per_sm;
+        long long grid = (long long)num_sms * per_sm;
+        const long long need = (n_blocks + wpb - 1) / wpb;
+        if (grid > need) grid = need;
+        kern<<<(unsigned)grid, wpb * 32, smem, st>>>(q, n_blocks);
+        ++launches;
+        SNG_CUDA(cudaGetLastError());
+        return SNG_OK;
+    }
+
+    template <int NCT, int ND>
+    int launch_step_n(const Params<real> &q, const real *actions, float *obs, real *reward, uint8_t *done, int n_steps,
+                      int bulk, cudaStream_t st)
+    {
+        if (bulk && use_pipeline && n_steps == 1 && q.n_envs >= kBlock && actions == q.actions && obs == q.obs &&
+            reward == q.reward && done == q.done) {
+            const long long n_blocks = q.n_envs / kBlock;
+            const int rc = launch_pipelined<NCT, ND>(q, n_blocks, st);
+            if (rc == SNG_OK) {
+                const long long e0 = n_blocks * kBlock;
+                if (e0 == q.n_envs) return SNG_OK;
+                const Params<real> tail = slice_of(q, e0, q.n_envs - e0);   // ragged last block
+                return launch_simple<NCT, ND>(tail, tail.actions, tail.obs, tail.reward, tail.done, 1, 0, st);
+            }
+            if (rc != SNG_ERR_UNSUPPORTED) return rc;
+        }
+        return launch_simple<NCT, ND>(q, actions, obs, reward, done, n_steps, bulk, st);
+    }
+
     // q: parameters (possibly of a slice of envs starting at a multiple of 32)
     int launch_step(const Params<real> &q, const real *actions, float *obs, real *reward, uint8_t *done, int n_steps,
                     cudaStream_t st)
     {
         // the copy engine needs 16-byte aligned row slabs: bases aligned and, for rollouts, slab strides too
-        int bulk = use_bulk && aligned16(actions) && aligned16(obs);
+        int bulk = (aligned16(actions) && aligned16(obs)) ? use_bulk : 0;
         if (n_steps > 1 && (((size_t)q.n_envs * q.A * sizeof(real)) % 16 != 0 || ((size_t)q.n_envs * q.D * sizeof(float)) % 16 != 0))
             bulk = 0;
         if constexpr (EXACT) {
@@ -471,20 +613,21 @@ public:
     }
 
     // Parameters with every per-env pointer advanced by e0 envs (e0 a multiple of 32).
-    Params<real> slice_params(long long e0, long long n) const
+    static Params<real> slice_of(const Params<real> &src, long long e0, long long n)
     {
-        Params<real> q = p;
+        Params<real> q = src;
         q.n_envs = n;
-        q.gid0 = p.gid0 + (unsigned long long)e0;
-        q.actions += (size_t)e0 * p.A; q.obs += (size_t)e0 * p.D; q.reward += e0; q.done += e0;
-        if (q.tobs) q.tobs += (size_t)e0 * p.D;
-        q.spot += (size_t)e0 * p.N * kPlanes; q.envst += e0;
-        if (q.plan) q.plan += (size_t)e0 * p.N * kMaxVehicles;
+        q.gid0 = src.gid0 + (unsigned long long)e0;
+        q.actions += (size_t)e0 * src.A; q.obs += (size_t)e0 * src.D; q.reward += e0; q.done += e0;
+        if (q.tobs) q.tobs += (size_t)e0 * src.D;
+        q.spot += (size_t)e0 * src.N * kPlanes; q.envst += e0;
+        if (q.plan) q.plan += (size_t)e0 * src.N * kMaxVehicles;
         if (q.err) q.err += e0;
         if (q.diag) q.diag += (size_t)e0 * D_COUNT;
         if (q.last_ret) q.last_ret += e0;
         return q;
     }
+    Params<real> slice_params(long long e0, long long n) const { return slice_of(p, e0, n); }
 
     // The gym-facing call with host buffers.  The batch is cut into chunks of envs that flow through
     // a three-stage pipeline on three streams (H2D actions | step kernel | D2H obs/reward/done), so the
@@ -581,6 +724,13 @@ public:
         }
         if (hc < 0 || hc > 64) { error = "sng_set_tuning: host_chunks must be in 0..64"; return SNG_ERR_ARG; }
         warps_per_cta = w; use_generic = g; use_bulk = b; host_chunks = hc;
+        return SNG_OK;
+    }
+
+    int set_pipeline(int up, int cps) override
+    {
+        if (cps < 0) { error = "sng_set_pipeline: bad arguments"; return SNG_ERR_ARG; }
+        use_pipeline = up; ctas_per_sm = cps;
         return SNG_OK;
     }
 };

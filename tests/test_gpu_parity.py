@@ -228,16 +228,19 @@ def test_sampler_matches_cpu_mirror_bit_exact():
     dict(number_of_chargers=7),
 ])
 def test_kernel_variants_are_bit_identical(kw):
-    """The specialised (compile-time N) and the generic kernel, the copy-engine and the plain-load staging
-    of action / observation rows, and every CTA shape run the same per-env body: outputs and state are
-    bit-identical, including the ragged last block (E not a multiple of 32)."""
+    """The persistent pipelined and the one-block-per-warp kernel, the specialised (compile-time N) and the
+    generic instantiation, the copy-engine and the plain-load staging of action / observation rows, and
+    every CTA shape run the same per-env body: outputs and state are bit-identical, including the ragged
+    last block (E not a multiple of 32)."""
     E = 5 * 256 + 104 + 13
-    variants = [dict(), dict(use_generic_kernel=1), dict(use_bulk_copy=0), dict(warps_per_cta=1),
-                dict(warps_per_cta=8, use_generic_kernel=1, use_bulk_copy=0)]
+    variants = [(dict(), dict()), (dict(use_generic_kernel=1), dict()), (dict(use_bulk_copy=0), dict()),
+                (dict(warps_per_cta=1), dict(use_pipelined_kernel=1, ctas_per_sm=1)), (dict(), dict(use_pipelined_kernel=1)),
+                (dict(warps_per_cta=4, use_generic_kernel=1), dict(use_pipelined_kernel=1))]
     envs = []
-    for v in variants:
+    for tune, pipe in variants:
         env = _env(E, "float32", seed=21, **kw)
-        env.set_tuning(**v)
+        env.set_tuning(**tune)
+        env.set_pipeline(**pipe)
         env.reset()
         envs.append(env)
     g = torch.Generator(device="cuda:0").manual_seed(3)
