@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- batched env-steps/sec of the nanogrid step on B200 (BASELINE.json metric).
 
-    python bench.py --gpus 1 --steps 240 --warmup 24
+    python bench.py --gpus 1 --steps 2400 --warmup 240
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
     python bench.py --impl reference            # the CPU restatement of the reference on the host cores
 
@@ -9,8 +9,9 @@ Workload (BASELINE config 4 per GPU): N = 10 charging spots, PV + battery, bound
 steps (24 per episode), fused step + auto-reset + in-kernel Philox schedule sampling,
 `--envs` environments per GPU (default 1,048,576: the working set of one step, ~0.4 GB, is larger
 than the 126 MB L2, so no flush is needed between iterations).  One "step" = one sng_step launch
-over all envs of the rank.  Envs shard trivially: rank r owns global env ids [r*E, (r+1)*E) and
-there is no collective on the step path (scaling = weak).
+over all envs of the rank (the launches of one episode are captured in a CUDA graph and replayed,
+`--graph-steps 0` launches them one by one).  Envs shard trivially: rank r owns global env ids
+[r*E, (r+1)*E) and there is no collective on the step path (scaling = weak).
 """
 import argparse
 import json
@@ -70,7 +71,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:  # noqa: BLE001
             self.proc = None
@@ -194,8 +195,9 @@ def run_reference_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=240)
-    ap.add_argument("--warmup", type=int, default=24)
+    ap.add_argument("--steps", type=int, default=2400)
+    ap.add_argument("--warmup", type=int, default=240)
+    ap.add_argument("--graph-steps", type=int, default=24, help="steps per captured CUDA graph (0 = plain launches)")
     ap.add_argument("--envs", type=int, default=1048576, help="environments per GPU")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--ref-envs", type=int, default=65536, help="sample size of the CPU reference arm")
@@ -245,8 +247,35 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    for _ in range(args.warmup):
+    for _ in range(min(args.warmup, 24)):
         env.step(actions)
+    barrier()
+
+    # one episode's worth of launches captured in a CUDA graph (removes the Python / driver launch cost
+    # from the timed region; the kernels and their work are unchanged)
+    gsteps = args.graph_steps if args.graph_steps > 0 and args.steps % max(args.graph_steps, 1) == 0 else 0
+    graph = None
+    if gsteps:
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                env.step(actions)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            for _ in range(gsteps):
+                env.step(actions)
+
+    def run_steps(n):
+        if graph is None:
+            for _ in range(n):
+                env.step(actions)
+        else:
+            for _ in range(n // gsteps):
+                graph.replay()
+
+    run_steps(max(args.warmup - 24, gsteps or 1) // (gsteps or 1) * (gsteps or 1))
     barrier()
 
     # ---- device-resident throughput: K launches bracketed by CUDA events on the launching stream ----
@@ -256,12 +285,11 @@ def main():
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record()
-    for _ in range(args.steps):
-        env.step(actions)
+    run_steps(args.steps)
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1)
-    launches = env.launch_count - launches0
+    launches = args.steps if graph is not None else env.launch_count - launches0
     clocks = sampler.stop()
     t = torch.tensor([ms], device=dev, dtype=torch.float64)
     if world > 1:
@@ -292,11 +320,8 @@ def main():
     d2h = o_h.numel() * 4 + r_h.numel() * 4 + d_h.numel()
 
     # ---- optional episode-return statistics: the only collective, off the step path ----
-    stats = torch.stack([env.last_return.double().sum(), (env.last_return.double() ** 2).sum(),
-                         torch.tensor(float(E), device=dev, dtype=torch.float64)])
-    if world > 1:
-        dist.all_reduce(stats)
-    mean_ret = float(stats[0] / stats[2])
+    from smart_nanogrid_gym_b200.sharding import ReturnStats
+    mean_ret = ReturnStats.from_returns(env.last_return).all_reduce(device=dev).mean
 
     if rank == 0:
         bytes_step = algorithmic_bytes_per_env_step(cfg.n_spots, int(cfg.batt), int(cfg.pv))
@@ -311,6 +336,7 @@ def main():
                                    "24-step episodes, %d envs per GPU" % E,
                        "envs_per_gpu": E, "total_envs": total_envs, "parallelism": "env-sharded x%d, no collective" % n_gpus,
                        "l2": "inputs larger than L2 (%.0f MB touched per step), no flush" % (bytes_step * E / 1e6),
+                       "launch": ("CUDA graph of %d step launches, replayed" % gsteps) if graph is not None else "one launch per step",
                        "mean_episode_return": mean_ret},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": args.e2e_steps, "path": "sng_step_host: pinned host buffers, H2D + step + D2H + sync"},

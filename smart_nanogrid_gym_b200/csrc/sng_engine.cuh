@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <string>
 #include <type_traits>
 #include <vector>
@@ -501,6 +502,17 @@ public:
 
     static bool aligned16(const void *q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; }
 
+    // cudaFuncSetAttribute once per (kernel, size) instead of on every launch
+    std::map<const void *, size_t> smem_set;
+    int ensure_smem(const void *kern, size_t smem)
+    {
+        auto it = smem_set.find(kern);
+        if (it != smem_set.end() && it->second == smem) return SNG_OK;
+        SNG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_set[kern] = smem;
+        return SNG_OK;
+    }
+
     size_t row_bytes(int stages) const
     {
         return (size_t)stages * align128((uint32_t)(kBlock * p.A * sizeof(real))) + align128((uint32_t)(kBlock * p.D * sizeof(float)));
@@ -518,7 +530,8 @@ public:
         const size_t smem = (size_t)wpb * per_warp;
         if (kStaticSmem + smem > smem_optin) { error = "step kernel: one warp's action/observation rows do not fit in shared memory"; return SNG_ERR_UNSUPPORTED; }
         auto kern = n_steps > 1 ? step_simple_kernel<real, NCT, ND, EXACT, true> : step_simple_kernel<real, NCT, ND, EXACT, false>;
-        SNG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int rc = ensure_smem((const void *)kern, smem);
+        if (rc) return rc;
         const long long blocks = (q.n_envs + kBlock - 1) / kBlock;
         const unsigned grid = (unsigned)((blocks + wpb - 1) / wpb);
         kern<<<grid, wpb * 32, smem, st>>>(q, actions, obs, reward, done, n_steps, bulk);
@@ -537,7 +550,8 @@ public:
         const size_t smem = (size_t)wpb * per_warp;
         if (kStaticSmem + smem > smem_optin) return SNG_ERR_UNSUPPORTED;
         auto kern = step_pipelined_kernel<real, NCT, ND, EXACT>;
-        SNG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int rc0 = ensure_smem((const void *)kern, smem);
+        if (rc0) return rc0;
         int per_sm = 0;
         SNG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, wpb * 32, smem));
         if (per_sm < 1) return SNG_ERR_UNSUPPORTED;

@@ -300,6 +300,37 @@ def test_zero_copy_out_buffers_and_state_dict():
     env.close()
 
 
+def test_step_is_cuda_graph_capturable():
+    """sng_step makes no hidden allocation or synchronisation: an episode of steps captured in a CUDA graph
+    and replayed equals the same steps launched one by one."""
+    E = 4096
+    a_env = _env(E, "float32", number_of_chargers=10, seed=13)
+    b_env = _env(E, "float32", number_of_chargers=10, seed=13)
+    a_env.reset()
+    b_env.reset()
+    g = torch.Generator(device="cuda:0").manual_seed(6)
+    acts = torch.stack([a_env.sample_actions(g) for _ in range(24)])
+    cur = torch.zeros_like(acts[0])
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        b_env.step(cur)                       # warm-up outside capture (first-launch attribute setup)
+    torch.cuda.current_stream().wait_stream(side)
+    b_env.reset(seed=13)
+    b_env.load_state_dict(a_env.state_dict())
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        o_g, r_g, d_g, _, _ = b_env.step(cur)
+    for s in range(24):
+        o, r, d, _, _ = a_env.step(acts[s])
+        cur.copy_(acts[s])
+        graph.replay()
+        assert torch.equal(o, o_g) and torch.equal(r, r_g) and torch.equal(d, d_g), s
+    assert torch.equal(a_env._spot, b_env._spot) and torch.equal(a_env._envst, b_env._envst)
+    a_env.close()
+    b_env.close()
+
+
 def test_shard_equivalence():
     """Env e of a 2-way split equals env e of the unsplit batch (streams keyed by global env id)."""
     E = 600
