@@ -24,8 +24,17 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-ENV_KW = dict(number_of_chargers=10, charging_mode="bounded", vehicle_uncharged_penalty_mode="sparse",
-              time_interval="1h")
+WORKLOADS = {
+    # BASELINE config 4 (the configuration the metric is quoted on), per GPU
+    "c4": dict(kw=dict(number_of_chargers=10, charging_mode="bounded", vehicle_uncharged_penalty_mode="sparse",
+                       time_interval="1h"), envs=1048576,
+               name="C4: fused step + auto-reset + in-kernel EV schedule sampling, N=10 spots, PV+battery, 24-step episodes"),
+    # BASELINE config 5 (an extension: the reference cannot run 15-minute steps)
+    "c5": dict(kw=dict(number_of_chargers=64, charging_mode="bounded", vehicle_uncharged_penalty_mode="sparse",
+                       time_interval="15min"), envs=262144,
+               name="C5: scaled station, N=64 spots, 15-min steps (96 per episode), PV+battery, fused step + auto-reset + sampling"),
+}
+ENV_KW = WORKLOADS["c4"]["kw"]
 METRIC = "batched env-steps/sec"
 UNIT = "env-steps/s"
 
@@ -216,14 +225,15 @@ def main():
     ap.add_argument("--steps", type=int, default=2400)
     ap.add_argument("--warmup", type=int, default=240)
     ap.add_argument("--graph-steps", type=int, default=24, help="steps per captured CUDA graph (0 = plain launches)")
-    ap.add_argument("--envs", type=int, default=1048576, help="environments per GPU")
+    ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
+    ap.add_argument("--envs", type=int, default=0, help="environments per GPU (0 = the workload's size)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--ref-envs", type=int, default=65536, help="sample size of the CPU reference arm")
     ap.add_argument("--cpu-seconds", type=float, default=10.0, help="wall time of the cpu_baseline leg")
     ap.add_argument("--e2e-steps", type=int, default=24)
     ap.add_argument("--warps", type=int, default=0, help="tuning: warps (blocks of 32 envs) per CTA (0 = auto)")
     ap.add_argument("--generic", action="store_true", help="tuning: use the generic runtime-N kernel")
-    ap.add_argument("--bulk", type=int, default=1, help="tuning: 0 plain loads/stores, 1 copy-engine action loads + vector obs stores, 3 copy engine both ways")
+    ap.add_argument("--bulk", type=int, default=1, help="tuning: row staging: -1 scalar, 0 vector loads/stores, 1 copy-engine loads + vector stores, 3 copy engine both ways")
     ap.add_argument("--host-chunks", type=int, default=0, help="tuning: env chunks of the pipelined host path")
     ap.add_argument("--pipeline", action="store_true", help="tuning: persistent pipelined kernel instead of one block per warp")
     ap.add_argument("--ctas", type=int, default=0, help="tuning: cap on resident CTAs per SM (pipelined kernel)")
@@ -249,9 +259,10 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
 
-    E = args.envs
+    wl = WORKLOADS[args.workload]
+    E = args.envs or wl["envs"]
     env = BatchedSmartNanogridEnv(E, device=dev, seed=0, env_gid0=rank * E, precision="float32", auto_reset=True,
-                                  **ENV_KW)
+                                  **wl["kw"])
     env.set_tuning(args.warps, int(args.generic), args.bulk, args.host_chunks)
     env.set_pipeline(1 if args.pipeline else 0, args.ctas)
     cfg = env.cfg
@@ -350,8 +361,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "C4: fused step + auto-reset + in-kernel EV schedule sampling, N=10 spots, PV+battery, "
-                                   "24-step episodes, %d envs per GPU" % E,
+            "config": {"workload": "%s, %d envs per GPU" % (wl["name"], E),
                        "envs_per_gpu": E, "total_envs": total_envs, "parallelism": "env-sharded x%d, no collective" % n_gpus,
                        "l2": "inputs larger than L2 (%.0f MB touched per step), no flush" % (bytes_step * E / 1e6),
                        "launch": ("CUDA graph of %d step launches, replayed" % gsteps) if graph is not None else "one launch per step",

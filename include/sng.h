@@ -179,9 +179,11 @@ int sng_error_flags(sng_env *env, uint32_t *host_out, void *stream);
 int64_t sng_launch_count(const sng_env *env);
 
 /* Tuning knobs for experiments and tests: warps (= blocks of 32 envs) per CTA (0 = auto); force the
- * generic runtime-N kernel instead of the specialised one; stage action / observation rows with the
- * copy engine (1, default) or with plain loads / stores (0); number of env chunks sng_step_host
- * pipelines over PCIe (0 = auto). */
+ * generic runtime-N kernel instead of the specialised one; how action / observation rows are staged
+ * through shared memory when the buffers are 16-byte aligned: -1 scalar loads / stores, 0 coalesced
+ * 16-byte vector loads / stores, 1 copy-engine (cp.async.bulk) loads + vector stores, 3 copy engine
+ * both ways (unaligned buffers and a partial last block always take the scalar path); number of env
+ * chunks sng_step_host pipelines over PCIe (0 = auto). */
 int sng_set_tuning(sng_env *env, int warps_per_cta, int use_generic_kernel, int use_bulk_copy, int host_chunks);
 /* Tuning knob: use the persistent software-pipelined step kernel (1) or the one-block-per-warp kernel
  * (0, default: it measured faster); cap on resident CTAs per SM of the pipelined kernel

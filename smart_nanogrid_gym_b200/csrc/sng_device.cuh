@@ -393,11 +393,19 @@ __device__ __noinline__ PowerSoc<real> discharge_vehicle(real power, real dt, re
 // NCT: number of spots at compile time (0 = runtime p.N); ND: see Offsets.  EXACT (double only):
 // reproduces numpy's summation order of the station power sums.
 // ------------------------------------------------------------------------------------------
-template <typename real, int NCT, int ND, bool EXACT, bool SMEM>
-__device__ __forceinline__ void env_step(const Params<real> &p, long long e, typename WordOf<real>::type *spot,
-                                         const StateRegs<real, NCT> &st, const real *act, float *obs,
-                                         real *reward_out, uint8_t *done_out)
+// What a thread hands to the warp-cooperative admission of arriving vehicles (admit_arrivals_warp).
+struct Arrivals {
+    uint32_t mask;      // spots of this env whose next vehicle arrives at tn (0 on the last step of the day)
+    uint32_t episode;
+    int tn;
+};
+
+template <typename real, int NCT, int ND, bool EXACT, bool SMEM, bool COOP = false>
+__device__ __forceinline__ Arrivals env_step(const Params<real> &p, long long e, typename WordOf<real>::type *spot,
+                                             const StateRegs<real, NCT> &st, const real *act, float *obs,
+                                             real *reward_out, uint8_t *done_out)
 {
+    static_assert(!COOP || (NCT > 0 && NCT <= 32), "cooperative admission needs a 32-bit arrival mask");
     typedef typename WordOf<real>::type word;
     const int N = NCT ? NCT : p.N;
     constexpr int CH = Chunk<NCT>::value;
@@ -577,9 +585,14 @@ __device__ __forceinline__ void env_step(const Params<real> &p, long long e, typ
     // ---- t += 1, termination, auto-reset (...environment.py:174-181, 311-351) ----
     real ep_ret = es.ep_ret + reward;
     real shift = es.pv_shift;
+    Arrivals out;
+    out.mask = (COOP && !is_done) ? (uint32_t)arrivals : 0u;
+    out.episode = episode;
+    out.tn = tn;
     if (!is_done) {
-        // admit the vehicles that arrive at tn (the observation above does not show them: quirk Q5)
-        while (arrivals) {
+        // admit the vehicles that arrive at tn (the observation above does not show them: quirk Q5);
+        // COOP: left to admit_arrivals_warp(), which spreads the warp's arrivals evenly over its lanes
+        while (!COOP && arrivals) {
             const int i = (NCT > 32) ? __ffsll((long long)arrivals) - 1 : __ffs((int)arrivals) - 1;
             arrivals &= arrivals - 1;
             store_vehicle<real>(spot + (size_t)i * SP, fetch_vehicle(p, N, e, i, episode, tn));
@@ -606,6 +619,47 @@ __device__ __forceinline__ void env_step(const Params<real> &p, long long e, typ
     reward_out[e] = reward;
     done_out[e] = is_done ? 1 : 0;
     if (err && p.err) atomicOr(p.err + e, err);
+    return out;
+}
+
+// Warp-cooperative admission of the vehicles arriving at the next step.  Each lane (= env) holds a
+// mask of its arriving spots; a lane may have 0..N of them while the warp has ~1.25 per env, so letting
+// every lane work through its own list costs max-over-lanes Philox rounds (~3.3 at N = 10).  Instead the
+// arrivals of the whole 32-env block are compacted into a shared-memory queue (prefix sum over the
+// lanes) and dealt out 32 at a time: ceil(total / 32) rounds (~1.9).  Any lane can admit any (env, spot)
+// of the block: the vehicle is a pure function of (seed, global env, spot, episode, step) and its state
+// words live at block_spot[(spot * 3 + plane) * 32 + env_lane].
+// All 32 lanes must call this (lanes without a valid env pass mask = 0); queue holds 32 * N entries.
+template <typename real, int NCT>
+__device__ __forceinline__ void admit_arrivals_warp(const Params<real> &p, long long e0, int lane,
+                                                    typename WordOf<real>::type *block_spot, const Arrivals &a,
+                                                    uint16_t *queue)
+{
+    constexpr uint32_t FULL = 0xffffffffu;
+    const int cnt = __popc(a.mask);
+    int incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int v = __shfl_up_sync(FULL, incl, d);
+        if (lane >= d) incl += v;
+    }
+    const int total = __shfl_sync(FULL, incl, 31);
+    if (total == 0) return;                       // warp-uniform
+    int pos = incl - cnt;
+    for (uint32_t m = a.mask; m; m &= m - 1) queue[pos++] = (uint16_t)((lane << 8) | (__ffs((int)m) - 1));
+    __syncwarp();
+    for (int base = 0; base < total; base += 32) {
+        const int idx = base + lane;
+        const bool mine = idx < total;
+        const uint32_t ev = mine ? queue[idx] : 0u;
+        const int src = (int)(ev >> 8), i = (int)(ev & 0xFFu);
+        const uint32_t episode = __shfl_sync(FULL, a.episode, src);
+        const int tn = __shfl_sync(FULL, a.tn, src);
+        if (mine)
+            store_vehicle<real>(block_spot + (size_t)i * (kPlanes * kBlock) + src,
+                                fetch_vehicle(p, NCT, e0 + src, i, episode, tn));
+    }
+    __syncwarp();                                 // the queue may be refilled by the next step
 }
 
 }  // namespace sng

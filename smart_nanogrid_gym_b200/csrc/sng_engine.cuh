@@ -57,8 +57,7 @@ EngineBase *make_engine_f64(const sng_config &cfg, int device, std::string &err)
 //                          rows into the other shared-memory stage, so DRAM never waits for the math.
 //   step_simple_kernel     one block per warp, no pipelining; any n_steps (the rollout: the same warp
 //                          advances its envs n_steps times, one action / obs / reward / done slab per
-//                          step), partial last block, and a plain load / store staging path for
-//                          buffers the copy engine cannot address (16-byte alignment) or use_bulk == 0.
+//                          step), partial last block, and every row-staging mode (STAGE_*).
 // ------------------------------------------------------------------------------------------
 template <typename real> __device__ __forceinline__ void publish_dep_table(const Params<real> &p)
 {
@@ -142,20 +141,28 @@ __global__ void __launch_bounds__(SNG_PIPE_THREADS, SNG_PIPE_MINB)
 #ifndef SNG_STEP_MINB
 #define SNG_STEP_MINB 8
 #endif
+// Row staging modes (kernel argument `mode`): how the 32 action rows reach shared memory and the 32
+// observation rows leave it.
+enum : int {
+    STAGE_SCALAR = 0,     // plain 4-byte loads / stores: unaligned buffers; always used for a partial last block
+    STAGE_TMA_LOAD = 1,   // actions: one cp.async.bulk per warp (mbarrier complete_tx)
+    STAGE_TMA_STORE = 2,  // observations: one cp.async.bulk per warp (bulk_group)
+    STAGE_ALIGNED = 4     // buffers are 16-byte aligned: 16-byte coalesced vector loads / stores where no TMA bit is set
+};
+
 // MULTI: n_steps > 1 (rollout); the single-step instantiation carries no slab arithmetic.
 template <typename real, int NCT, int ND, bool EXACT, bool MULTI>
 __global__ void __launch_bounds__(SNG_STEP_MAXT, EXACT ? 1 : SNG_STEP_MINB)
     step_simple_kernel(const Params<real> p, const real *actions, float *obs_out, real *reward, uint8_t *done, int n_steps,
-                       int use_bulk)
+                       int mode)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     typedef typename WordOf<real>::type word;
-    publish_dep_table(p);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     const int n_envs = (int)p.n_envs;                            // a handle owns < 2^31 envs (sng_create)
     const int blk = blockIdx.x * wpb + warp;                     // state block = 32 envs
     const int e0 = blk * kBlock;
-    if (e0 >= n_envs) return;
+    const bool active = e0 < n_envs;                             // warp-uniform; idle warps only join the CTA barrier
     const int N = NCT ? NCT : p.N;
     const int A = p.A, D = p.D;
     const uint32_t act_bytes = (uint32_t)(kBlock * A * sizeof(real)), obs_bytes = (uint32_t)(kBlock * D * sizeof(float));
@@ -164,53 +171,85 @@ __global__ void __launch_bounds__(SNG_STEP_MAXT, EXACT ? 1 : SNG_STEP_MINB)
     real *act_s = reinterpret_cast<real *>(wbase);
     float *obs_s = reinterpret_cast<float *>(wbase + align128(act_bytes));
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem + (size_t)wpb * per_warp) + warp;
+    constexpr bool COOP = !EXACT && NCT > 0 && NCT <= 16;         // warp-cooperative admission of arriving vehicles
+    // its queue reuses the action stage: every lane is done with its action row when the admission starts
+    // (the warp-wide shuffles at its top are the barrier), and 32 * N * 2 B <= 32 * A * sizeof(real)
+    uint16_t *queue = reinterpret_cast<uint16_t *>(act_s);
 
-    const int n_valid = min(kBlock, n_envs - e0);
-    const bool bulk = (use_bulk & 1) && n_valid == kBlock;
-    const bool bulk_store = (use_bulk & 2) != 0;             // observation rows leave through the copy engine too
+    const int n_valid = active ? min(kBlock, n_envs - e0) : 0;
+    const bool full = n_valid == kBlock;
+    const bool tma_load = full && (mode & STAGE_TMA_LOAD), tma_store = full && (mode & STAGE_TMA_STORE);
+    const bool vec = full && (mode & STAGE_ALIGNED);
     const bool valid = lane < n_valid;
     const int e = e0 + lane;
     word *spot = p.spot + (size_t)blk * (size_t)(N * kPlanes * kBlock) + lane;
+    // float4 per lane of a block's action rows held in registers by the vector path (specialised kernels)
+    constexpr int AV = (NCT && sizeof(real) == 4) ? (NCT + 1 + 3) / 4 : 1;
+    const int act_vec = (int)(act_bytes / 16);                    // float4 per block of action rows
 
-    if (bulk) {
-        if (lane == 0) {
-            mbar_init(bar, 1);
-            fence_mbar_init();
-        }
-        __syncwarp();
-    }
 #pragma unroll 1
     for (int s = 0; s < (MULTI ? n_steps : 1); ++s) {
         const size_t slab = MULTI ? (size_t)s * (size_t)n_envs : 0;   // row offset of this step's slab
         const real *act_g = actions + (slab + (size_t)e0) * A;
         float *obs_g = obs_out + (slab + (size_t)e0) * D;
         StateRegs<real, NCT> st;
-        if (bulk) {
+        float4 areg[AV];
+        // ---- put everything this block needs in flight first ----
+        if (tma_load) {
             if (lane == 0) {
-                if (MULTI && s > 0 && bulk_store) bulk_wait_read<0>();   // the previous obs store has left shared memory
+                if (s == 0) {
+                    mbar_init(bar, 1);
+                    fence_mbar_init();
+                }
+                if (MULTI && s > 0 && tma_store) bulk_wait_read<0>();   // the previous obs store has left shared memory
                 mbar_expect_tx(bar, act_bytes);
                 bulk_g2s(act_s, act_g, act_bytes, bar);
             }
+        } else if (vec && NCT && sizeof(real) == 4) {
+#pragma unroll
+            for (int j = 0; j < AV; ++j) {
+                const int k = lane + 32 * j;
+                if (k < act_vec) areg[j] = reinterpret_cast<const float4 *>(act_g)[k];
+            }
+        }
+        if (valid) load_state<real, NCT>(p, e, spot, st);
+        if (s == 0) publish_dep_table(p);     // CTA barrier; also orders the mbarrier init before the other lanes' waits
+        if (!active) return;
+        // ---- action rows into shared memory ----
+        if (tma_load) {
             if (MULTI) __syncwarp();
-            load_state<real, NCT>(p, e, spot, st);                // state loads fly while the actions arrive
             mbar_wait(bar, (uint32_t)(s & 1));
+        } else if (vec) {
+            if (NCT && sizeof(real) == 4) {
+#pragma unroll
+                for (int j = 0; j < AV; ++j) {
+                    const int k = lane + 32 * j;
+                    if (k < act_vec) reinterpret_cast<float4 *>(act_s)[k] = areg[j];
+                }
+            } else {
+#pragma unroll 1
+                for (int k = lane; k < act_vec; k += 32) reinterpret_cast<float4 *>(act_s)[k] = reinterpret_cast<const float4 *>(act_g)[k];
+            }
+            __syncwarp();
         } else {
 #pragma unroll 1
             for (int k = lane; k < n_valid * A; k += 32) act_s[k] = act_g[k];
             __syncwarp();
-            if (valid) load_state<real, NCT>(p, e, spot, st);
         }
+        Arrivals arrivals = {0u, 0u, 0};
         if (valid)
-            env_step<real, NCT, ND, EXACT, true>(p, e, spot, st, act_s + lane * A, obs_s + lane * D, reward + slab,
-                                                 done + slab);
-        if (bulk && bulk_store) {
+            arrivals = env_step<real, NCT, ND, EXACT, true, COOP>(p, e, spot, st, act_s + lane * A, obs_s + lane * D,
+                                                                  reward + slab, done + slab);
+        if (COOP) admit_arrivals_warp<real, NCT>(p, e0, lane, spot - lane, arrivals, queue);
+        // ---- observation rows out of shared memory ----
+        if (tma_store) {
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) {
                 bulk_s2g(obs_g, obs_s, obs_bytes);
                 bulk_commit();
             }
-        } else if (bulk) {
+        } else if (vec) {
             // 32 rows = 8 * D float4 (16-byte aligned on both sides): coalesced 512-byte warp stores
             __syncwarp();
             const float4 *src = reinterpret_cast<const float4 *>(obs_s);
@@ -225,7 +264,7 @@ __global__ void __launch_bounds__(SNG_STEP_MAXT, EXACT ? 1 : SNG_STEP_MINB)
             __syncwarp();
         }
     }
-    if (bulk && bulk_store && lane == 0) bulk_wait_read<0>();   // shared memory must stay valid until the store has read it
+    if (tma_store && lane == 0) bulk_wait_read<0>();   // shared memory must stay valid until the store has read it
 }
 
 template <typename real>
@@ -569,7 +608,7 @@ public:
     int launch_step_n(const Params<real> &q, const real *actions, float *obs, real *reward, uint8_t *done, int n_steps,
                       int bulk, cudaStream_t st)
     {
-        if (bulk && use_pipeline && n_steps == 1 && q.n_envs >= kBlock && actions == q.actions && obs == q.obs &&
+        if ((bulk & STAGE_ALIGNED) && use_pipeline && n_steps == 1 && q.n_envs >= kBlock && actions == q.actions && obs == q.obs &&
             reward == q.reward && done == q.done) {
             const long long n_blocks = q.n_envs / kBlock;
             const int rc = launch_pipelined<NCT, ND>(q, n_blocks, st);
@@ -588,10 +627,12 @@ public:
     int launch_step(const Params<real> &q, const real *actions, float *obs, real *reward, uint8_t *done, int n_steps,
                     cudaStream_t st)
     {
-        // the copy engine needs 16-byte aligned row slabs: bases aligned and, for rollouts, slab strides too
-        int bulk = (aligned16(actions) && aligned16(obs)) ? use_bulk : 0;
+        // the copy engine and the 16-byte vector path need aligned row slabs: bases aligned and, for rollouts,
+        // slab strides too; otherwise every block is staged with scalar accesses
+        bool aligned = aligned16(actions) && aligned16(obs);
         if (n_steps > 1 && (((size_t)q.n_envs * q.A * sizeof(real)) % 16 != 0 || ((size_t)q.n_envs * q.D * sizeof(float)) % 16 != 0))
-            bulk = 0;
+            aligned = false;
+        const int bulk = (aligned && use_bulk >= 0) ? (STAGE_ALIGNED | (use_bulk & 3)) : STAGE_SCALAR;
         if constexpr (EXACT) {
             return launch_step_n<0, 0>(q, actions, obs, reward, done, n_steps, bulk, st);
         } else {

@@ -234,6 +234,7 @@ def test_kernel_variants_are_bit_identical(kw):
     last block (E not a multiple of 32)."""
     E = 5 * 256 + 104 + 13
     variants = [(dict(), dict()), (dict(use_generic_kernel=1), dict()), (dict(use_bulk_copy=0), dict()),
+                (dict(use_bulk_copy=-1), dict()), (dict(use_bulk_copy=3), dict()), (dict(use_bulk_copy=1, use_generic_kernel=1), dict()),
                 (dict(warps_per_cta=1), dict(use_pipelined_kernel=1, ctas_per_sm=1)), (dict(), dict(use_pipelined_kernel=1)),
                 (dict(warps_per_cta=4, use_generic_kernel=1), dict(use_pipelined_kernel=1))]
     envs = []
