@@ -146,6 +146,32 @@ def cpu_port_throughput(n_envs, seconds, threads):
     return n_envs * steps / el, el, steps
 
 
+def rollout_leg(env, n_steps, dev):
+    """BASELINE config 3: policy in the loop.  Reported beside the headline, not as it."""
+    import torch
+    from smart_nanogrid_gym_b200.rollout import MlpPolicy, RolloutBuffer, collect_rollout
+    torch.manual_seed(0)
+    policy = MlpPolicy(env.cfg.obs_dim, env.cfg.act_dim).to(dev)
+    buf = RolloutBuffer(n_steps, env.num_envs, env.cfg.obs_dim, env.cfg.act_dim, dev)
+    g = torch.Generator(device=dev).manual_seed(0)
+    obs = env.reset()
+    starts = torch.ones(env.num_envs, dtype=torch.uint8, device=dev)
+    for _ in range(2):
+        obs, starts = collect_rollout(env, policy, buf, obs, starts, generator=g)
+    torch.cuda.synchronize(dev)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 5
+    ev0.record()
+    for _ in range(reps):
+        obs, starts = collect_rollout(env, policy, buf, obs, starts, generator=g)
+    ev1.record()
+    torch.cuda.synchronize(dev)
+    ms = ev0.elapsed_time(ev1)
+    return {"value": env.num_envs * n_steps * reps / (ms * 1e-3), "unit": UNIT, "n_steps": n_steps, "envs": env.num_envs,
+            "policy": "tanh MLP %d-64-64-%d (torch), actions clipped to the Box, GAE by sng_gae" % (env.cfg.obs_dim, env.cfg.act_dim),
+            "mean_step_reward": float(buf.rewards.mean())}
+
+
 def run_reference_arm(args):
     """--impl reference: the reference's own algorithm on the host CPU.  The reference is pure Python and
     cannot be installed on the GPU box (no gym, read-only tree absent), so this times the oracle port
@@ -238,6 +264,8 @@ def main():
     ap.add_argument("--pipeline", action="store_true", help="tuning: persistent pipelined kernel instead of one block per warp")
     ap.add_argument("--ctas", type=int, default=0, help="tuning: cap on resident CTAs per SM (pipelined kernel)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--rollout", type=int, default=0, help="extra leg: PPO rollout collection (tanh 64-64 MLP policy in the "
+                    "loop, obs/reward/done written into rollout-buffer slabs, GAE kernel) with this many steps per rollout")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -374,6 +402,8 @@ def main():
                          "traffic": ncu_traffic_bytes(E), "peak_source": how,
                          "algorithmic_bytes_per_env_step": bytes_step, "kernel_ms": kernel_ms},
         }
+        if args.rollout > 0:
+            line["rollout_collection"] = rollout_leg(env, args.rollout, dev)
         if not args.no_cpu and n_gpus == 1:
             from oracle import oracle as orc
             orc.build()

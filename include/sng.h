@@ -175,6 +175,15 @@ int sng_sample_plan(sng_env *env, void *stream);
 /* OR of all per-env error flags (synchronises the stream). */
 int sng_error_flags(sng_env *env, uint32_t *host_out, void *stream);
 
+/* Next row of the path: advantages / returns of a collected rollout, for the trainer that
+ * drives the step (solvers/RL/ppo_train.py:94-101 -> stable_baselines3 PPO.collect_rollouts ->
+ * RolloutBuffer.compute_returns_and_advantage).  All arrays on the device; rewards, values, advantages,
+ * returns [n_steps][E] float32, episode_starts [n_steps][E] u8 (1 = the env was reset before that step),
+ * last_values [E] = V(obs after the last step), last_dones [E].  Asynchronous on `stream`. */
+int sng_gae(const float *rewards, const float *values, const uint8_t *episode_starts, const float *last_values,
+            const uint8_t *last_dones, float *advantages, float *returns, int n_steps, int64_t n_envs, float gamma,
+            float gae_lambda, void *stream);
+
 /* Kernels launched by this handle so far (bench.py's gpu_launches claim). */
 int64_t sng_launch_count(const sng_env *env);
 

@@ -21,7 +21,7 @@ DIAG = ("total_ch", "total_dis", "solar", "batt_power", "grid_power", "grid_cost
 
 EXPORTS = ("sng_abi_version", "sng_sizeof", "sng_last_error", "sng_query_layout", "sng_create", "sng_destroy", "sng_bind",
            "sng_reset", "sng_load_schedule", "sng_step", "sng_rollout", "sng_step_host", "sng_sample_plan",
-           "sng_error_flags", "sng_launch_count", "sng_set_tuning", "sng_set_pipeline")
+           "sng_error_flags", "sng_launch_count", "sng_set_tuning", "sng_set_pipeline", "sng_gae")
 
 
 class SngConfig(C.Structure):
@@ -101,6 +101,7 @@ def lib():
         L.sng_launch_count.restype = C.c_int64
         L.sng_set_tuning.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
         L.sng_set_pipeline.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.sng_gae.argtypes = [C.c_void_p] * 7 + [C.c_int, C.c_int64, C.c_float, C.c_float, C.c_void_p]
         if L.sng_abi_version() != 2:
             raise NativeError("libsng.so ABI version mismatch")
         for which, st in enumerate((SngConfig, SngLayout, SngBuffers, SngScheduleView)):

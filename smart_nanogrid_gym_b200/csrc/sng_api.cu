@@ -14,6 +14,34 @@ EngineBase *make_engine_f32(const sng_config &cfg, int device, std::string &err)
 }
 }  // namespace sng
 
+// Generalised advantage estimation over a rollout, one thread per env walking the steps backwards
+// (every access of a warp is one coalesced line of the [n_steps][E] slabs).  Restates
+// stable_baselines3 RolloutBuffer.compute_returns_and_advantage, the consumer of the rollouts the
+// reference's trainer collects (solvers/RL/ppo_train.py:94-101).
+__global__ void __launch_bounds__(256) gae_kernel(const float *__restrict__ rewards, const float *__restrict__ values,
+                                                 const uint8_t *__restrict__ episode_starts,
+                                                 const float *__restrict__ last_values,
+                                                 const uint8_t *__restrict__ last_dones, float *__restrict__ advantages,
+                                                 float *__restrict__ returns, int n_steps, long long n_envs, float gamma,
+                                                 float lam)
+{
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_envs) return;
+    float next_value = last_values[e];
+    float next_non_terminal = last_dones[e] ? 0.0f : 1.0f;
+    float gae = 0.0f;
+    for (int t = n_steps - 1; t >= 0; --t) {
+        const size_t k = (size_t)t * (size_t)n_envs + (size_t)e;
+        const float v = values[k];
+        const float delta = rewards[k] + gamma * next_value * next_non_terminal - v;
+        gae = delta + gamma * lam * next_non_terminal * gae;
+        advantages[k] = gae;
+        returns[k] = gae + v;
+        next_value = v;
+        next_non_terminal = episode_starts[k] ? 0.0f : 1.0f;
+    }
+}
+
 struct sng_env {
     sng::EngineBase *eng;
 };
@@ -150,6 +178,21 @@ int sng_set_tuning(sng_env *env, int warps_per_cta, int use_generic_kernel, int 
 {
     SNG_ENV_CHECK(env);
     return done(env, env->eng->set_tuning(warps_per_cta, use_generic_kernel, use_bulk_copy, host_chunks));
+}
+
+int sng_gae(const float *rewards, const float *values, const uint8_t *episode_starts, const float *last_values,
+            const uint8_t *last_dones, float *advantages, float *returns, int n_steps, int64_t n_envs, float gamma,
+            float gae_lambda, void *stream)
+{
+    if (!rewards || !values || !episode_starts || !last_values || !last_dones || !advantages || !returns || n_steps < 1 ||
+        n_envs < 1)
+        return fail(SNG_ERR_ARG, "sng_gae: bad arguments");
+    gae_kernel<<<(unsigned)((n_envs + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        rewards, values, episode_starts, last_values, last_dones, advantages, returns, n_steps, (long long)n_envs, gamma,
+        gae_lambda);
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(SNG_ERR_CUDA, std::string("sng_gae: ") + cudaGetErrorString(e));
+    return SNG_OK;
 }
 
 int sng_set_pipeline(sng_env *env, int use_pipelined_kernel, int ctas_per_sm)

@@ -1,0 +1,120 @@
+"""On-device PPO rollout collection around the batched step (BASELINE config 3).
+
+The reference trains with Stable-Baselines3 PPO on ONE env (solvers/RL/ppo_train.py:89-102): SB3's
+`collect_rollouts` loops `policy(obs) -> clip -> env.step -> buffer.add` and then computes GAE.  Here the
+same loop runs for E envs without leaving the GPU: the step kernel writes observations / rewards / dones
+straight into the rollout-buffer slices (zero-copy `out=`), the policy is a torch MLP of SB3's default
+MlpPolicy shape (tanh 64-64 actor and critic, state-independent log-std), and advantages / returns come
+from the `sng_gae` kernel.  Not a trainer: it is the caller-side row next to the hot path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import torch
+from torch import nn
+
+from . import _native as nat
+
+
+class MlpPolicy(nn.Module):
+    """SB3 ActorCriticPolicy defaults for Box actions: separate tanh 64-64 networks, DiagGaussian head."""
+
+    def __init__(self, obs_dim: int, act_dim: int, hidden: int = 64, log_std_init: float = 0.0):
+        super().__init__()
+        self.pi = nn.Sequential(nn.Linear(obs_dim, hidden), nn.Tanh(), nn.Linear(hidden, hidden), nn.Tanh())
+        self.vf = nn.Sequential(nn.Linear(obs_dim, hidden), nn.Tanh(), nn.Linear(hidden, hidden), nn.Tanh())
+        self.action_net = nn.Linear(hidden, act_dim)
+        self.value_net = nn.Linear(hidden, 1)
+        self.log_std = nn.Parameter(torch.full((act_dim,), float(log_std_init)))
+
+    def forward(self, obs: torch.Tensor, noise: torch.Tensor | None = None):
+        """-> (actions, values, log_probs); `noise` ~ N(0, 1) of the action shape (None = deterministic)."""
+        mean = self.action_net(self.pi(obs))
+        values = self.value_net(self.vf(obs)).squeeze(-1)
+        if noise is None:
+            noise = torch.zeros_like(mean)
+        actions = mean + noise * self.log_std.exp()
+        log_probs = (-0.5 * noise.pow(2) - self.log_std - 0.5 * math.log(2 * math.pi)).sum(-1)
+        return actions, values, log_probs
+
+    def predict_values(self, obs: torch.Tensor) -> torch.Tensor:
+        return self.value_net(self.vf(obs)).squeeze(-1)
+
+
+class RolloutBuffer:
+    """[n_steps, E, ...] device tensors, SB3 RolloutBuffer field for field.  `observations` has n_steps + 1
+    slabs: slab s is what the policy saw at step s, slab s + 1 is written by the step kernel itself."""
+
+    def __init__(self, n_steps: int, n_envs: int, obs_dim: int, act_dim: int, device, gamma: float = 0.99,
+                 gae_lambda: float = 0.95):
+        z = lambda *shape, dtype=torch.float32: torch.zeros(*shape, dtype=dtype, device=device)  # noqa: E731
+        self.n_steps, self.n_envs, self.gamma, self.gae_lambda = n_steps, n_envs, gamma, gae_lambda
+        self.observations = z(n_steps + 1, n_envs, obs_dim)
+        self.actions = z(n_steps, n_envs, act_dim)            # what the env executed (clipped to the Box)
+        self.raw_actions = z(n_steps, n_envs, act_dim)        # what the policy sampled (SB3 stores these)
+        self.rewards = z(n_steps, n_envs)
+        self.dones = z(n_steps, n_envs, dtype=torch.uint8)
+        self.episode_starts = z(n_steps, n_envs, dtype=torch.uint8)
+        self.values = z(n_steps, n_envs)
+        self.log_probs = z(n_steps, n_envs)
+        self.advantages = z(n_steps, n_envs)
+        self.returns = z(n_steps, n_envs)
+        self.last_values = z(n_envs)
+
+    def compute_returns_and_advantage(self, last_values: torch.Tensor, last_dones: torch.Tensor):
+        """SB3 RolloutBuffer.compute_returns_and_advantage on the device (sng_gae kernel)."""
+        p = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+        lv = last_values.detach().float().contiguous()
+        ld = last_dones.to(torch.uint8).contiguous()
+        stream = C.c_void_p(torch.cuda.current_stream(self.rewards.device).cuda_stream)
+        nat.check(nat.lib().sng_gae(p(self.rewards), p(self.values), p(self.episode_starts), p(lv), p(ld),
+                                    p(self.advantages), p(self.returns), self.n_steps, self.n_envs,
+                                    C.c_float(self.gamma), C.c_float(self.gae_lambda), stream))
+        return self.advantages, self.returns
+
+
+@torch.no_grad()
+def collect_rollout(env, policy: MlpPolicy, buf: RolloutBuffer, obs: torch.Tensor, episode_starts: torch.Tensor,
+                    generator: torch.Generator | None = None, deterministic: bool = False):
+    """SB3 OnPolicyAlgorithm.collect_rollouts for a BatchedSmartNanogridEnv: n_steps policy + env steps,
+    then GAE.  `obs` [E, D] is the current observation (from reset() or the previous rollout),
+    `episode_starts` [E] u8.  Returns (last_obs, last_dones) to carry into the next call."""
+    low, high = env.action_low.float(), env.action_high.float()
+    buf.observations[0].copy_(obs)
+    starts = episode_starts.to(torch.uint8)
+    for s in range(buf.n_steps):
+        o = buf.observations[s]
+        noise = None if deterministic else torch.randn(buf.n_envs, buf.actions.shape[2], device=o.device, generator=generator)
+        a, v, lp = policy(o, noise)
+        buf.raw_actions[s].copy_(a)
+        torch.clamp(a, low, high, out=buf.actions[s])          # SB3 clips Box actions before env.step
+        buf.values[s].copy_(v)
+        buf.log_probs[s].copy_(lp)
+        buf.episode_starts[s].copy_(starts)
+        # the kernel writes the next observation, the reward and the done flag into the buffer slabs
+        env.step(buf.actions[s], out=(buf.observations[s + 1], buf.rewards[s], buf.dones[s]))
+        starts = buf.dones[s]
+    last_obs = buf.observations[buf.n_steps]
+    buf.last_values.copy_(policy.predict_values(last_obs))
+    buf.compute_returns_and_advantage(buf.last_values, buf.dones[buf.n_steps - 1])
+    return last_obs, buf.dones[buf.n_steps - 1]
+
+
+def gae_reference(rewards, values, episode_starts, last_values, last_dones, gamma, gae_lambda):
+    """Plain torch float64 restatement of SB3's loop (the checker of the sng_gae kernel in tests)."""
+    n = rewards.shape[0]
+    adv = torch.zeros_like(rewards, dtype=torch.float64)
+    last_gae = torch.zeros_like(last_values, dtype=torch.float64)
+    for t in reversed(range(n)):
+        if t == n - 1:
+            non_terminal = 1.0 - last_dones.double()
+            next_values = last_values.double()
+        else:
+            non_terminal = 1.0 - episode_starts[t + 1].double()
+            next_values = values[t + 1].double()
+        delta = rewards[t].double() + gamma * next_values * non_terminal - values[t].double()
+        last_gae = delta + gamma * gae_lambda * non_terminal * last_gae
+        adv[t] = last_gae
+    return adv, adv + values.double()

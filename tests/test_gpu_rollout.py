@@ -1,0 +1,65 @@
+"""SURVEY 8f row 1 (BASELINE config 3): on-device PPO rollout collection around the step -- the step kernel
+writes into rollout-buffer slabs zero-copy, and the sng_gae kernel matches SB3's advantage recursion."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+KW = dict(number_of_chargers=10, charging_mode="bounded", vehicle_uncharged_penalty_mode="sparse", time_interval="1h")
+
+
+def test_gae_kernel_matches_sb3_recursion():
+    from smart_nanogrid_gym_b200.rollout import RolloutBuffer, gae_reference
+    n, E = 37, 5003
+    g = torch.Generator(device="cuda:0").manual_seed(0)
+    buf = RolloutBuffer(n, E, 29, 11, "cuda:0", gamma=0.99, gae_lambda=0.95)
+    buf.rewards.copy_(-10 * torch.rand(n, E, device="cuda:0", generator=g))
+    buf.values.copy_(-50 * torch.rand(n, E, device="cuda:0", generator=g))
+    buf.episode_starts.copy_((torch.rand(n, E, device="cuda:0", generator=g) < 0.1).to(torch.uint8))
+    last_values = -50 * torch.rand(E, device="cuda:0", generator=g)
+    last_dones = (torch.rand(E, device="cuda:0", generator=g) < 0.3).to(torch.uint8)
+    adv, ret = buf.compute_returns_and_advantage(last_values, last_dones)
+    adv_ref, ret_ref = gae_reference(buf.rewards, buf.values, buf.episode_starts, last_values, last_dones, 0.99, 0.95)
+    assert torch.allclose(adv.double(), adv_ref, rtol=1e-5, atol=1e-4)
+    assert torch.allclose(ret.double(), ret_ref, rtol=1e-5, atol=1e-4)
+
+
+def test_collect_rollout_is_zero_copy_and_matches_manual_stepping():
+    from smart_nanogrid_gym_b200 import BatchedSmartNanogridEnv
+    from smart_nanogrid_gym_b200.rollout import MlpPolicy, RolloutBuffer, collect_rollout, gae_reference
+    E, n = 2048, 30
+    env = BatchedSmartNanogridEnv(E, seed=3, **KW)
+    twin = BatchedSmartNanogridEnv(E, seed=3, **KW)
+    torch.manual_seed(0)
+    policy = MlpPolicy(env.cfg.obs_dim, env.cfg.act_dim).to("cuda:0")
+    buf = RolloutBuffer(n, E, env.cfg.obs_dim, env.cfg.act_dim, "cuda:0")
+    ptrs = (buf.observations.data_ptr(), buf.rewards.data_ptr(), buf.dones.data_ptr())
+    obs = env.reset()
+    obs_twin = twin.reset().clone()
+    assert torch.equal(obs, obs_twin)
+    g = torch.Generator(device="cuda:0").manual_seed(5)
+    starts = torch.ones(E, dtype=torch.uint8, device="cuda:0")
+    last_obs, last_dones = collect_rollout(env, policy, buf, obs, starts, generator=g)
+    assert ptrs == (buf.observations.data_ptr(), buf.rewards.data_ptr(), buf.dones.data_ptr())   # nothing reallocated
+    lo, hi = env.action_low, env.action_high
+    assert (buf.actions >= lo).all() and (buf.actions <= hi).all()
+    assert torch.equal(buf.actions, torch.minimum(torch.maximum(buf.raw_actions, lo), hi))
+    # the same actions through a second env stepped the ordinary way reproduce every slab bit for bit
+    assert torch.equal(buf.observations[0], obs_twin)
+    for s in range(n):
+        o, r, d, _, _ = twin.step(buf.actions[s].clone())
+        assert torch.equal(o, buf.observations[s + 1]) and torch.equal(r, buf.rewards[s]) and torch.equal(d, buf.dones[s]), s
+        expect_start = starts if s == 0 else buf.dones[s - 1]
+        assert torch.equal(buf.episode_starts[s], expect_start)
+    assert buf.dones[23].all() and buf.dones.sum().item() == E          # one termination per env in 30 steps
+    assert torch.equal(last_obs, buf.observations[n]) and torch.equal(last_dones, buf.dones[n - 1])
+    with torch.no_grad():
+        assert torch.allclose(buf.values[7], policy.predict_values(buf.observations[7]), atol=1e-5)
+    adv_ref, ret_ref = gae_reference(buf.rewards, buf.values, buf.episode_starts, buf.last_values, last_dones,
+                                     buf.gamma, buf.gae_lambda)
+    assert torch.allclose(buf.advantages.double(), adv_ref, rtol=1e-5, atol=1e-3)
+    assert torch.allclose(buf.returns.double(), ret_ref, rtol=1e-5, atol=1e-3)
+    assert env.error_flags() == 0
+    env.close()
+    twin.close()
