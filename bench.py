@@ -261,7 +261,7 @@ def main():
     ap.add_argument("--generic", action="store_true", help="tuning: use the generic runtime-N kernel")
     ap.add_argument("--bulk", type=int, default=1, help="tuning: row staging: -1 scalar, 0 vector loads/stores, 1 copy-engine loads + vector stores, 3 copy engine both ways")
     ap.add_argument("--host-chunks", type=int, default=0, help="tuning: env chunks of the pipelined host path")
-    ap.add_argument("--pipeline", action="store_true", help="tuning: persistent pipelined kernel instead of one block per warp")
+    ap.add_argument("--variant", type=int, default=0, help="tuning: 0 one block per warp, 1 persistent pipelined kernel")
     ap.add_argument("--ctas", type=int, default=0, help="tuning: cap on resident CTAs per SM (pipelined kernel)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--rollout", type=int, default=0, help="extra leg: PPO rollout collection (tanh 64-64 MLP policy in the "
@@ -292,7 +292,7 @@ def main():
     env = BatchedSmartNanogridEnv(E, device=dev, seed=0, env_gid0=rank * E, precision="float32", auto_reset=True,
                                   **wl["kw"])
     env.set_tuning(args.warps, int(args.generic), args.bulk, args.host_chunks)
-    env.set_pipeline(1 if args.pipeline else 0, args.ctas)
+    env.set_pipeline(args.variant, args.ctas)
     cfg = env.cfg
     env.reset()
     # actions: a pre-filled U(low, high) tensor re-read from HBM every step

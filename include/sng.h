@@ -194,10 +194,10 @@ int64_t sng_launch_count(const sng_env *env);
  * both ways (unaligned buffers and a partial last block always take the scalar path); number of env
  * chunks sng_step_host pipelines over PCIe (0 = auto). */
 int sng_set_tuning(sng_env *env, int warps_per_cta, int use_generic_kernel, int use_bulk_copy, int host_chunks);
-/* Tuning knob: use the persistent software-pipelined step kernel (1) or the one-block-per-warp kernel
- * (0, default: it measured faster); cap on resident CTAs per SM of the pipelined kernel
- * (0 = as many as fit). */
-int sng_set_pipeline(sng_env *env, int use_pipelined_kernel, int ctas_per_sm);
+/* Tuning knob: which single-step kernel runs: 0 (default) or 2 one 32-env block per warp, 1 the
+ * persistent software-pipelined kernel (measured slower); cap on resident CTAs per SM of
+ * the pipelined kernel (0 = as many as fit). */
+int sng_set_pipeline(sng_env *env, int kernel_variant, int ctas_per_sm);
 
 #ifdef __cplusplus
 }

@@ -130,8 +130,9 @@ class BatchedSmartNanogridEnv:
         """Experiment / test knobs of the step launch (include/sng.h sng_set_tuning)."""
         nat.check(self._lib.sng_set_tuning(self._h, warps_per_cta, use_generic_kernel, use_bulk_copy, host_chunks))
 
-    def set_pipeline(self, use_pipelined_kernel=0, ctas_per_sm=0):
-        nat.check(self._lib.sng_set_pipeline(self._h, use_pipelined_kernel, ctas_per_sm))
+    def set_pipeline(self, kernel_variant=0, ctas_per_sm=0):
+        """0 one 32-env block per warp (default), 1 persistent pipelined kernel (include/sng.h)."""
+        nat.check(self._lib.sng_set_pipeline(self._h, kernel_variant, ctas_per_sm))
 
     def _plane(self, f):
         """Plane f of the blocked per-spot state -> a de-blocked [E, N] copy (words)."""

@@ -195,10 +195,10 @@ int sng_gae(const float *rewards, const float *values, const uint8_t *episode_st
     return SNG_OK;
 }
 
-int sng_set_pipeline(sng_env *env, int use_pipelined_kernel, int ctas_per_sm)
+int sng_set_pipeline(sng_env *env, int kernel_variant, int ctas_per_sm)
 {
     SNG_ENV_CHECK(env);
-    return done(env, env->eng->set_pipeline(use_pipelined_kernel, ctas_per_sm));
+    return done(env, env->eng->set_pipeline(kernel_variant, ctas_per_sm));
 }
 
 }  // extern "C"

@@ -336,7 +336,7 @@ __device__ __forceinline__ void begin_episode(const Params<real> &p, int N, long
 
 // Spots whose state loads are issued together (and, in the pipelined kernel, one block ahead).
 template <int NCT> struct Chunk {
-    static constexpr int value = NCT == 0 ? 1 : (NCT <= 16 ? NCT : 8);
+    static constexpr int value = NCT == 0 ? 1 : (NCT <= 16 ? NCT : 16);
     static_assert(NCT == 0 || NCT % value == 0, "the chunk must divide the number of spots");
 };
 
@@ -393,6 +393,31 @@ __device__ __noinline__ PowerSoc<real> discharge_vehicle(real power, real dt, re
 // NCT: number of spots at compile time (0 = runtime p.N); ND: see Offsets.  EXACT (double only):
 // reproduces numpy's summation order of the station power sums.
 // ------------------------------------------------------------------------------------------
+// ------------------------------------------------------------------------------------------
+// How a thread reaches its action row and its observation row.
+//   RowIO   the whole rows of the warp's 32 envs sit in shared memory; everything is a plain
+//           shared-memory access.  (A variant that moved the rows of large stations through [32 envs][16
+//           spots] tiles to save shared memory was measured 30 % slower at N = 64 -- its 64-byte row
+//           pieces are partial-sector writes -- and was dropped; the hooks remain.)
+// ------------------------------------------------------------------------------------------
+template <typename real> struct RowIO {
+    const real *act;   // [A] this env's action row
+    float *obs;        // [D] this env's observation row
+    int off_soc, off_dep;
+    __device__ __forceinline__ void begin_chunk(int) const {}
+    __device__ __forceinline__ void end_chunk(int) const {}
+    __device__ __forceinline__ real action(int c, int j) const { return act[c + j]; }
+    __device__ __forceinline__ real action_at(int i) const { return act[i]; }
+    __device__ __forceinline__ void put_spot(int c, int j, float soc, float dep) const
+    {
+        obs[off_soc + c + j] = soc;
+        obs[off_dep + c + j] = dep;
+    }
+    __device__ __forceinline__ void fix_soc(int i, float soc) const { obs[off_soc + i] = soc; }
+    __device__ __forceinline__ float *row() const { return obs; }
+    __device__ __forceinline__ float read_back(int k) const { return obs[k]; }
+};
+
 // What a thread hands to the warp-cooperative admission of arriving vehicles (admit_arrivals_warp).
 struct Arrivals {
     uint32_t mask;      // spots of this env whose next vehicle arrives at tn (0 on the last step of the day)
@@ -400,11 +425,12 @@ struct Arrivals {
     int tn;
 };
 
-template <typename real, int NCT, int ND, bool EXACT, bool SMEM, bool COOP = false>
+template <typename real, int NCT, int ND, bool EXACT, bool SMEM, bool COOP = false, typename IO = RowIO<real>>
 __device__ __forceinline__ Arrivals env_step(const Params<real> &p, long long e, typename WordOf<real>::type *spot,
-                                             const StateRegs<real, NCT> &st, const real *act, float *obs,
-                                             real *reward_out, uint8_t *done_out)
+                                             const StateRegs<real, NCT> &st, const IO &io, real *reward_out,
+                                             uint8_t *done_out)
 {
+    float *const obs = io.row();   // env-level entries, reset observation
     static_assert(!COOP || (NCT > 0 && NCT <= 32), "cooperative admission needs a 32-bit arrival mask");
     typedef typename WordOf<real>::type word;
     const int N = NCT ? NCT : p.N;
@@ -437,6 +463,7 @@ __device__ __forceinline__ Arrivals env_step(const Params<real> &p, long long e,
     //      penalty (penaliser.py:39-87) ----
 #pragma unroll 1
     for (int c = 0; c < N; c += CH) {
+        io.begin_chunk(c);
         word wh[CH], wr[CH], ws[CH];
         if (c == 0) {
 #pragma unroll
@@ -451,7 +478,7 @@ __device__ __forceinline__ Arrivals env_step(const Params<real> &p, long long e,
             const real rq = word_to_real(wr[j], (real)0);
             const real s_prev = word_to_real(ws[j], (real)0);  // SoC column t-1 (the arrival SoC when arr == t, charger.py:62-67)
             const int arr = (int)(hd & 0xFFu), dep = (int)((hd >> 8) & 0xFFu);   // arr == 0xFF: no vehicle yet
-            const real a = act[i];
+            const real a = io.action(c, j);
             if (EXACT) {
                 if (a != a) err |= FLAG_NAN_ACTION;
             } else {
@@ -504,8 +531,8 @@ __device__ __forceinline__ Arrivals env_step(const Params<real> &p, long long e,
             }
             word *sp = spot + (size_t)i * SP;
             sp[PL_SOC * kBlock] = real_to_word(s_new);
-            obs[off_soc + i] = (float)s_new;                                  // charging_station.py:114-117
-            obs[off_dep + i] = present ? dep_lookup<SMEM>(p, dep_base, dep - t) : 0.0f;   // :92-112, "/ 24" env:208
+            io.put_spot(c, j, (float)s_new,                                    // charging_station.py:114-117
+                        present ? dep_lookup<SMEM>(p, dep_base, dep - t) : 0.0f);     // :92-112, "/ 24" env:208
             if ((hd >> 24) == tn_key) {
                 if (NCT) {
                     arrivals |= (decltype(arrivals))1 << i;
@@ -514,6 +541,7 @@ __device__ __forceinline__ Arrivals env_step(const Params<real> &p, long long e,
                 }
             }
         }
+        io.end_chunk(c + CH);
     }
     if (EXACT) {
         neg = (real)numpy_sum(cneg, nneg);
@@ -525,11 +553,11 @@ __device__ __forceinline__ Arrivals env_step(const Params<real> &p, long long e,
         word *sp = spot + (size_t)i * SP;
         const uint32_t hd = (uint32_t)sp[PL_HDR * kBlock];
         const real s_prev = word_to_real(sp[PL_SOC * kBlock], (real)0);   // the hot loop left it unchanged
-        const PowerSoc<real> r = discharge_vehicle(act[i] * p.ev_pmax * p.ev_eff, p.dt, s_prev, (real)((hd >> 16) & 0xFFu));
+        const PowerSoc<real> r = discharge_vehicle(io.action_at(i) * p.ev_pmax * p.ev_eff, p.dt, s_prev, (real)((hd >> 16) & 0xFFu));
         if (r.P < 0) neg += r.P;
         if (r.P > 0) pos += r.P;
         sp[PL_SOC * kBlock] = real_to_word(r.soc);
-        obs[off_soc + i] = (float)r.soc;
+        io.fix_soc(i, (float)r.soc);
     }
 
     // ---- env-level phase: CentralManagementSystem.manage_nanogrid (central_management_system.py:99-113) ----
@@ -539,7 +567,7 @@ __device__ __forceinline__ Arrivals env_step(const Params<real> &p, long long e,
     real rem = total_power - solar;                                       // :167
     real soc_b = es.soc_b, batt_power = 0, pen_b = 0;
     if (p.batt) {                                                         // battery_energy_storage_system.py:30-106
-        const real ab = act[N];                                           // actions[-1], :88-89
+        const real ab = io.action_at(N);                                  // actions[-1], :88-89
         if (EXACT) {
             if (ab != ab) err |= FLAG_NAN_ACTION;
         } else {
@@ -604,7 +632,7 @@ __device__ __forceinline__ Arrivals env_step(const Params<real> &p, long long e,
         if (p.auto_reset) {
             if (p.tobs) {
                 float *tobs = p.tobs + (size_t)e * p.D;
-                for (int k = 0; k < p.D; ++k) tobs[k] = obs[k];
+                for (int k = 0; k < p.D; ++k) tobs[k] = io.read_back(k);
             }
             episode = (episode + 1u) & 0xFFFFFFu;
             if (p.mode == MODE_SAMPLE) shift = sample_pv_shift(p, N, p.gid0 + (unsigned long long)e, episode);

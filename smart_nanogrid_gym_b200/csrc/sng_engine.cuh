@@ -6,6 +6,8 @@
 #include <cstdio>
 #include <cstring>
 #include <map>
+#include <mutex>
+#include <utility>
 #include <string>
 #include <type_traits>
 #include <vector>
@@ -27,7 +29,7 @@ struct EngineBase {
     virtual int sample_plan(cudaStream_t st) = 0;
     virtual int error_flags(uint32_t *out, cudaStream_t st) = 0;
     virtual int set_tuning(int warps_per_cta, int use_generic, int use_bulk, int host_chunks) = 0;
-    virtual int set_pipeline(int use_pipeline, int ctas_per_sm) = 0;
+    virtual int set_pipeline(int kernel_variant, int ctas_per_sm) = 0;
     int64_t launches = 0;
     std::string error;
 };
@@ -118,9 +120,9 @@ __global__ void __launch_bounds__(SNG_PIPE_THREADS, SNG_PIPE_MINB)
         }
         mbar_wait(bar + stage, (uint32_t)((it >> 1) & 1));
         const long long e = blk * kBlock + lane;
-        env_step<real, NCT, ND, EXACT, true>(p, e, p.spot + (size_t)blk * blk_words + lane, cur,
-                                             reinterpret_cast<const real *>(wbase + stage * act_stage) + lane * A,
-                                             obs_s + lane * D, p.reward, p.done);
+        const RowIO<real> io = {reinterpret_cast<const real *>(wbase + stage * act_stage) + lane * A, obs_s + lane * D,
+                                Offsets<NCT, ND>::soc(p), Offsets<NCT, ND>::dep(p)};
+        env_step<real, NCT, ND, EXACT, true>(p, e, p.spot + (size_t)blk * blk_words + lane, cur, io, p.reward, p.done);
         __syncwarp();            // obs rows complete; everyone is done reading this action stage
         {   // 32 rows = 8 * D float4 (16-byte aligned on both sides): coalesced 512-byte warp stores.
             // (Plain stores, not cp.async.bulk: waiting for a bulk group drains the scoreboard the
@@ -152,7 +154,7 @@ enum : int {
 
 // MULTI: n_steps > 1 (rollout); the single-step instantiation carries no slab arithmetic.
 template <typename real, int NCT, int ND, bool EXACT, bool MULTI>
-__global__ void __launch_bounds__(SNG_STEP_MAXT, EXACT ? 1 : SNG_STEP_MINB)
+__global__ void __launch_bounds__(SNG_STEP_MAXT, (EXACT || NCT > 16) ? 2 : SNG_STEP_MINB)   // large rows: shared memory bounds occupancy, not registers
     step_simple_kernel(const Params<real> p, const real *actions, float *obs_out, real *reward, uint8_t *done, int n_steps,
                        int mode)
 {
@@ -237,9 +239,10 @@ __global__ void __launch_bounds__(SNG_STEP_MAXT, EXACT ? 1 : SNG_STEP_MINB)
             __syncwarp();
         }
         Arrivals arrivals = {0u, 0u, 0};
-        if (valid)
-            arrivals = env_step<real, NCT, ND, EXACT, true, COOP>(p, e, spot, st, act_s + lane * A, obs_s + lane * D,
-                                                                  reward + slab, done + slab);
+        if (valid) {
+            const RowIO<real> io = {act_s + lane * A, obs_s + lane * D, Offsets<NCT, ND>::soc(p), Offsets<NCT, ND>::dep(p)};
+            arrivals = env_step<real, NCT, ND, EXACT, true, COOP>(p, e, spot, st, io, reward + slab, done + slab);
+        }
         if (COOP) admit_arrivals_warp<real, NCT>(p, e0, lane, spot - lane, arrivals, queue);
         // ---- observation rows out of shared memory ----
         if (tma_store) {
@@ -344,7 +347,8 @@ public:
     bool bound = false, started = false;
     int device = 0;
     int warps_per_cta = 0;   // 0 = auto
-    int use_generic = 0, use_bulk = 1, host_chunks = 0, use_pipeline = 0, ctas_per_sm = 0;
+    int use_generic = 0, use_bulk = 1, host_chunks = 0, ctas_per_sm = 0;
+    int kernel_variant = 0;   // 0 / 2 one block per warp, 1 persistent pipelined
     int num_sms = 148;
     size_t smem_optin = 0;
     void *d_tables = nullptr;
@@ -541,14 +545,17 @@ public:
 
     static bool aligned16(const void *q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; }
 
-    // cudaFuncSetAttribute once per (kernel, size) instead of on every launch
-    std::map<const void *, size_t> smem_set;
+    // The dynamic shared-memory limit is a per-function, per-device attribute shared by every handle:
+    // raise it monotonically, once per (device, kernel), instead of setting it on every launch.
     int ensure_smem(const void *kern, size_t smem)
     {
-        auto it = smem_set.find(kern);
-        if (it != smem_set.end() && it->second == smem) return SNG_OK;
+        static std::mutex mu;
+        static std::map<std::pair<int, const void *>, size_t> limit;
+        std::lock_guard<std::mutex> lock(mu);
+        size_t &cur = limit[std::make_pair(device, kern)];
+        if (smem <= cur) return SNG_OK;
         SNG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        smem_set[kern] = smem;
+        cur = smem;
         return SNG_OK;
     }
 
@@ -608,7 +615,7 @@ public:
     int launch_step_n(const Params<real> &q, const real *actions, float *obs, real *reward, uint8_t *done, int n_steps,
                       int bulk, cudaStream_t st)
     {
-        if ((bulk & STAGE_ALIGNED) && use_pipeline && n_steps == 1 && q.n_envs >= kBlock && actions == q.actions && obs == q.obs &&
+        if ((bulk & STAGE_ALIGNED) && kernel_variant == 1 && n_steps == 1 && q.n_envs >= kBlock && actions == q.actions && obs == q.obs &&
             reward == q.reward && done == q.done) {
             const long long n_blocks = q.n_envs / kBlock;
             const int rc = launch_pipelined<NCT, ND>(q, n_blocks, st);
@@ -784,8 +791,8 @@ public:
 
     int set_pipeline(int up, int cps) override
     {
-        if (cps < 0) { error = "sng_set_pipeline: bad arguments"; return SNG_ERR_ARG; }
-        use_pipeline = up; ctas_per_sm = cps;
+        if (cps < 0 || up < 0 || up > 2) { error = "sng_set_pipeline: bad arguments"; return SNG_ERR_ARG; }
+        kernel_variant = up; ctas_per_sm = cps;
         return SNG_OK;
     }
 };

@@ -235,8 +235,8 @@ def test_kernel_variants_are_bit_identical(kw):
     E = 5 * 256 + 104 + 13
     variants = [(dict(), dict()), (dict(use_generic_kernel=1), dict()), (dict(use_bulk_copy=0), dict()),
                 (dict(use_bulk_copy=-1), dict()), (dict(use_bulk_copy=3), dict()), (dict(use_bulk_copy=1, use_generic_kernel=1), dict()),
-                (dict(warps_per_cta=1), dict(use_pipelined_kernel=1, ctas_per_sm=1)), (dict(), dict(use_pipelined_kernel=1)),
-                (dict(warps_per_cta=4, use_generic_kernel=1), dict(use_pipelined_kernel=1))]
+                (dict(warps_per_cta=1), dict(kernel_variant=1, ctas_per_sm=1)), (dict(), dict(kernel_variant=1)),
+                (dict(warps_per_cta=4, use_generic_kernel=1), dict(kernel_variant=1)), (dict(), dict(kernel_variant=2))]
     envs = []
     for tune, pipe in variants:
         env = _env(E, "float32", seed=21, **kw)
