@@ -149,25 +149,26 @@ def cpu_port_throughput(n_envs, seconds, threads):
 def rollout_leg(env, n_steps, dev):
     """BASELINE config 3: policy in the loop.  Reported beside the headline, not as it."""
     import torch
-    from smart_nanogrid_gym_b200.rollout import MlpPolicy, RolloutBuffer, collect_rollout
+    from smart_nanogrid_gym_b200.rollout import GraphedRollout, MlpPolicy, RolloutBuffer
     torch.manual_seed(0)
     policy = MlpPolicy(env.cfg.obs_dim, env.cfg.act_dim).to(dev)
     buf = RolloutBuffer(n_steps, env.num_envs, env.cfg.obs_dim, env.cfg.act_dim, dev)
-    g = torch.Generator(device=dev).manual_seed(0)
     obs = env.reset()
     starts = torch.ones(env.num_envs, dtype=torch.uint8, device=dev)
+    collect = GraphedRollout(env, policy, buf)
     for _ in range(2):
-        obs, starts = collect_rollout(env, policy, buf, obs, starts, generator=g)
+        obs, starts = collect(obs, starts)
     torch.cuda.synchronize(dev)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    reps = 5
+    reps = 10
     ev0.record()
     for _ in range(reps):
-        obs, starts = collect_rollout(env, policy, buf, obs, starts, generator=g)
+        obs, starts = collect(obs, starts)
     ev1.record()
     torch.cuda.synchronize(dev)
     ms = ev0.elapsed_time(ev1)
     return {"value": env.num_envs * n_steps * reps / (ms * 1e-3), "unit": UNIT, "n_steps": n_steps, "envs": env.num_envs,
+            "launch": "one CUDA graph per rollout",
             "policy": "tanh MLP %d-64-64-%d (torch), actions clipped to the Box, GAE by sng_gae" % (env.cfg.obs_dim, env.cfg.act_dim),
             "mean_step_reward": float(buf.rewards.mean())}
 

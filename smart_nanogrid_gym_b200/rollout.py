@@ -102,6 +102,34 @@ def collect_rollout(env, policy: MlpPolicy, buf: RolloutBuffer, obs: torch.Tenso
     return last_obs, buf.dones[buf.n_steps - 1]
 
 
+class GraphedRollout:
+    """collect_rollout captured ONCE in a CUDA graph (n_steps x [policy MLP, clip, step kernel] + GAE) and
+    replayed: at 65,536 envs the eager loop is bound by ~20 small launches per step, the graph is not.
+    Sampling noise comes from torch's default CUDA generator (graph-safe); `deterministic=True` uses the mean."""
+
+    def __init__(self, env, policy: MlpPolicy, buf: RolloutBuffer, deterministic: bool = False):
+        dev = buf.rewards.device
+        self.env, self.policy, self.buf = env, policy, buf
+        self.obs_in = torch.zeros(buf.n_envs, buf.observations.shape[2], device=dev)
+        self.starts_in = torch.zeros(buf.n_envs, dtype=torch.uint8, device=dev)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):                     # warm-up outside capture (lazy inits, cuBLAS workspaces)
+            self.obs_in.copy_(env.obs)
+            collect_rollout(env, policy, buf, self.obs_in, self.starts_in, deterministic=deterministic)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.last_obs, self.last_dones = collect_rollout(env, policy, buf, self.obs_in, self.starts_in,
+                                                             deterministic=deterministic)
+
+    def __call__(self, obs: torch.Tensor, episode_starts: torch.Tensor):
+        self.obs_in.copy_(obs)
+        self.starts_in.copy_(episode_starts)
+        self.graph.replay()
+        return self.last_obs, self.last_dones
+
+
 def gae_reference(rewards, values, episode_starts, last_values, last_dones, gamma, gae_lambda):
     """Plain torch float64 restatement of SB3's loop (the checker of the sng_gae kernel in tests)."""
     n = rewards.shape[0]

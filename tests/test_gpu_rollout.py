@@ -63,3 +63,33 @@ def test_collect_rollout_is_zero_copy_and_matches_manual_stepping():
     assert env.error_flags() == 0
     env.close()
     twin.close()
+
+
+def test_graphed_rollout_equals_eager():
+    """The whole rollout (policy, clip, step kernel, GAE) captured in one CUDA graph reproduces the eager loop."""
+    from smart_nanogrid_gym_b200 import BatchedSmartNanogridEnv
+    from smart_nanogrid_gym_b200.rollout import GraphedRollout, MlpPolicy, RolloutBuffer, collect_rollout
+    E, n = 4096, 24
+    torch.manual_seed(1)
+    policy = MlpPolicy(29, 11).to("cuda:0")
+    env_e = BatchedSmartNanogridEnv(E, seed=9, **KW)
+    env_g = BatchedSmartNanogridEnv(E, seed=9, **KW)
+    buf_e = RolloutBuffer(n, E, 29, 11, "cuda:0")
+    buf_g = RolloutBuffer(n, E, 29, 11, "cuda:0")
+    env_g.reset()
+    graphed = GraphedRollout(env_g, policy, buf_g, deterministic=True)     # steps env_g during warm-up and capture
+    obs_e = env_e.reset()
+    obs_g = env_g.reset(seed=9)
+    env_g.load_state_dict(env_e.state_dict())
+    starts = torch.ones(E, dtype=torch.uint8, device="cuda:0")
+    s_e, s_g = starts, starts
+    for _ in range(3):
+        obs_e, s_e = collect_rollout(env_e, policy, buf_e, obs_e, s_e, deterministic=True)
+        obs_g, s_g = graphed(obs_g, s_g)
+        for name in ("observations", "actions", "rewards", "dones", "episode_starts", "values", "advantages", "returns"):
+            a, b = getattr(buf_e, name), getattr(buf_g, name)
+            assert torch.allclose(a.float(), b.float(), rtol=1e-5, atol=1e-5), name
+        obs_e, obs_g = obs_e.clone(), obs_g.clone()
+        s_e, s_g = s_e.clone(), s_g.clone()
+    env_e.close()
+    env_g.close()
