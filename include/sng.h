@@ -158,8 +158,7 @@ int sng_load_schedule(sng_env *env, const sng_schedule_view *view, void *stream)
 int sng_step(sng_env *env, void *stream);
 
 /* n_steps consecutive steps in one launch.  actions [n_steps][E][act_dim], obs [n_steps][E][obs_dim],
- * reward [n_steps][E], done [n_steps][E] (device).  actions == NULL: uniform random actions from
- * the action box are drawn in-kernel (throughput probe). */
+ * reward [n_steps][E], done [n_steps][E] (device, all required). */
 int sng_rollout(sng_env *env, const void *actions, float *obs, void *reward, uint8_t *done, int n_steps,
                 void *stream);
 

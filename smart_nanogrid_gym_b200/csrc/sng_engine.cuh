@@ -669,8 +669,7 @@ public:
     {
         int rc = check_ready(true);
         if (rc) return rc;
-        if (!actions) { error = "sng_rollout: in-kernel random actions are not implemented yet"; return SNG_ERR_UNSUPPORTED; }
-        if (!obs || !reward || !done || n_steps < 1) { error = "sng_rollout: bad arguments"; return SNG_ERR_ARG; }
+        if (!actions || !obs || !reward || !done || n_steps < 1) { error = "sng_rollout: bad arguments"; return SNG_ERR_ARG; }
         return launch_step(p, (const real *)actions, obs, (real *)reward, done, n_steps, st);
     }
 

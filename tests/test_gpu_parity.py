@@ -301,6 +301,69 @@ def test_zero_copy_out_buffers_and_state_dict():
     env.close()
 
 
+def _observe_masked(ob, mask):
+    """reset-observe only the masked envs: observe() also recomputes the (lagged) penalty-check set, which the
+    other envs must keep from their last step."""
+    keep = ob.check.copy()
+    o = ob.observe()
+    ob.check[~mask] = keep[~mask]
+    return o
+
+
+@pytest.mark.parametrize("precision", ["float32", "float64"])
+@pytest.mark.parametrize("n_envs", [1, 31, 33, 97])
+def test_small_and_ragged_batches_with_masked_resets_vs_oracle(n_envs, precision):
+    """Batches smaller than / not a multiple of the 32-env state block, and per-env (masked) resets in the
+    middle of an episode: envs leave lock-step, each keeps its own t and episode counter."""
+    from oracle.oracle import OracleBatch
+    seed = 5
+    f64 = precision == "float64"
+    env = _env(n_envs, precision, number_of_chargers=10, seed=seed, enable_requested_state_of_charge=True)
+    cfg = env.cfg
+    ob = OracleBatch(cfg, n_envs, n_threads=2)
+    obs = env.reset().cpu().numpy()
+    ob.sample(seed, 0, 0)
+    o_ref = ob.observe()
+    assert np.array_equal(obs, o_ref) if f64 else np.allclose(obs, o_ref, rtol=1e-5, atol=1e-6)
+    rng = np.random.default_rng(n_envs)
+    lo, hi = cfg.action_bounds()
+    episode = np.zeros(n_envs, np.uint32)
+    for s in range(60):
+        if s in (7, 19, 40):          # reset a random subset mid-episode (battery SoC is kept: quirk Q8)
+            mask = rng.random(n_envs) < 0.4
+            mask[0] = True
+            episode[mask] += 1
+            env.reset(mask=torch.tensor(mask, device="cuda:0"))
+            ob.sample(seed, 0, episode, mask=mask)
+            o_ref = _observe_masked(ob, mask)
+            got = env.obs.cpu().numpy()
+            assert np.array_equal(got[mask], o_ref[mask]) if f64 else np.allclose(got[mask], o_ref[mask], rtol=1e-5, atol=1e-6)
+        a = branchy_actions(rng, lo, hi, (n_envs,))
+        a_dev = torch.tensor(a, device="cuda:0", dtype=env.real)
+        a_or = a if f64 else a.astype(np.float32).astype(np.float64)
+        near = penalty_margin_distance(ob) < (0 if f64 else 1e-5)
+        o_ref, r_ref, d_ref = ob.step(a_or)
+        obs, rew, done, _, _ = env.step(a_dev)
+        obs, rew, done = obs.cpu().numpy(), rew.cpu().numpy(), done.cpu().numpy()
+        assert np.array_equal(done, d_ref), s
+        if d_ref.any():               # auto-reset of the envs that finished their day
+            fin = d_ref.astype(bool)
+            episode[fin] += 1
+            ob.sample(seed, 0, episode, mask=fin)
+            o_new = _observe_masked(ob, fin)
+            o_ref = np.where(fin[:, None], o_new, o_ref)
+        if f64:
+            assert np.array_equal(obs, o_ref), s
+            assert _ulp_diff(rew, r_ref).max() <= 4, s
+        else:
+            assert_close_f32("obs", obs, o_ref, atol=1e-6)
+            assert_close_f32("reward", rew, r_ref, atol=1e-5, mask=~near)
+    st = env.env_state()
+    assert np.array_equal(st["t"], ob.t) and np.array_equal(st["episode"], episode)
+    assert env.error_flags() == 0
+    env.close()
+
+
 def test_step_is_cuda_graph_capturable():
     """sng_step makes no hidden allocation or synchronisation: an episode of steps captured in a CUDA graph
     and replayed equals the same steps launched one by one."""
