@@ -72,6 +72,8 @@ template <typename real> struct Params {
     int i4, i10, i1;  // int(4/dt), int(10/dt), int(1/dt): charging_station.py:271-279
     int off_soc, off_dep, off_batt;
     int max_togo;     // penalty-check window: 0 none, 1 on_departure, 3 sparse, 1<<20 dense
+    int has_req;      // 0: every vehicle requests SoC 1.0 (sampling without enable_requested_state_of_charge): the
+                      //    requested-SoC plane is neither read nor written
     real dt, ev_pmax, ev_eff, b_cap, b_pmax, b_eff, b_dod, b_soc0, sell, cost_w, batt_w, margin;
     // shared read-only tables in global memory (L1-resident; every env of a lock-stepped batch reads the same entry)
     const real *pv_power, *irr_norm, *price, *price_norm;  // [table_len]
@@ -209,10 +211,10 @@ __device__ __forceinline__ Vehicle<real> fetch_vehicle(const Params<real> &p, in
 
 // Install vehicle `v` at the spot whose plane-0 word is *sp (planes are kBlock words apart).
 template <typename real>
-__device__ __forceinline__ void store_vehicle(typename WordOf<real>::type *sp, const Vehicle<real> &v)
+__device__ __forceinline__ void store_vehicle(typename WordOf<real>::type *sp, const Vehicle<real> &v, bool has_req)
 {
     sp[PL_HDR * kBlock] = v.hdr;
-    sp[PL_REQ * kBlock] = real_to_word(v.req);
+    if (has_req) sp[PL_REQ * kBlock] = real_to_word(v.req);
     sp[PL_SOC * kBlock] = real_to_word(v.soc0);   // the step at `arr` starts from the arrival SoC (charger.py:62-67)
 }
 
@@ -326,7 +328,7 @@ __device__ __forceinline__ void begin_episode(const Params<real> &p, int N, long
         if (next == 0u) v = fetch_vehicle(p, N, e, i, episode, 0);
         // the dense SoC array holds the arrival SoC at slot `arr` (charging_station.py:257-259),
         // so the reset observation shows it for vehicles arriving at t = 0
-        store_vehicle<real>(spot + (size_t)i * (kPlanes * kBlock), v);
+        store_vehicle<real>(spot + (size_t)i * (kPlanes * kBlock), v, p.has_req != 0);
         const bool present = (v.hdr & 0xFFu) == 0u;
         obs[off_soc + i] = present ? (float)v.soc0 : 0.0f;
         obs[off_dep + i] = present ? dep_lookup<SMEM>(p, dep_base, (int)((v.hdr >> 8) & 0xFFu)) : 0.0f;
@@ -348,14 +350,15 @@ template <typename real, int NCT> struct StateRegs {
 };
 
 template <typename real, int CH>
-__device__ __forceinline__ void load_spots(const typename WordOf<real>::type *spot, int c, typename WordOf<real>::type (&h)[CH],
-                                           typename WordOf<real>::type (&r)[CH], typename WordOf<real>::type (&s)[CH])
+__device__ __forceinline__ void load_spots(const typename WordOf<real>::type *spot, int c, bool has_req,
+                                           typename WordOf<real>::type (&h)[CH], typename WordOf<real>::type (&r)[CH],
+                                           typename WordOf<real>::type (&s)[CH])
 {
 #pragma unroll
     for (int j = 0; j < CH; ++j) {
         const typename WordOf<real>::type *sp = spot + (size_t)(c + j) * (kPlanes * kBlock);
         h[j] = sp[PL_HDR * kBlock];
-        r[j] = sp[PL_REQ * kBlock];
+        r[j] = has_req ? sp[PL_REQ * kBlock] : real_to_word((typename std::conditional<sizeof(typename WordOf<real>::type) == 4, float, double>::type)1);
         s[j] = sp[PL_SOC * kBlock];
     }
 }
@@ -366,7 +369,7 @@ __device__ __forceinline__ void load_state(const Params<real> &p, long long e, c
                                            StateRegs<real, NCT> &st)
 {
     st.es = p.envst[e];
-    load_spots<real, Chunk<NCT>::value>(spot, 0, st.h, st.r, st.s);
+    load_spots<real, Chunk<NCT>::value>(spot, 0, p.has_req != 0, st.h, st.r, st.s);
 }
 
 // Discharging an EV (V2X) -- Charger.discharge_vehicle, charger.py:108-140.  Kept out of line: the
@@ -469,7 +472,7 @@ __device__ __forceinline__ Arrivals env_step(const Params<real> &p, long long e,
 #pragma unroll
             for (int j = 0; j < CH; ++j) { wh[j] = st.h[j]; wr[j] = st.r[j]; ws[j] = st.s[j]; }
         } else {
-            load_spots<real, CH>(spot, c, wh, wr, ws);
+            load_spots<real, CH>(spot, c, p.has_req != 0, wh, wr, ws);
         }
 #pragma unroll
         for (int j = 0; j < CH; ++j) {
@@ -537,7 +540,7 @@ __device__ __forceinline__ Arrivals env_step(const Params<real> &p, long long e,
                 if (NCT) {
                     arrivals |= (decltype(arrivals))1 << i;
                 } else {                                   // generic kernel: admit the arriving vehicle in place
-                    store_vehicle<real>(sp, fetch_vehicle(p, N, e, i, episode, tn));
+                    store_vehicle<real>(sp, fetch_vehicle(p, N, e, i, episode, tn), p.has_req != 0);
                 }
             }
         }
@@ -623,7 +626,7 @@ __device__ __forceinline__ Arrivals env_step(const Params<real> &p, long long e,
         while (!COOP && arrivals) {
             const int i = (NCT > 32) ? __ffsll((long long)arrivals) - 1 : __ffs((int)arrivals) - 1;
             arrivals &= arrivals - 1;
-            store_vehicle<real>(spot + (size_t)i * SP, fetch_vehicle(p, N, e, i, episode, tn));
+            store_vehicle<real>(spot + (size_t)i * SP, fetch_vehicle(p, N, e, i, episode, tn), p.has_req != 0);
         }
         es.t_ep = (episode << 8) | (uint32_t)tn;
     } else {
@@ -685,7 +688,7 @@ __device__ __forceinline__ void admit_arrivals_warp(const Params<real> &p, long 
         const int tn = __shfl_sync(FULL, a.tn, src);
         if (mine)
             store_vehicle<real>(block_spot + (size_t)i * (kPlanes * kBlock) + src,
-                                fetch_vehicle(p, NCT, e0 + src, i, episode, tn));
+                                fetch_vehicle(p, NCT, e0 + src, i, episode, tn), p.has_req != 0);
     }
     __syncwarp();                                 // the queue may be refilled by the next step
 }

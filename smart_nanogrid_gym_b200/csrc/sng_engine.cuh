@@ -472,6 +472,7 @@ public:
         p.seed_lo = (uint32_t)seed;
         p.seed_hi = (uint32_t)(seed >> 32);
         p.mode = MODE_SAMPLE;
+        p.has_req = p.req_soc;
         rc = launch_reset(mask, first ? 1 : 0, 1, reset_battery, st);
         if (rc == SNG_OK) started = true;
         return rc;
@@ -537,6 +538,7 @@ public:
         }
         if (!started && buf.err) SNG_CUDA(cudaMemsetAsync(buf.err, 0, sizeof(uint32_t) * E, st));
         p.mode = MODE_REPLAY;
+        p.has_req = 1;
         rc = launch_reset(nullptr, 0, 0, 0, st);
         SNG_CUDA(cudaStreamSynchronize(st));  // `plan` staging vector goes out of scope
         if (rc == SNG_OK) started = true;
