@@ -311,7 +311,9 @@ def main():
 
     # one episode's worth of launches captured in a CUDA graph (removes the Python / driver launch cost
     # from the timed region; the kernels and their work are unchanged)
-    gsteps = args.graph_steps if args.graph_steps > 0 and args.steps % max(args.graph_steps, 1) == 0 else 0
+    gsteps = 0
+    if args.graph_steps > 0:     # the largest graph length <= --graph-steps that divides K exactly
+        gsteps = next((g for g in range(min(args.graph_steps, args.steps), 1, -1) if args.steps % g == 0), 0)
     graph = None
     if gsteps:
         side = torch.cuda.Stream(device=dev)
@@ -348,7 +350,22 @@ def main():
     barrier()
     ms = ev0.elapsed_time(ev1)
     launches = args.steps if graph is not None else env.launch_count - launches0
-    clocks = sampler.stop()
+    clock_window = "timed region"
+    if ms >= 150.0:
+        clocks = sampler.stop()
+    else:
+        # the timed region is shorter than a few nvidia-smi samples: keep sampling while the same kernel
+        # runs on (untimed), so that the clock record is taken under this load
+        clock_window = "timed region + %d untimed steps of the same kernel" % 0
+        extra = 0
+        t_end = time.perf_counter() + 0.4
+        while time.perf_counter() < t_end:
+            run_steps(gsteps or 8)
+            torch.cuda.synchronize(dev)
+            extra += gsteps or 8
+        clock_window = "timed region + %d untimed steps of the same kernel" % extra
+        clocks = sampler.stop()
+    clocks["window"] = clock_window
     t = torch.tensor([ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
