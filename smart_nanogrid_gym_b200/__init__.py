@@ -5,6 +5,8 @@ Public surface:
   BatchedSmartNanogridEnv   E envs per CUDA launch, torch tensors, zero-copy (needs a GPU)
   SmartNanogridEnv, make    the reference's single-env gym API (E = 1, float64 build)
   ScheduleRecords, ...      schedule containers / initial_values.json I/O
+  EpisodeRecorder           prediction_results.json export for one env (trace.py)
+  collect_rollout, ...      on-device PPO rollout collection + GAE kernel (rollout.py)
 """
 from .config import NanogridConfig, PENALTY_MODES  # noqa: F401
 from .schedule import (ScheduleRecords, records_from_dense, dense_from_records, concat_records,  # noqa: F401
@@ -19,6 +21,12 @@ def __getattr__(name):  # torch / CUDA are only imported when the env classes ar
     if name == "BatchedSmartNanogridEnv":
         from .batched_env import BatchedSmartNanogridEnv
         return BatchedSmartNanogridEnv
+    if name == "EpisodeRecorder":
+        from .trace import EpisodeRecorder
+        return EpisodeRecorder
+    if name in ("MlpPolicy", "RolloutBuffer", "collect_rollout", "GraphedRollout"):
+        from . import rollout
+        return getattr(rollout, name)
     if name in ("SmartNanogridEnv", "make", "register_with_gym", "ENV_ID"):
         from . import env
         return getattr(env, name)

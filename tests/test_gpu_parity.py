@@ -507,3 +507,40 @@ def test_single_env_gym_adapter_matches_reference_recording():
     obs, info = env.reset()
     assert obs.shape == (17,)
     env.close()
+
+
+@pytest.mark.parametrize("tag", ["g1", "g2"])
+def test_prediction_results_trace_matches_reference_recording(tag, tmp_path):
+    """replaying the reference's recorded episode (its own initial_values.json + recorded
+    actions) and exporting `prediction_results.json` reproduces every recorded series of the reference's file
+    (float32-action signature of the recording: <= 3e-6; Total_cost was recorded with the old 0.8 cost weight,
+    SURVEY section 4, so it is checked against 0.8 * |cost| + penalty)."""
+    from smart_nanogrid_gym_b200 import BatchedSmartNanogridEnv, load_initial_values_json
+    from smart_nanogrid_gym_b200.trace import EpisodeRecorder
+    rec = load_initial_values_json(os.path.join(GOLD, "%s_initial_values.json" % tag))
+    with open(os.path.join(GOLD, "%s_prediction_results.json" % tag)) as fp:
+        ref = json.load(fp)
+    env = BatchedSmartNanogridEnv(1, precision="float64", auto_reset=False, want_diagnostics=True,
+                                  number_of_chargers=4, **DEFAULT)
+    shift = ref["Utilized_solar_energy"][12] / env.cfg.pv_power[12]
+    env.load_schedule(rec, pv_shift=shift, soc_b=ref["Initial_battery_state_of_charge"])
+    tr = EpisodeRecorder(env, 0)
+    for t in range(24):
+        a = np.array(ref["Charger_actions"][t] + [ref["Battery_action"][t]])
+        tr.step(torch.tensor(a[None, :], device="cuda:0", dtype=torch.float64))
+    out = tr.results()
+    assert sorted(out.keys()) == sorted(ref.keys())
+    path = tmp_path / "prediction_results.json"
+    tr.save(str(path))
+    with open(path) as fp:
+        assert sorted(json.load(fp).keys()) == sorted(ref.keys())
+    for key in ref:
+        if key == "Total_cost":
+            want = 0.8 * np.abs(np.array(ref["Grid_energy_cost"])) + np.array(ref["Total_penalties"])
+            assert np.allclose(np.array(ref[key]), want, atol=1e-9)          # what the recording used
+            ours = 0.75 * np.abs(np.array(out["Grid_energy_cost"])) + np.array(out["Total_penalties"])
+            assert np.allclose(np.array(out[key]), ours, atol=1e-9)          # what the current code uses
+            continue
+        assert np.allclose(np.array(out[key], dtype=np.float64), np.array(ref[key], dtype=np.float64),
+                           rtol=3e-6, atol=3e-6), key
+    env.close()
