@@ -652,6 +652,7 @@ public:
                 case 4: return launch_step_n<4, 8>(q, actions, obs, reward, done, n_steps, bulk, st);
                 case 8: return launch_step_n<8, 8>(q, actions, obs, reward, done, n_steps, bulk, st);
                 case 10: return launch_step_n<10, 8>(q, actions, obs, reward, done, n_steps, bulk, st);
+                case 32: return launch_step_n<32, 8>(q, actions, obs, reward, done, n_steps, bulk, st);
                 case 64: return launch_step_n<64, 8>(q, actions, obs, reward, done, n_steps, bulk, st);
                 default: break;
                 }
