@@ -49,17 +49,20 @@ EngineBase *make_engine_f64(const sng_config &cfg, int device, std::string &err)
 // ------------------------------------------------------------------------------------------
 // Step kernels.  One warp = one block of 32 consecutive envs, one thread per env; warps are
 // independent (the only CTA-wide barrier publishes the departure table).  Action rows arrive and
-// observation rows leave through shared memory, moved by the copy engine (one cp.async.bulk per warp
-// and direction, mbarrier complete_tx / bulk_group); the blocked state is read and written with
-// coalesced 128-byte warp accesses; env_step() is the same body everywhere.
+// observation rows leave through shared memory, moved by the copy engine (cp.async.bulk, mbarrier
+// complete_tx / bulk_group) or by 16-byte coalesced vector accesses (STAGE_* below); the blocked state is
+// read and written with coalesced 128-byte warp accesses; env_step() is the same body everywhere.
 //
-//   step_pipelined_kernel  the production single-step kernel: persistent warps walk the blocks
-//                          grid-stride and software-pipeline them -- while block k is computed, the
-//                          state words of block k+1 are already loading into registers and its action
-//                          rows into the other shared-memory stage, so DRAM never waits for the math.
-//   step_simple_kernel     one block per warp, no pipelining; any n_steps (the rollout: the same warp
-//                          advances its envs n_steps times, one action / obs / reward / done slab per
-//                          step), partial last block, and every row-staging mode (STAGE_*).
+//   step_simple_kernel     THE production kernel: one block per warp, all loads issued up front, latency
+//                          hidden by 32 resident warps per SM.  Also the rollout (n_steps > 1: the same
+//                          warp advances its envs n_steps times, one action / obs / reward / done slab
+//                          per step), the partial last block, and every row-staging mode.
+//   step_pipelined_kernel  an alternative kept for comparison: persistent warps walk the blocks
+//                          grid-stride and software-pipeline them (state words of block k+1 loading
+//                          into registers, its action rows into a second shared-memory stage, while
+//                          block k is computed).  Measured slower: the prefetch registers
+//                          cost a third of the resident warps, and the step is bound by per-warp
+//                          instruction latency rather than by DRAM latency.
 // ------------------------------------------------------------------------------------------
 template <typename real> __device__ __forceinline__ void publish_dep_table(const Params<real> &p)
 {
