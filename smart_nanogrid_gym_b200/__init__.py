@@ -5,6 +5,7 @@ Public surface:
   BatchedSmartNanogridEnv   E envs per CUDA launch, torch tensors, zero-copy (needs a GPU)
   SmartNanogridEnv, make    the reference's single-env gym API (E = 1, float64 build)
   ScheduleRecords, ...      schedule containers / initial_values.json I/O
+  SmartNanogridVecEnv       Stable-Baselines3-style VecEnv facade (numpy in / out, terminal_observation in infos)
   EpisodeRecorder           prediction_results.json export for one env (trace.py)
   collect_rollout, ...      on-device PPO rollout collection + GAE kernel (rollout.py)
 """
@@ -21,6 +22,9 @@ def __getattr__(name):  # torch / CUDA are only imported when the env classes ar
     if name == "BatchedSmartNanogridEnv":
         from .batched_env import BatchedSmartNanogridEnv
         return BatchedSmartNanogridEnv
+    if name == "SmartNanogridVecEnv":
+        from .vec_env import SmartNanogridVecEnv
+        return SmartNanogridVecEnv
     if name == "EpisodeRecorder":
         from .trace import EpisodeRecorder
         return EpisodeRecorder

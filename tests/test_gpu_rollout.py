@@ -93,3 +93,34 @@ def test_graphed_rollout_equals_eager():
         s_e, s_g = s_e.clone(), s_g.clone()
     env_e.close()
     env_g.close()
+
+
+def test_sb3_style_vec_env_protocol():
+    """numpy in / numpy out, 4-tuple step_wait, auto-reset with infos[i]['terminal_observation'] (SB3 VecEnv)."""
+    from smart_nanogrid_gym_b200 import BatchedSmartNanogridEnv
+    from smart_nanogrid_gym_b200.vec_env import SmartNanogridVecEnv
+    E = 300
+    venv = SmartNanogridVecEnv(E, seed=4, **KW)
+    twin = BatchedSmartNanogridEnv(E, seed=4, want_terminal_obs=True, **KW)
+    obs = venv.reset()
+    assert isinstance(obs, np.ndarray) and obs.shape == (E, 29) and obs.dtype == np.float32
+    assert np.array_equal(obs, twin.reset().cpu().numpy())
+    assert venv.observation_space.shape == (29,) and venv.action_space.shape == (11,) and venv.num_envs == E
+    rng = np.random.default_rng(0)
+    for s in range(26):
+        a = rng.uniform(venv.action_space.low, venv.action_space.high, size=(E, 11)).astype(np.float32)
+        venv.step_async(a)
+        o, r, d, infos = venv.step_wait()
+        to, tr, td, _, _ = twin.step(torch.tensor(a, device="cuda:0"))
+        assert o.dtype == np.float32 and r.dtype == np.float32 and d.dtype == bool and len(infos) == E
+        assert np.array_equal(o, to.cpu().numpy()) and np.array_equal(r, tr.cpu().numpy()) and np.array_equal(d, td.cpu().numpy().astype(bool))
+        if s == 23:
+            assert d.all()
+            term = twin.terminal_obs.cpu().numpy()
+            for i in (0, 17, E - 1):
+                assert np.array_equal(infos[i]["terminal_observation"], term[i]) and infos[i]["TimeLimit.truncated"] is False
+        else:
+            assert not d.any() and all(info == {} for info in infos)
+    assert venv.env_is_wrapped(object) == [False] * E and len(venv.get_attr("num_envs")) == E
+    venv.close()
+    twin.close()
