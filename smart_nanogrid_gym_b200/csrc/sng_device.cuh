@@ -446,7 +446,9 @@ __device__ __forceinline__ Arrivals env_step(const Params<real> &p, long long e,
     const int tn = t + 1;
     const bool is_done = (tn == p.T);
     const uint32_t tn_key = is_done ? 0x100u : (uint32_t)tn;   // never equals a header's `next` byte when done
-    real pos = 0, neg = 0, pen_veh = 0;
+    // Station sums are kept per spot PARITY (even spots, odd spots) and combined at the end: a fixed
+    // association order that a two-lanes-per-env mapping (lane = parity) reproduces bit for bit.
+    real pos_e = 0, pos_o = 0, neg_e = 0, neg_o = 0, pen_e = 0, pen_o = 0;
     uint32_t err = 0;
     // spots whose next vehicle arrives at tn (specialised kernels only: N <= 64)
     typename std::conditional<(NCT > 32), unsigned long long, uint32_t>::type arrivals = 0, discharging = 0;
@@ -477,6 +479,7 @@ __device__ __forceinline__ Arrivals env_step(const Params<real> &p, long long e,
 #pragma unroll
         for (int j = 0; j < CH; ++j) {
             const int i = c + j;
+            const int par = (NCT ? j : i) & 1;                 // spot parity (chunks of the specialised kernels are even)
             const uint32_t hd = (uint32_t)wh[j];
             const real rq = word_to_real(wr[j], (real)0);
             const real s_prev = word_to_real(ws[j], (real)0);  // SoC column t-1 (the arrival SoC when arr == t, charger.py:62-67)
@@ -493,7 +496,8 @@ __device__ __forceinline__ Arrivals env_step(const Params<real> &p, long long e,
             const real lower = p.margin * rq;                  // penaliser.py:72
             if (checked && s_prev < rq - lower) {              // :78
                 const real d = (rq - s_prev) * (real)10;
-                pen_veh = pen_veh + d * d;                     // :79 (Python `** 2`)
+                real &pen = (par && !EXACT) ? pen_o : pen_e;   // the float64 build sums in spot order like the reference
+                pen = pen + d * d;                             // :79 (Python `** 2`)
             }
 
             const bool present = arr <= t && t < dep;          // charger.occupancy[t] == 1
@@ -518,7 +522,7 @@ __device__ __forceinline__ Arrivals env_step(const Params<real> &p, long long e,
                 if (EXACT) {
                     if (P > 0) cpos[npos++] = (double)P;
                 } else {
-                    pos += P;                                  // P >= 0 here
+                    (par ? pos_o : pos_e) += P;                // P >= 0 here
                 }
             } else if (present) {                              // a < 0 (or NaN): V2X discharge
                 const PowerSoc<real> r = discharge_vehicle(a * p.ev_pmax * p.ev_eff, p.dt, s_prev, (real)((hd >> 16) & 0xFFu));
@@ -528,8 +532,8 @@ __device__ __forceinline__ Arrivals env_step(const Params<real> &p, long long e,
                     if (P < 0) cneg[nneg++] = (double)P;
                     if (P > 0) cpos[npos++] = (double)P;
                 } else {
-                    if (P < 0) neg += P;
-                    if (P > 0) pos += P;
+                    if (P < 0) (par ? neg_o : neg_e) += P;
+                    if (P > 0) (par ? pos_o : pos_e) += P;
                 }
             }
             word *sp = spot + (size_t)i * SP;
@@ -546,6 +550,7 @@ __device__ __forceinline__ Arrivals env_step(const Params<real> &p, long long e,
         }
         io.end_chunk(c + CH);
     }
+    real pos, neg;
     if (EXACT) {
         neg = (real)numpy_sum(cneg, nneg);
         pos = (real)numpy_sum(cpos, npos);
@@ -557,13 +562,23 @@ __device__ __forceinline__ Arrivals env_step(const Params<real> &p, long long e,
         const uint32_t hd = (uint32_t)sp[PL_HDR * kBlock];
         const real s_prev = word_to_real(sp[PL_SOC * kBlock], (real)0);   // the hot loop left it unchanged
         const PowerSoc<real> r = discharge_vehicle(io.action_at(i) * p.ev_pmax * p.ev_eff, p.dt, s_prev, (real)((hd >> 16) & 0xFFu));
-        if (r.P < 0) neg += r.P;
-        if (r.P > 0) pos += r.P;
+        if (i & 1) {
+            if (r.P < 0) neg_o += r.P;
+            if (r.P > 0) pos_o += r.P;
+        } else {
+            if (r.P < 0) neg_e += r.P;
+            if (r.P > 0) pos_e += r.P;
+        }
         sp[PL_SOC * kBlock] = real_to_word(r.soc);
         io.fix_soc(i, (float)r.soc);
     }
 
     // ---- env-level phase: CentralManagementSystem.manage_nanogrid (central_management_system.py:99-113) ----
+    if (!EXACT) {
+        pos = pos_e + pos_o;
+        neg = neg_e + neg_o;
+    }
+    const real pen_veh = pen_e + pen_o;
     const real total_power = pos + neg;                                   // :105
     if (total_power < (real)0 && !p.v2x) err |= FLAG_NEG_DEMAND;          // reference raises, :158-159
     const real solar = p.pv ? __ldg(p.pv_power + t) * es.pv_shift : (real)0;   // :99-103
