@@ -193,9 +193,10 @@ int64_t sng_launch_count(const sng_env *env);
  * both ways (unaligned buffers and a partial last block always take the scalar path); number of env
  * chunks sng_step_host pipelines over PCIe (0 = auto). */
 int sng_set_tuning(sng_env *env, int warps_per_cta, int use_generic_kernel, int use_bulk_copy, int host_chunks);
-/* Tuning knob: which single-step kernel runs: 0 (default) or 2 one 32-env block per warp, 1 the
- * persistent software-pipelined kernel (measured slower); cap on resident CTAs per SM of
- * the pipelined kernel (0 = as many as fit). */
+/* Tuning knob: which step kernel runs: 0 (default) one 32-env block per warp, with two lanes per env for
+ * specialised stations of more than 32 spots; 1 the persistent software-pipelined kernel (measured slower,
+ * see DESIGN.md); 2 one block per warp and always one lane per env.  ctas_per_sm caps the resident CTAs
+ * per SM of the pipelined kernel (0 = as many as fit). */
 int sng_set_pipeline(sng_env *env, int kernel_variant, int ctas_per_sm);
 
 #ifdef __cplusplus

@@ -131,7 +131,8 @@ class BatchedSmartNanogridEnv:
         nat.check(self._lib.sng_set_tuning(self._h, warps_per_cta, use_generic_kernel, use_bulk_copy, host_chunks))
 
     def set_pipeline(self, kernel_variant=0, ctas_per_sm=0):
-        """0 one 32-env block per warp (default), 1 persistent pipelined kernel (include/sng.h)."""
+        """0 default (two lanes per env for large stations), 1 persistent pipelined kernel, 2 always one lane per env
+        (include/sng.h)."""
         nat.check(self._lib.sng_set_pipeline(self._h, kernel_variant, ctas_per_sm))
 
     def _plane(self, f):

@@ -1,7 +1,8 @@
 // sng_device.cuh -- device-side types, the counter-based schedule sampler and the per-environment
 // step body.
 //
-// Thread mapping: ONE THREAD PER ENVIRONMENT, 32 consecutive envs per warp.  Per-spot state is a
+// Thread mapping: ONE THREAD PER ENVIRONMENT, 32 consecutive envs per warp (two lanes per env, 16 envs
+// per warp, for 64-spot stations whose rows would otherwise leave 8 warps per SM).  Per-spot state is a
 // structure of arrays blocked by 32 envs ([E/32][N][3 planes][32]), so lane l of a warp reads plane f
 // of spot i of its env from word  ((block*N + i)*3 + f)*32 + l : every state load / store of a warp is
 // one full 128-byte line, and all of a thread's accesses are constant offsets from one base pointer.
@@ -311,15 +312,17 @@ __device__ __forceinline__ void write_obs_env(const Params<real> &p, float *obs,
 // per spot, schedule the first arrival of the day (and admit it when it is at step 0), clear the SoC
 // state (clear_initialisation_variables, charging_station.py:138-150) and write the reset observation.
 // `spot` points at (this env, spot 0, plane 0).
-template <typename real, int NCT, int ND, bool SMEM>
+// With L lanes per env, lane `sub` handles the spots sub, sub + L, ... (`spot` points at its first one)
+// and lane 0 writes the env-level entries.
+template <typename real, int NCT, int ND, bool SMEM, int L = 1>
 __device__ __forceinline__ void begin_episode(const Params<real> &p, int N, long long e,
                                               typename WordOf<real>::type *spot, uint32_t episode, real shift,
-                                              real soc_b, float *obs)
+                                              real soc_b, float *obs, int sub = 0)
 {
     const int off_soc = Offsets<NCT, ND>::soc(p), off_dep = Offsets<NCT, ND>::dep(p);
     const uint32_t dep_base = SMEM ? dep_table_base() : 0u;
 #pragma unroll 1
-    for (int i = 0; i < N; ++i) {
+    for (int i = sub; i < N; i += L) {
         const uint32_t next = first_arrival(p, N, e, i, episode);
         Vehicle<real> v;
         v.hdr = make_hdr(kNoVehicle, 0, 0, next);
@@ -328,12 +331,12 @@ __device__ __forceinline__ void begin_episode(const Params<real> &p, int N, long
         if (next == 0u) v = fetch_vehicle(p, N, e, i, episode, 0);
         // the dense SoC array holds the arrival SoC at slot `arr` (charging_station.py:257-259),
         // so the reset observation shows it for vehicles arriving at t = 0
-        store_vehicle<real>(spot + (size_t)i * (kPlanes * kBlock), v, p.has_req != 0);
+        store_vehicle<real>(spot + (size_t)(i / L) * (L * kPlanes * kBlock), v, p.has_req != 0);
         const bool present = (v.hdr & 0xFFu) == 0u;
         obs[off_soc + i] = present ? (float)v.soc0 : 0.0f;
         obs[off_dep + i] = present ? dep_lookup<SMEM>(p, dep_base, (int)((v.hdr >> 8) & 0xFFu)) : 0.0f;
     }
-    write_obs_env<real, NCT, ND>(p, obs, 0, shift, soc_b);   // battery SoC survives resets (quirk Q8)
+    if (L == 1 || sub == 0) write_obs_env<real, NCT, ND>(p, obs, 0, shift, soc_b);   // battery SoC survives resets (quirk Q8)
 }
 
 // Spots whose state loads are issued together (and, in the pipelined kernel, one block ahead).
@@ -349,14 +352,16 @@ template <typename real, int NCT> struct StateRegs {
     word h[Chunk<NCT>::value], r[Chunk<NCT>::value], s[Chunk<NCT>::value];
 };
 
-template <typename real, int CH>
+// L lanes share an env (L = 1, or 2 for large stations): lane `sub` owns the spots sub, sub + L, ...;
+// `spot` points at its first one and its k-th ("virtual") spot is L * kPlanes * kBlock words further.
+template <typename real, int CH, int L>
 __device__ __forceinline__ void load_spots(const typename WordOf<real>::type *spot, int c, bool has_req,
                                            typename WordOf<real>::type (&h)[CH], typename WordOf<real>::type (&r)[CH],
                                            typename WordOf<real>::type (&s)[CH])
 {
 #pragma unroll
     for (int j = 0; j < CH; ++j) {
-        const typename WordOf<real>::type *sp = spot + (size_t)(c + j) * (kPlanes * kBlock);
+        const typename WordOf<real>::type *sp = spot + (size_t)(c + j) * (L * kPlanes * kBlock);
         h[j] = sp[PL_HDR * kBlock];
         r[j] = has_req ? sp[PL_REQ * kBlock] : real_to_word((typename std::conditional<sizeof(typename WordOf<real>::type) == 4, float, double>::type)1);
         s[j] = sp[PL_SOC * kBlock];
@@ -364,12 +369,13 @@ __device__ __forceinline__ void load_spots(const typename WordOf<real>::type *sp
 }
 
 // Issue the loads of one env's scalars and first state chunk (consumed by env_step, possibly one block later).
-template <typename real, int NCT>
+// (MCT = spots per lane at compile time = N / L.)
+template <typename real, int MCT, int L = 1>
 __device__ __forceinline__ void load_state(const Params<real> &p, long long e, const typename WordOf<real>::type *spot,
-                                           StateRegs<real, NCT> &st)
+                                           StateRegs<real, MCT> &st)
 {
     st.es = p.envst[e];
-    load_spots<real, Chunk<NCT>::value>(spot, 0, p.has_req != 0, st.h, st.r, st.s);
+    load_spots<real, Chunk<MCT>::value, L>(spot, 0, p.has_req != 0, st.h, st.r, st.s);
 }
 
 // Discharging an EV (V2X) -- Charger.discharge_vehicle, charger.py:108-140.  Kept out of line: the
@@ -403,20 +409,21 @@ __device__ __noinline__ PowerSoc<real> discharge_vehicle(real power, real dt, re
 //           spots] tiles to save shared memory was measured 30 % slower at N = 64 -- its 64-byte row
 //           pieces are partial-sector writes -- and was dropped; the hooks remain.)
 // ------------------------------------------------------------------------------------------
-template <typename real> struct RowIO {
-    const real *act;   // [A] this env's action row
+template <typename real, int L = 1> struct RowIO {
+    const real *act;   // this env's action row, advanced by `sub`: the lane's k-th spot is act[k * L]
+    const real *act0;  // this env's action row (battery action, cold paths)
     float *obs;        // [D] this env's observation row
-    int off_soc, off_dep;
+    int off_soc, off_dep;   // offsets of the lane's first spot (advanced by `sub`)
     __device__ __forceinline__ void begin_chunk(int) const {}
     __device__ __forceinline__ void end_chunk(int) const {}
-    __device__ __forceinline__ real action(int c, int j) const { return act[c + j]; }
-    __device__ __forceinline__ real action_at(int i) const { return act[i]; }
+    __device__ __forceinline__ real action(int c, int j) const { return act[(c + j) * L]; }
+    __device__ __forceinline__ real action_at(int i) const { return act0[i]; }     // i: real spot / action index
     __device__ __forceinline__ void put_spot(int c, int j, float soc, float dep) const
     {
-        obs[off_soc + c + j] = soc;
-        obs[off_dep + c + j] = dep;
+        obs[off_soc + (c + j) * L] = soc;
+        obs[off_dep + (c + j) * L] = dep;
     }
-    __device__ __forceinline__ void fix_soc(int i, float soc) const { obs[off_soc + i] = soc; }
+    __device__ __forceinline__ void fix_soc(int k, float soc) const { obs[off_soc + k * L] = soc; }   // k: the lane's k-th spot
     __device__ __forceinline__ float *row() const { return obs; }
     __device__ __forceinline__ float read_back(int k) const { return obs[k]; }
 };
@@ -428,17 +435,25 @@ struct Arrivals {
     int tn;
 };
 
-template <typename real, int NCT, int ND, bool EXACT, bool SMEM, bool COOP = false, typename IO = RowIO<real>>
+// L > 1 (specialised float32 kernels of large stations): L lanes of the warp share the env, lane `sub`
+// (= lane / (32 / L)) owns the spots sub, sub + L, ...; `spot` and the RowIO are advanced to its first
+// spot, the partial station sums are combined with a shuffle, every lane computes the env-level phase
+// and lane 0 alone writes its results.  All 32 lanes of the warp must be in env_step together then.
+template <typename real, int NCT, int ND, bool EXACT, bool SMEM, bool COOP = false, int L = 1, typename IO = RowIO<real, L>>
 __device__ __forceinline__ Arrivals env_step(const Params<real> &p, long long e, typename WordOf<real>::type *spot,
-                                             const StateRegs<real, NCT> &st, const IO &io, real *reward_out,
-                                             uint8_t *done_out)
+                                             const StateRegs<real, NCT / L> &st, const IO &io, real *reward_out,
+                                             uint8_t *done_out, int sub = 0)
 {
     float *const obs = io.row();   // env-level entries, reset observation
-    static_assert(!COOP || (NCT > 0 && NCT <= 32), "cooperative admission needs a 32-bit arrival mask");
+    static_assert(!COOP || (NCT > 0 && NCT <= 32 && L == 1), "cooperative admission needs a 32-bit arrival mask");
+    static_assert(L == 1 || (L == 2 && NCT > 0 && NCT % 2 == 0 && !EXACT), "two lanes per env: even compile-time N, float32");
     typedef typename WordOf<real>::type word;
+    constexpr int MCT = NCT / L;                               // spots per lane at compile time
     const int N = NCT ? NCT : p.N;
-    constexpr int CH = Chunk<NCT>::value;
-    constexpr int SP = kPlanes * kBlock;                       // words between consecutive spots of an env
+    const int M = NCT ? MCT : p.N;                             // spots this lane walks
+    constexpr int CH = Chunk<MCT>::value;
+    constexpr int SP = L * kPlanes * kBlock;                   // words between consecutive spots of this lane
+    const bool lead = (L == 1) || sub == 0;                    // writes the env-level results
     const int off_soc = Offsets<NCT, ND>::soc(p), off_dep = Offsets<NCT, ND>::dep(p);
     EnvSt<real> es = st.es;
     const int t = (int)(es.t_ep & 0xFFu);
@@ -451,7 +466,7 @@ __device__ __forceinline__ Arrivals env_step(const Params<real> &p, long long e,
     real pos_e = 0, pos_o = 0, neg_e = 0, neg_o = 0, pen_e = 0, pen_o = 0;
     uint32_t err = 0;
     // spots whose next vehicle arrives at tn (specialised kernels only: N <= 64)
-    typename std::conditional<(NCT > 32), unsigned long long, uint32_t>::type arrivals = 0, discharging = 0;
+    typename std::conditional<(MCT > 32), unsigned long long, uint32_t>::type arrivals = 0, discharging = 0;   // bit k: the lane's k-th spot
     constexpr bool DEFER = NCT > 0 && !EXACT;   // V2X discharges are finished after the (branch-free) hot loop
     double cpos[EXACT ? 256 : 1], cneg[EXACT ? 256 : 1];
     int npos = 0, nneg = 0;
@@ -467,19 +482,20 @@ __device__ __forceinline__ Arrivals env_step(const Params<real> &p, long long e,
     //      Charger.charge_or_discharge_vehicle (charger.py:37-140) and the lagged undercharge
     //      penalty (penaliser.py:39-87) ----
 #pragma unroll 1
-    for (int c = 0; c < N; c += CH) {
+    for (int c = 0; c < M; c += CH) {
         io.begin_chunk(c);
         word wh[CH], wr[CH], ws[CH];
         if (c == 0) {
 #pragma unroll
             for (int j = 0; j < CH; ++j) { wh[j] = st.h[j]; wr[j] = st.r[j]; ws[j] = st.s[j]; }
         } else {
-            load_spots<real, CH>(spot, c, p.has_req != 0, wh, wr, ws);
+            load_spots<real, CH, L>(spot, c, p.has_req != 0, wh, wr, ws);
         }
 #pragma unroll
         for (int j = 0; j < CH; ++j) {
-            const int i = c + j;
-            const int par = (NCT ? j : i) & 1;                 // spot parity (chunks of the specialised kernels are even)
+            const int i = c + j;                               // the lane's i-th spot = real spot i * L + sub
+            const int par = (L == 1) ? ((NCT ? j : i) & 1) : 0;   // spot parity (chunks of the specialised kernels are even;
+                                                               // with two lanes per env the lane IS the parity)
             const uint32_t hd = (uint32_t)wh[j];
             const real rq = word_to_real(wr[j], (real)0);
             const real s_prev = word_to_real(ws[j], (real)0);  // SoC column t-1 (the arrival SoC when arr == t, charger.py:62-67)
@@ -544,7 +560,7 @@ __device__ __forceinline__ Arrivals env_step(const Params<real> &p, long long e,
                 if (NCT) {
                     arrivals |= (decltype(arrivals))1 << i;
                 } else {                                   // generic kernel: admit the arriving vehicle in place
-                    store_vehicle<real>(sp, fetch_vehicle(p, N, e, i, episode, tn), p.has_req != 0);
+                    store_vehicle<real>(sp, fetch_vehicle(p, N, e, i * L + sub, episode, tn), p.has_req != 0);
                 }
             }
         }
@@ -556,13 +572,13 @@ __device__ __forceinline__ Arrivals env_step(const Params<real> &p, long long e,
         pos = (real)numpy_sum(cpos, npos);
     }
     while (DEFER && discharging) {   // cold pass: V2X discharges (and NaN actions) left out of the hot loop
-        const int i = (NCT > 32) ? __ffsll((long long)discharging) - 1 : __ffs((int)discharging) - 1;
+        const int i = (MCT > 32) ? __ffsll((long long)discharging) - 1 : __ffs((int)discharging) - 1;
         discharging &= discharging - 1;
         word *sp = spot + (size_t)i * SP;
         const uint32_t hd = (uint32_t)sp[PL_HDR * kBlock];
         const real s_prev = word_to_real(sp[PL_SOC * kBlock], (real)0);   // the hot loop left it unchanged
-        const PowerSoc<real> r = discharge_vehicle(io.action_at(i) * p.ev_pmax * p.ev_eff, p.dt, s_prev, (real)((hd >> 16) & 0xFFu));
-        if (i & 1) {
+        const PowerSoc<real> r = discharge_vehicle(io.action(i, 0) * p.ev_pmax * p.ev_eff, p.dt, s_prev, (real)((hd >> 16) & 0xFFu));
+        if ((L == 1) && (i & 1)) {
             if (r.P < 0) neg_o += r.P;
             if (r.P > 0) pos_o += r.P;
         } else {
@@ -574,6 +590,13 @@ __device__ __forceinline__ Arrivals env_step(const Params<real> &p, long long e,
     }
 
     // ---- env-level phase: CentralManagementSystem.manage_nanogrid (central_management_system.py:99-113) ----
+    if (L > 1) {   // this lane's spots all have parity `sub`: fetch the other parity's sums from the partner lane
+        constexpr uint32_t FULL = 0xffffffffu;
+        pos_o = __shfl_xor_sync(FULL, pos_e, 32 / L);
+        neg_o = __shfl_xor_sync(FULL, neg_e, 32 / L);
+        pen_o = __shfl_xor_sync(FULL, pen_e, 32 / L);
+        nan_probe += __shfl_xor_sync(FULL, nan_probe, 32 / L);
+    }
     if (!EXACT) {
         pos = pos_e + pos_o;
         neg = neg_e + neg_o;
@@ -620,8 +643,8 @@ __device__ __forceinline__ Arrivals env_step(const Params<real> &p, long long e,
     const real total_cost = p.cost_w * fabs(cost) + total_pen;            // accountant.py:35
     const real reward = -total_cost;                                      // ...environment.py:183
 
-    write_obs_env<real, NCT, ND>(p, obs, t, es.pv_shift, soc_b);          // obs at the pre-increment t, :173
-    if (p.diag) {
+    if (lead) write_obs_env<real, NCT, ND>(p, obs, t, es.pv_shift, soc_b);   // obs at the pre-increment t, :173
+    if (lead && p.diag) {
         real *diag = p.diag + (size_t)e * D_COUNT;
         diag[D_TOTAL_CH] = pos; diag[D_TOTAL_DIS] = neg; diag[D_SOLAR] = solar;
         diag[D_BATT_POWER] = batt_power; diag[D_GRID_POWER] = rem; diag[D_GRID_COST] = cost;
@@ -639,31 +662,38 @@ __device__ __forceinline__ Arrivals env_step(const Params<real> &p, long long e,
         // admit the vehicles that arrive at tn (the observation above does not show them: quirk Q5);
         // COOP: left to admit_arrivals_warp(), which spreads the warp's arrivals evenly over its lanes
         while (!COOP && arrivals) {
-            const int i = (NCT > 32) ? __ffsll((long long)arrivals) - 1 : __ffs((int)arrivals) - 1;
+            const int i = (MCT > 32) ? __ffsll((long long)arrivals) - 1 : __ffs((int)arrivals) - 1;
             arrivals &= arrivals - 1;
-            store_vehicle<real>(spot + (size_t)i * SP, fetch_vehicle(p, N, e, i, episode, tn), p.has_req != 0);
+            store_vehicle<real>(spot + (size_t)i * SP, fetch_vehicle(p, N, e, i * L + sub, episode, tn), p.has_req != 0);
         }
         es.t_ep = (episode << 8) | (uint32_t)tn;
     } else {
-        if (p.last_ret) p.last_ret[e] = ep_ret;
+        if (lead && p.last_ret) p.last_ret[e] = ep_ret;
         ep_ret = 0;
         if (p.auto_reset) {
+            // lanes sharing an env take this branch together: pair barriers keep the partner's row entries
+            // complete before they are copied and untouched until they have been
+            const uint32_t pair = (L == 1) ? 0u : ((1u << (threadIdx.x & 31)) | (1u << ((threadIdx.x & 31) ^ (32 / L))));
             if (p.tobs) {
+                if (L > 1) __syncwarp(pair);
                 float *tobs = p.tobs + (size_t)e * p.D;
-                for (int k = 0; k < p.D; ++k) tobs[k] = io.read_back(k);
+                for (int k = sub; k < p.D; k += L) tobs[k] = io.read_back(k);
             }
+            if (L > 1) __syncwarp(pair);
             episode = (episode + 1u) & 0xFFFFFFu;
             if (p.mode == MODE_SAMPLE) shift = sample_pv_shift(p, N, p.gid0 + (unsigned long long)e, episode);
-            begin_episode<real, NCT, ND, SMEM>(p, N, e, spot, episode, shift, soc_b, obs);
+            begin_episode<real, NCT, ND, SMEM, L>(p, N, e, spot, episode, shift, soc_b, obs, sub);
         }
         es.t_ep = (episode << 8);                                         // t wraps to 0, :178
     }
     es.soc_b = soc_b;
     es.pv_shift = shift;
     es.ep_ret = ep_ret;
-    p.envst[e] = es;
-    reward_out[e] = reward;
-    done_out[e] = is_done ? 1 : 0;
+    if (lead) {
+        p.envst[e] = es;
+        reward_out[e] = reward;
+        done_out[e] = is_done ? 1 : 0;
+    }
     if (err && p.err) atomicOr(p.err + e, err);
     return out;
 }

@@ -123,8 +123,8 @@ __global__ void __launch_bounds__(SNG_PIPE_THREADS, SNG_PIPE_MINB)
         }
         mbar_wait(bar + stage, (uint32_t)((it >> 1) & 1));
         const long long e = blk * kBlock + lane;
-        const RowIO<real> io = {reinterpret_cast<const real *>(wbase + stage * act_stage) + lane * A, obs_s + lane * D,
-                                Offsets<NCT, ND>::soc(p), Offsets<NCT, ND>::dep(p)};
+        const real *act_row = reinterpret_cast<const real *>(wbase + stage * act_stage) + lane * A;
+        const RowIO<real> io = {act_row, act_row, obs_s + lane * D, Offsets<NCT, ND>::soc(p), Offsets<NCT, ND>::dep(p)};
         env_step<real, NCT, ND, EXACT, true>(p, e, p.spot + (size_t)blk * blk_words + lane, cur, io, p.reward, p.done);
         __syncwarp();            // obs rows complete; everyone is done reading this action stage
         {   // 32 rows = 8 * D float4 (16-byte aligned on both sides): coalesced 512-byte warp stores.
@@ -156,40 +156,47 @@ enum : int {
 };
 
 // MULTI: n_steps > 1 (rollout); the single-step instantiation carries no slab arithmetic.
-template <typename real, int NCT, int ND, bool EXACT, bool MULTI>
-__global__ void __launch_bounds__(SNG_STEP_MAXT, (EXACT || NCT > 16) ? 2 : SNG_STEP_MINB)   // large rows: shared memory bounds occupancy, not registers
+// L: lanes per env (1; 2 for large specialised stations: a warp then covers 16 envs, needs half the shared
+// memory per warp and half the work per thread, so twice as many warps stay resident.  L = 2 handles whole
+// 32-env state blocks only -- the host sends a ragged last block to the L = 1 instantiation, whose sums
+// associate identically).
+template <typename real, int NCT, int ND, bool EXACT, bool MULTI, int L>
+__global__ void __launch_bounds__(SNG_STEP_MAXT, (EXACT || NCT / L > 32) ? 2 : (NCT / L > 16 ? 4 : SNG_STEP_MINB))   // large rows: shared memory bounds occupancy, not registers
     step_simple_kernel(const Params<real> p, const real *actions, float *obs_out, real *reward, uint8_t *done, int n_steps,
                        int mode)
 {
+    constexpr int EPW = kBlock / L;   // envs per warp
     extern __shared__ __align__(128) unsigned char smem[];
     typedef typename WordOf<real>::type word;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     const int n_envs = (int)p.n_envs;                            // a handle owns < 2^31 envs (sng_create)
-    const int blk = blockIdx.x * wpb + warp;                     // state block = 32 envs
-    const int e0 = blk * kBlock;
+    const int blk = blockIdx.x * wpb + warp;                     // this warp's group of EPW envs (L = 1: a state block)
+    const int e0 = blk * EPW;
     const bool active = e0 < n_envs;                             // warp-uniform; idle warps only join the CTA barrier
     const int N = NCT ? NCT : p.N;
     const int A = p.A, D = p.D;
-    const uint32_t act_bytes = (uint32_t)(kBlock * A * sizeof(real)), obs_bytes = (uint32_t)(kBlock * D * sizeof(float));
+    const uint32_t act_bytes = (uint32_t)(EPW * A * sizeof(real)), obs_bytes = (uint32_t)(EPW * D * sizeof(float));
     const uint32_t per_warp = align128(act_bytes) + align128(obs_bytes);
     unsigned char *wbase = smem + (size_t)warp * per_warp;
     real *act_s = reinterpret_cast<real *>(wbase);
     float *obs_s = reinterpret_cast<float *>(wbase + align128(act_bytes));
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem + (size_t)wpb * per_warp) + warp;
-    constexpr bool COOP = !EXACT && NCT > 0 && NCT <= 16;         // warp-cooperative admission of arriving vehicles
+    constexpr bool COOP = !EXACT && NCT > 0 && NCT <= 16 && L == 1;   // warp-cooperative admission of arriving vehicles
     // its queue reuses the action stage: every lane is done with its action row when the admission starts
     // (the warp-wide shuffles at its top are the barrier), and 32 * N * 2 B <= 32 * A * sizeof(real)
     uint16_t *queue = reinterpret_cast<uint16_t *>(act_s);
 
-    const int n_valid = active ? min(kBlock, n_envs - e0) : 0;
-    const bool full = n_valid == kBlock;
+    const int n_valid = active ? min(EPW, n_envs - e0) : 0;   // envs of this warp (L = 2: always EPW, see above)
+    const bool full = n_valid == EPW;
     const bool tma_load = full && (mode & STAGE_TMA_LOAD), tma_store = full && (mode & STAGE_TMA_STORE);
     const bool vec = full && (mode & STAGE_ALIGNED);
-    const bool valid = lane < n_valid;
-    const int e = e0 + lane;
-    word *spot = p.spot + (size_t)blk * (size_t)(N * kPlanes * kBlock) + lane;
-    // float4 per lane of a block's action rows held in registers by the vector path (specialised kernels)
-    constexpr int AV = (NCT && sizeof(real) == 4) ? (NCT + 1 + 3) / 4 : 1;
+    const int el = lane % EPW, sub = lane / EPW;                 // env within the warp's group, lane within the env
+    const bool valid = el < n_valid;
+    const int e = e0 + el;
+    // (this env, the lane's first spot, plane 0) in the 32-env blocked state array
+    word *spot = p.spot + (size_t)(e / kBlock) * (size_t)(N * kPlanes * kBlock) + (e % kBlock) + sub * (kPlanes * kBlock);
+    // float4 per lane of a group's action rows held in registers by the vector path (specialised kernels)
+    constexpr int AV = (NCT && sizeof(real) == 4) ? ((NCT + 1) * EPW / 4 + 31) / 32 : 1;
     const int act_vec = (int)(act_bytes / 16);                    // float4 per block of action rows
 
 #pragma unroll 1
@@ -197,7 +204,7 @@ __global__ void __launch_bounds__(SNG_STEP_MAXT, (EXACT || NCT > 16) ? 2 : SNG_S
         const size_t slab = MULTI ? (size_t)s * (size_t)n_envs : 0;   // row offset of this step's slab
         const real *act_g = actions + (slab + (size_t)e0) * A;
         float *obs_g = obs_out + (slab + (size_t)e0) * D;
-        StateRegs<real, NCT> st;
+        StateRegs<real, NCT / L> st;
         float4 areg[AV];
         // ---- put everything this block needs in flight first ----
         if (tma_load) {
@@ -217,7 +224,7 @@ __global__ void __launch_bounds__(SNG_STEP_MAXT, (EXACT || NCT > 16) ? 2 : SNG_S
                 if (k < act_vec) areg[j] = reinterpret_cast<const float4 *>(act_g)[k];
             }
         }
-        if (valid) load_state<real, NCT>(p, e, spot, st);
+        if (valid) load_state<real, NCT / L, L>(p, e, spot, st);
         if (s == 0) publish_dep_table(p);     // CTA barrier; also orders the mbarrier init before the other lanes' waits
         if (!active) return;
         // ---- action rows into shared memory ----
@@ -243,8 +250,9 @@ __global__ void __launch_bounds__(SNG_STEP_MAXT, (EXACT || NCT > 16) ? 2 : SNG_S
         }
         Arrivals arrivals = {0u, 0u, 0};
         if (valid) {
-            const RowIO<real> io = {act_s + lane * A, obs_s + lane * D, Offsets<NCT, ND>::soc(p), Offsets<NCT, ND>::dep(p)};
-            arrivals = env_step<real, NCT, ND, EXACT, true, COOP>(p, e, spot, st, io, reward + slab, done + slab);
+            const RowIO<real, L> io = {act_s + el * A + sub, act_s + el * A, obs_s + el * D, Offsets<NCT, ND>::soc(p) + sub,
+                                       Offsets<NCT, ND>::dep(p) + sub};
+            arrivals = env_step<real, NCT, ND, EXACT, true, COOP, L>(p, e, spot, st, io, reward + slab, done + slab, sub);
         }
         if (COOP) admit_arrivals_warp<real, NCT>(p, e0, lane, spot - lane, arrivals, queue);
         // ---- observation rows out of shared memory ----
@@ -256,12 +264,12 @@ __global__ void __launch_bounds__(SNG_STEP_MAXT, (EXACT || NCT > 16) ? 2 : SNG_S
                 bulk_commit();
             }
         } else if (vec) {
-            // 32 rows = 8 * D float4 (16-byte aligned on both sides): coalesced 512-byte warp stores
+            // EPW rows = EPW / 4 * D float4 (16-byte aligned on both sides): coalesced 512-byte warp stores
             __syncwarp();
             const float4 *src = reinterpret_cast<const float4 *>(obs_s);
             float4 *dst = reinterpret_cast<float4 *>(obs_g);
 #pragma unroll 4
-            for (int k = lane; k < 8 * D; k += 32) dst[k] = src[k];
+            for (int k = lane; k < (EPW / 4) * D; k += 32) dst[k] = src[k];
             if (MULTI) __syncwarp();
         } else {
             __syncwarp();
@@ -352,6 +360,7 @@ public:
     int warps_per_cta = 0;   // 0 = auto
     int use_generic = 0, use_bulk = 1, host_chunks = 0, ctas_per_sm = 0;
     int kernel_variant = 0;   // 0 / 2 one block per warp, 1 persistent pipelined
+    int lanes_per_env = 0;    // 0 auto (2 for specialised stations of more than 32 spots), 1 always one lane per env
     int num_sms = 148;
     size_t smem_optin = 0;
     void *d_tables = nullptr;
@@ -570,21 +579,23 @@ public:
     }
     static constexpr size_t kStaticSmem = kDepTab * sizeof(float);
 
-    template <int NCT, int ND>
+    // L lanes per env (see step_simple_kernel); L = 2 requires q.n_envs to be a multiple of 32.
+    template <int NCT, int ND, int L = 1>
     int launch_simple(const Params<real> &q, const real *actions, float *obs, real *reward, uint8_t *done, int n_steps,
                       int bulk, cudaStream_t st)
     {
-        const size_t per_warp = row_bytes(1) + 8;
+        constexpr int EPW = kBlock / L;
+        const size_t per_warp = align128((uint32_t)(EPW * p.A * sizeof(real))) + align128((uint32_t)(EPW * p.D * sizeof(float))) + 8;
         int wpb = warps_per_cta > 0 ? warps_per_cta : 2;
         if (wpb * 32 > SNG_STEP_MAXT) wpb = SNG_STEP_MAXT / 32;
         while (wpb > 1 && kStaticSmem + (size_t)wpb * per_warp > smem_optin) wpb >>= 1;
         const size_t smem = (size_t)wpb * per_warp;
         if (kStaticSmem + smem > smem_optin) { error = "step kernel: one warp's action/observation rows do not fit in shared memory"; return SNG_ERR_UNSUPPORTED; }
-        auto kern = n_steps > 1 ? step_simple_kernel<real, NCT, ND, EXACT, true> : step_simple_kernel<real, NCT, ND, EXACT, false>;
+        auto kern = n_steps > 1 ? step_simple_kernel<real, NCT, ND, EXACT, true, L> : step_simple_kernel<real, NCT, ND, EXACT, false, L>;
         int rc = ensure_smem((const void *)kern, smem);
         if (rc) return rc;
-        const long long blocks = (q.n_envs + kBlock - 1) / kBlock;
-        const unsigned grid = (unsigned)((blocks + wpb - 1) / wpb);
+        const long long groups = (q.n_envs + EPW - 1) / EPW;       // one warp each
+        const unsigned grid = (unsigned)((groups + wpb - 1) / wpb);
         kern<<<grid, wpb * 32, smem, st>>>(q, actions, obs, reward, done, n_steps, bulk);
         ++launches;
         SNG_CUDA(cudaGetLastError());
@@ -631,6 +642,20 @@ public:
                 return launch_simple<NCT, ND>(tail, tail.actions, tail.obs, tail.reward, tail.done, 1, 0, st);
             }
             if (rc != SNG_ERR_UNSUPPORTED) return rc;
+        }
+        if constexpr (!EXACT && NCT > 32 && NCT % 2 == 0) {
+            // large stations (64 spots): two lanes per env over the whole 32-env blocks, the ragged last block one lane
+            // per env (a 32-spot station already reaches 85 % of the HBM roofline with one lane per env)
+            if (lanes_per_env != 1 && q.n_envs >= kBlock) {
+                const long long full = q.n_envs / kBlock * kBlock;
+                if (full == q.n_envs) return launch_simple<NCT, ND, 2>(q, actions, obs, reward, done, n_steps, bulk, st);
+                if (n_steps == 1 && actions == q.actions && obs == q.obs && reward == q.reward && done == q.done) {
+                    const Params<real> head = slice_of(q, 0, full), tail = slice_of(q, full, q.n_envs - full);
+                    const int rc = launch_simple<NCT, ND, 2>(head, head.actions, head.obs, head.reward, head.done, 1, bulk, st);
+                    if (rc) return rc;
+                    return launch_simple<NCT, ND, 1>(tail, tail.actions, tail.obs, tail.reward, tail.done, 1, STAGE_SCALAR, st);
+                }
+            }
         }
         return launch_simple<NCT, ND>(q, actions, obs, reward, done, n_steps, bulk, st);
     }
@@ -797,7 +822,9 @@ public:
     int set_pipeline(int up, int cps) override
     {
         if (cps < 0 || up < 0 || up > 2) { error = "sng_set_pipeline: bad arguments"; return SNG_ERR_ARG; }
-        kernel_variant = up; ctas_per_sm = cps;
+        kernel_variant = up == 2 ? 0 : up;
+        lanes_per_env = up == 2 ? 1 : 0;
+        ctas_per_sm = cps;
         return SNG_OK;
     }
 };
