@@ -17,6 +17,8 @@
  *   sng_sample_plan     the `initial_values.json` dump        utils/charging_station.py:173-186
  *   sng_error_flags     the reference's `raise ValueError` sites
  *                       (central_management_system.py:158-159, penaliser.py:111)
+ *   sng_gae             (next row of the path) stable_baselines3 RolloutBuffer.compute_returns_and_advantage,
+ *                       the consumer of the rollouts collected by solvers/RL/ppo_train.py:94-101
  *
  * Conventions: plain pointers and sizes only.  All device buffers are owned by the caller
  * (torch) and merely borrowed between sng_bind and sng_destroy.  Every call is asynchronous
@@ -98,8 +100,10 @@ typedef struct {
  * env_block = 32 envs: word (env e, spot i, plane f) lives at index
  *     (((e / 32) * n_spots + i) * 3 + f) * 32 + e % 32
  * with plane 0 = header word (arrival | departure << 8 | capacity << 16 | next arrival << 24, zero
- * extended), plane 1 = requested SoC, plane 2 = SoC column the next step starts from (both `real`
- * bit patterns).  The caller allocates ceil(E / 32) * n_spots * 3 * 32 words of real_bytes bytes. */
+ * extended), plane 1 = requested SoC (not maintained while every vehicle requests 1.0, i.e. sampled
+ * schedules without enable_requested_state_of_charge), plane 2 = SoC column the next step starts from
+ * (both `real` bit patterns).  The caller allocates ceil(E / 32) * n_spots * 3 * 32 words of real_bytes
+ * bytes. */
 typedef struct {
     uint32_t struct_size;
     uint32_t _pad;
