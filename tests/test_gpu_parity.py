@@ -544,3 +544,30 @@ def test_prediction_results_trace_matches_reference_recording(tag, tmp_path):
         assert np.allclose(np.array(out[key], dtype=np.float64), np.array(ref[key], dtype=np.float64),
                            rtol=3e-6, atol=3e-6), key
     env.close()
+
+
+def test_unaligned_buffers_take_the_scalar_path_and_agree():
+    """Rollout-buffer slabs that are not 16-byte aligned (odd E) cannot use the copy engine or vector
+    accesses; the scalar staging path must give the same results as stepping into the env's own buffers."""
+    E, n = 33, 6
+    a_env = _env(E, "float32", number_of_chargers=10, seed=2)
+    b_env = _env(E, "float32", number_of_chargers=10, seed=2)
+    a_env.reset()
+    b_env.reset()
+    buf_o = torch.zeros(n, E, 29, device="cuda:0")
+    buf_r = torch.zeros(n, E, device="cuda:0")
+    buf_d = torch.zeros(n, E, device="cuda:0", dtype=torch.uint8)
+    assert buf_o[1].data_ptr() % 16 != 0
+    g = torch.Generator(device="cuda:0").manual_seed(8)
+    acts = torch.stack([a_env.sample_actions(g) for _ in range(n)])
+    assert acts[1].data_ptr() % 16 != 0
+    for s in range(n):
+        o, r, d, _, _ = a_env.step(acts[s].clone())
+        b_env.step(acts[s], out=(buf_o[s], buf_r[s], buf_d[s]))
+        assert torch.equal(o, buf_o[s]) and torch.equal(r, buf_r[s]) and torch.equal(d, buf_d[s]), s
+    o2, r2, d2 = a_env.rollout(acts)         # unaligned slab strides inside one launch
+    for s in range(n):
+        b_env.step(acts[s].clone())
+        assert torch.equal(b_env.obs, o2[s]) and torch.equal(b_env.reward, r2[s]) and torch.equal(b_env.done, d2[s]), s
+    a_env.close()
+    b_env.close()
