@@ -146,6 +146,24 @@ def cpu_port_throughput(n_envs, seconds, threads):
     return n_envs * steps / el, el, steps
 
 
+def bind_to_gpu_numa_node(gpu_index):
+    """Multi-rank runs: pin this process to the CPUs NVML reports as local to its GPU, so that the pinned host
+    buffers of the end-to-end leg are allocated on the NUMA node the GPU hangs off (first touch)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+        cpus = [64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1 and 64 * w + b < n_cpu]
+        allowed = sorted(set(cpus) & os.sched_getaffinity(0))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+        return len(allowed)
+    except Exception:  # noqa: BLE001 -- best effort; the bench is valid without it
+        return 0
+
+
 def rollout_leg(env, n_steps, dev):
     """BASELINE config 3: policy in the loop.  Reported beside the headline, not as it."""
     import torch
@@ -285,6 +303,7 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     n_gpus = world if world > 1 else 1
+    numa_cpus = bind_to_gpu_numa_node(local_rank) if world > 1 else 0
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
 
@@ -413,7 +432,8 @@ def main():
                        "launch": ("CUDA graph of %d step launches, replayed" % gsteps) if graph is not None else "one launch per step",
                        "mean_episode_return": mean_ret},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": args.e2e_steps, "path": "sng_step_host: pinned host buffers, H2D + step + D2H + sync"},
+                    "steps": args.e2e_steps, "path": "sng_step_host: pinned host buffers, H2D + step + D2H + sync",
+                    "numa_local_cpus": numa_cpus},
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
