@@ -44,7 +44,7 @@ def penalty_margin_distance(ob: OracleBatch):
     s = np.take_along_axis(ob.soc, col, axis=2)[:, :, 0]
     r = np.take_along_axis(ob.req, col, axis=2)[:, :, 0]
     d = np.abs(s - (r - ob.cfg.soc_margin_ratio * r))
-    d = np.where(ob.check.astype(bool), d, np.inf)
+    d = np.where(ob.check.astype(bool) & (r > 0), d, np.inf)     # r == 0 (empty column, e.g. at t = 0): no penalty either way
     return d.min(axis=1)
 
 

@@ -145,7 +145,7 @@ def _lockstep(env, ob, cfg, n_steps, rng, seed, check_soc=True, f64=False):
             assert_close_f32("obs", obs, o_ref, atol=1e-6)
             assert_close_f32("reward", rew, r_ref, atol=1e-5, mask=~near)
             worst["obs"] = max(worst["obs"], float(np.abs(obs - o_ref).max()))
-            worst["reward"] = max(worst["reward"], float((np.abs(rew - r_ref) / np.maximum(np.abs(r_ref), 1.0))[~near].max()))
+            worst["reward"] = max(worst["reward"], float((np.abs(rew - r_ref) / np.maximum(np.abs(r_ref), 1.0))[~near].max(initial=0.0)))
     st = env.env_state()
     assert np.array_equal(st["t"], ob.t) and np.array_equal(st["episode"], episode)
     if f64:
@@ -180,6 +180,9 @@ def test_config2_sampled_episodes_with_auto_reset(precision, n_envs):
     dict(number_of_chargers=33, price_model=3, vehicle_uncharged_penalty_mode="no_penalty"),
     dict(number_of_chargers=64, time_interval="15min", enable_requested_state_of_charge=True),   # BASELINE config 5
     dict(number_of_chargers=1, time_interval="2h"),
+    dict(number_of_chargers=10, hours_ahead=5),                                   # forecast horizon
+    dict(number_of_chargers=6, hours_ahead=1, pv_system_available_in_model=False, price_model=2),
+    dict(number_of_chargers=32, time_interval="30min", price_model=4, vehicle_uncharged_penalty_mode="dense"),
 ])
 @pytest.mark.parametrize("precision", ["float32", "float64"])
 def test_variants_sampled_vs_oracle(kw, precision):
