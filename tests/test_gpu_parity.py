@@ -574,3 +574,34 @@ def test_unaligned_buffers_take_the_scalar_path_and_agree():
         assert torch.equal(b_env.obs, o2[s]) and torch.equal(b_env.reward, r2[s]) and torch.equal(b_env.done, d2[s]), s
     a_env.close()
     b_env.close()
+
+
+def test_single_env_reload_of_last_schedule_follows_quirk_q7():
+    """reset(generate_new_initial_values=False) replays the last generated schedule like the reference's reload
+    of initial_values.json -- which forgets the requested SoC (charging_station.py:119-136), so no vehicle can
+    be penalised afterwards, unless restore_requested_soc_on_reload=True."""
+    from smart_nanogrid_gym_b200 import SmartNanogridEnv
+    kw = dict(number_of_chargers=6, enable_requested_state_of_charge=True, vehicle_uncharged_penalty_mode="dense", **{
+        k: v for k, v in DEFAULT.items() if k != "vehicle_uncharged_penalty_mode"})
+    rewards = {}
+    for restore in (False, True):
+        env = SmartNanogridEnv(seed=12, restore_requested_soc_on_reload=restore, **kw)
+        obs0, _ = env.reset()
+        plan = env._last_plan
+        first = []
+        for t in range(24):
+            obs, r, term, _, _ = env.step(np.zeros(7, np.float32))
+            first.append(r)
+        assert term
+        obs1, _ = env.reset(generate_new_initial_values=False)
+        assert np.array_equal(obs1[2 * 4:2 * 4 + 12], obs0[2 * 4:2 * 4 + 12])       # same vehicles, SoCs and departures
+        again = [env.step(np.zeros(7, np.float32))[1] for _ in range(24)]
+        rewards[restore] = (first, again)
+        assert env._last_plan is plan or np.array_equal(env._last_plan.arr, plan.arr)
+        env.close()
+    first, again = rewards[False]
+    assert min(first) < -1.0                      # idle charging under dense penalties is penalised ...
+    assert max(abs(x) for x in again) < abs(min(first))   # ... but not after the lossy reload (only energy cost is left)
+    first_r, again_r = rewards[True]
+    # with the requested SoC restored the penalties come back (pv_shift is redrawn on reset, so costs differ slightly)
+    assert min(again_r) < -1.0
