@@ -6,9 +6,10 @@
 // structure of arrays blocked by 32 envs ([E/32][N][3 planes][32]), so lane l of a warp reads plane f
 // of spot i of its env from word  ((block*N + i)*3 + f)*32 + l : every state load / store of a warp is
 // one full 128-byte line, and all of a thread's accesses are constant offsets from one base pointer.
-// Spots are walked sequentially inside the thread (no shuffles, sums in spot order, results do not
-// depend on how envs are split over GPUs).  DESIGN.md "Thread mapping" has the measurements behind
-// this choice (a warp-per-env mapping leaves 22 of 32 lanes idle at 10 spots and is issue-bound).
+// Spots are walked sequentially inside the thread; the station sums are kept per spot parity and combined
+// in a fixed order, so results do not depend on the kernel variant or on how envs are split over GPUs.
+// DESIGN.md section 3.1 has the measurements behind this choice (a warp-per-env mapping leaves 22 of 32
+// lanes idle at 10 spots and is issue-bound).
 //
 // File:line citations refer to the reference tree (smart_nanogrid_gym/...).  SURVEY.md section 2.3
 // is the step-by-step specification.
