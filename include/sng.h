@@ -187,6 +187,26 @@ int sng_gae(const float *rewards, const float *values, const uint8_t *episode_st
             const uint8_t *last_dones, float *advantages, float *returns, int n_steps, int64_t n_envs, float gamma,
             float gae_lambda, void *stream);
 
+/* Fused actor-critic forward pass of Stable-Baselines3's default MlpPolicy (two tanh 64-64 networks, linear
+ * action head with state-independent log-std, linear value head; what PPO("MlpPolicy", env) at
+ * solvers/RL/ppo_train.py:89-92 builds), for rollout collection around the step: one launch computes values,
+ * sampled actions (mean + noise * exp(log_std), `noise` ~ N(0,1) supplied by the caller, NULL = deterministic), the
+ * actions clipped to the Box (what env.step receives) and their log-probabilities.  All pointers are device
+ * pointers to float32, weights row-major [out][in] as torch.nn.Linear stores them.  actions == NULL computes the
+ * values only.  Supported shapes: hidden = 64, the observation / action sizes of 4-, 8- and 10-spot stations;
+ * otherwise SNG_ERR_UNSUPPORTED (callers fall back to their own framework).  Asynchronous on `stream`. */
+typedef struct {
+    uint32_t struct_size;
+    int32_t obs_dim, hidden, act_dim;
+    const float *w_pi0, *b_pi0, *w_pi1, *b_pi1;   /* actor:  [64][obs_dim], [64], [64][64], [64] */
+    const float *w_act, *b_act, *log_std;         /* action head [act_dim][64], [act_dim]; log-std [act_dim] */
+    const float *w_vf0, *b_vf0, *w_vf1, *b_vf1;   /* critic: [64][obs_dim], [64], [64][64], [64] */
+    const float *w_val, *b_val;                   /* value head [1][64], [1] */
+} sng_mlp;
+int sng_policy_forward(const sng_mlp *mlp, const float *obs, const float *noise, const float *low, const float *high,
+                       float *raw_actions, float *actions, float *values, float *log_probs, int64_t n_envs,
+                       void *stream);
+
 /* Kernels launched by this handle so far (bench.py's gpu_launches claim). */
 int64_t sng_launch_count(const sng_env *env);
 

@@ -21,7 +21,7 @@ DIAG = ("total_ch", "total_dis", "solar", "batt_power", "grid_power", "grid_cost
 
 EXPORTS = ("sng_abi_version", "sng_sizeof", "sng_last_error", "sng_query_layout", "sng_create", "sng_destroy", "sng_bind",
            "sng_reset", "sng_load_schedule", "sng_step", "sng_rollout", "sng_step_host", "sng_sample_plan",
-           "sng_error_flags", "sng_launch_count", "sng_set_tuning", "sng_set_pipeline", "sng_gae")
+           "sng_error_flags", "sng_launch_count", "sng_set_tuning", "sng_set_pipeline", "sng_gae", "sng_policy_forward")
 
 
 class SngConfig(C.Structure):
@@ -52,6 +52,12 @@ class SngBuffers(C.Structure):
 class SngScheduleView(C.Structure):
     _fields_ = [("struct_size", C.c_uint32), ("n_slots", C.c_int32)] + [(n, C.c_void_p) for n in (
         "arr", "dep", "cap", "soc0", "req", "n_veh", "pv_shift", "soc_b")]
+
+
+class SngMlp(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("obs_dim", C.c_int32), ("hidden", C.c_int32), ("act_dim", C.c_int32)] + [
+        (n, C.c_void_p) for n in ("w_pi0", "b_pi0", "w_pi1", "b_pi1", "w_act", "b_act", "log_std",
+                                  "w_vf0", "b_vf0", "w_vf1", "b_vf1", "w_val", "b_val")]
 
 
 class NativeError(RuntimeError):
@@ -102,6 +108,7 @@ def lib():
         L.sng_set_tuning.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
         L.sng_set_pipeline.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.sng_gae.argtypes = [C.c_void_p] * 7 + [C.c_int, C.c_int64, C.c_float, C.c_float, C.c_void_p]
+        L.sng_policy_forward.argtypes = [C.POINTER(SngMlp)] + [C.c_void_p] * 8 + [C.c_int64, C.c_void_p]
         if L.sng_abi_version() != 2:
             raise NativeError("libsng.so ABI version mismatch")
         for which, st in enumerate((SngConfig, SngLayout, SngBuffers, SngScheduleView)):

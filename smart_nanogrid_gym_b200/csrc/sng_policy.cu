@@ -1,0 +1,195 @@
+// sng_policy.cu -- fused actor-critic forward pass for the rollout-collection row.
+//
+// The reference trains with Stable-Baselines3 PPO("MlpPolicy") (solvers/RL/ppo_train.py:89-92): two
+// separate tanh 64-64 networks (actor, critic), a linear action head with a state-independent log-std
+// (DiagGaussian) and a linear value head; collect_rollouts clips the sampled actions to the Box before
+// env.step.  With the step kernel at a few microseconds per 65,536-env step, ~20 small library launches per
+// policy call dominate rollout collection, so this kernel does the whole forward pass -- both networks, the
+// heads, sampling with supplied N(0,1) noise, clipping, log-probabilities -- in one launch, one thread per env:
+// weights in shared memory (broadcast LDS.128), the first hidden layer in registers, the second hidden layer
+// consumed by the heads as it is produced.  FP32 throughout (CUDA cores: the matrices are 29x64 / 64x64 per
+// env; tensor cores would need TF32/BF16 inputs and change the numerics of a trainer expecting FP32).
+#include <cmath>
+#include <cstdint>
+#include <string>
+
+#include <cuda_runtime.h>
+
+#include "../../include/sng.h"
+
+namespace {
+
+constexpr int H = 64;          // hidden width of SB3's default MlpPolicy
+constexpr int kThreads = 128;
+
+struct Net {                   // one tanh H-H network + linear head, as laid out in shared memory
+    const float *w0, *b0, *w1, *b1, *wh, *bh;
+};
+
+// y[j] = tanh(b0[j] + sum_k w0[j][k] x[k]) for j < H; w0 rows padded to DP floats in shared memory.
+template <int DP> __device__ __forceinline__ void layer0(const float *w0, const float *b0, const float (&x)[DP], float (&h)[H])
+{
+#pragma unroll
+    for (int j = 0; j < H; ++j) {
+        float acc = b0[j];
+        const float4 *w = reinterpret_cast<const float4 *>(w0 + j * DP);
+#pragma unroll
+        for (int k = 0; k < DP / 4; ++k) {
+            const float4 v = w[k];
+            acc = fmaf(v.x, x[4 * k], acc);
+            acc = fmaf(v.y, x[4 * k + 1], acc);
+            acc = fmaf(v.z, x[4 * k + 2], acc);
+            acc = fmaf(v.w, x[4 * k + 3], acc);
+        }
+        h[j] = tanhf(acc);
+    }
+}
+
+// out[a] = bh[a] + sum_j wh_t[j][a] * tanh(b1[j] + sum_k w1[j][k] h[k]); the second hidden layer is never stored.
+// wh_t is the head weight transposed and padded to AP floats per row.
+template <int AP> __device__ __forceinline__ void layer1_and_head(const float *w1, const float *b1, const float *wh_t,
+                                                                  const float *bh, const float (&h)[H], float (&out)[AP])
+{
+#pragma unroll
+    for (int a = 0; a < AP; ++a) out[a] = bh[a];
+#pragma unroll 2
+    for (int j = 0; j < H; ++j) {
+        float acc0 = b1[j], acc1 = 0.f;           // two chains: halves the dependent-FMA latency
+        const float4 *w = reinterpret_cast<const float4 *>(w1 + j * H);
+#pragma unroll
+        for (int k = 0; k < H / 4; ++k) {
+            const float4 v = w[k];
+            acc0 = fmaf(v.x, h[4 * k], acc0);
+            acc1 = fmaf(v.y, h[4 * k + 1], acc1);
+            acc0 = fmaf(v.z, h[4 * k + 2], acc0);
+            acc1 = fmaf(v.w, h[4 * k + 3], acc1);
+        }
+        const float g = tanhf(acc0 + acc1);
+        const float4 *t = reinterpret_cast<const float4 *>(wh_t + j * AP);
+#pragma unroll
+        for (int a = 0; a < AP / 4; ++a) {
+            const float4 v = t[a];
+            out[4 * a] = fmaf(v.x, g, out[4 * a]);
+            out[4 * a + 1] = fmaf(v.y, g, out[4 * a + 1]);
+            out[4 * a + 2] = fmaf(v.z, g, out[4 * a + 2]);
+            out[4 * a + 3] = fmaf(v.w, g, out[4 * a + 3]);
+        }
+    }
+}
+
+// DP: obs_dim padded to a multiple of 4 (<= 32); AP: act_dim padded to a multiple of 4 (<= 16).
+template <int DP, int AP>
+__global__ void __launch_bounds__(kThreads) policy_forward_kernel(const sng_mlp m, const float *__restrict__ obs,
+                                                                 const float *__restrict__ noise,
+                                                                 const float *__restrict__ low,
+                                                                 const float *__restrict__ high, float *raw_actions,
+                                                                 float *actions, float *values, float *log_probs,
+                                                                 long long n_envs)
+{
+    extern __shared__ __align__(16) float sm[];
+    const int D = m.obs_dim, A = m.act_dim;
+    // ---- weights into shared memory, rows padded: [H][DP] | [H] | [H][H] | [H] | head^T [H][AP or 4] | head bias ----
+    float *p_w0 = sm, *p_b0 = p_w0 + H * DP, *p_w1 = p_b0 + H, *p_b1 = p_w1 + H * H, *p_wh = p_b1 + H, *p_bh = p_wh + H * AP;
+    float *v_w0 = p_bh + AP, *v_b0 = v_w0 + H * DP, *v_w1 = v_b0 + H, *v_b1 = v_w1 + H * H, *v_wh = v_b1 + H, *v_bh = v_wh + H * 4;
+    float *tile = v_bh + 4;                     // per-warp obs tile [32][D]
+    const int tid = threadIdx.x;
+    for (int i = tid; i < H * DP; i += kThreads) {
+        const int j = i / DP, k = i - j * DP;
+        p_w0[i] = k < D ? m.w_pi0[j * D + k] : 0.f;
+        v_w0[i] = k < D ? m.w_vf0[j * D + k] : 0.f;
+    }
+    for (int i = tid; i < H * H; i += kThreads) { p_w1[i] = m.w_pi1[i]; v_w1[i] = m.w_vf1[i]; }
+    for (int i = tid; i < H; i += kThreads) { p_b0[i] = m.b_pi0[i]; p_b1[i] = m.b_pi1[i]; v_b0[i] = m.b_vf0[i]; v_b1[i] = m.b_vf1[i]; }
+    for (int i = tid; i < H * AP; i += kThreads) {
+        const int j = i / AP, a = i - j * AP;
+        p_wh[i] = a < A ? m.w_act[a * H + j] : 0.f;          // transposed: row j holds the A head weights of hidden unit j
+    }
+    for (int i = tid; i < H * 4; i += kThreads) v_wh[i] = (i & 3) == 0 ? m.w_val[i >> 2] : 0.f;
+    if (tid < AP) p_bh[tid] = tid < A ? m.b_act[tid] : 0.f;
+    if (tid < 4) v_bh[tid] = tid == 0 ? m.b_val[0] : 0.f;
+    __syncthreads();
+
+    const int lane = tid & 31, warp = tid >> 5;
+    float *rows = tile + warp * (32 * D);
+    const long long n_blocks = (n_envs + 31) / 32;
+    for (long long blk = (long long)blockIdx.x * (kThreads / 32) + warp; blk < n_blocks; blk += (long long)gridDim.x * (kThreads / 32)) {
+        const long long e0 = blk * 32;
+        const int n_valid = (int)((n_envs - e0) < 32 ? (n_envs - e0) : 32);
+        __syncwarp();
+        for (int i = lane; i < n_valid * D; i += 32) rows[i] = obs[e0 * D + i];      // coalesced; rows then read per thread
+        __syncwarp();
+        if (lane >= n_valid) continue;
+        const long long e = e0 + lane;
+        float x[DP];
+#pragma unroll
+        for (int k = 0; k < DP; ++k) x[k] = k < D ? rows[lane * D + k] : 0.f;
+        float h[H];
+        // ---- critic ----
+        float val[4];
+        layer0<DP>(v_w0, v_b0, x, h);
+        layer1_and_head<4>(v_w1, v_b1, v_wh, v_bh, h, val);
+        values[e] = val[0];
+        if (actions == nullptr) continue;        // value-only call (bootstrap value of the last observation)
+        // ---- actor ----
+        float mean[AP];
+        layer0<DP>(p_w0, p_b0, x, h);
+        layer1_and_head<AP>(p_w1, p_b1, p_wh, p_bh, h, mean);
+        float lp = 0.f;
+#pragma unroll
+        for (int a = 0; a < AP; ++a) {
+            if (a < A) {
+                const float ls = __ldg(m.log_std + a);
+                const float z = noise ? noise[e * A + a] : 0.f;
+                const float act = fmaf(z, expf(ls), mean[a]);          // DiagGaussian sample
+                raw_actions[e * A + a] = act;
+                actions[e * A + a] = fminf(fmaxf(act, __ldg(low + a)), __ldg(high + a));   // SB3 clips Box actions before env.step
+                lp += -0.5f * z * z - ls - 0.91893853320467274f;      // log N(act; mean, std), 0.5 * log(2 pi)
+            }
+        }
+        log_probs[e] = lp;
+    }
+}
+
+thread_local std::string g_err;
+
+template <int DP, int AP>
+int launch(const sng_mlp &m, const float *obs, const float *noise, const float *low, const float *high, float *raw,
+           float *act, float *val, float *lp, long long n, cudaStream_t st)
+{
+    auto kern = policy_forward_kernel<DP, AP>;
+    const size_t smem = sizeof(float) * ((size_t)2 * (H * DP + H + H * H + H) + H * AP + AP + H * 4 + 4 + (size_t)(kThreads / 32) * 32 * m.obs_dim);
+    static size_t set = 0;
+    if (smem > set) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return SNG_ERR_CUDA;
+        set = smem;
+    }
+    int dev = 0, sms = 148, per_sm = 1;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem);
+    long long grid = (long long)sms * (per_sm > 0 ? per_sm : 1);
+    const long long need = (n + kThreads - 1) / kThreads;
+    if (grid > need) grid = need;
+    kern<<<(unsigned)grid, kThreads, smem, st>>>(m, obs, noise, low, high, raw, act, val, lp, n);
+    return cudaGetLastError() == cudaSuccess ? SNG_OK : SNG_ERR_CUDA;
+}
+
+}  // namespace
+
+extern "C" int sng_policy_forward(const sng_mlp *mlp, const float *obs, const float *noise, const float *low,
+                                  const float *high, float *raw_actions, float *actions, float *values,
+                                  float *log_probs, int64_t n_envs, void *stream)
+{
+    if (!mlp || mlp->struct_size != sizeof(sng_mlp) || !obs || !values || n_envs < 1) return SNG_ERR_ARG;
+    if (actions && (!raw_actions || !log_probs || !low || !high)) return SNG_ERR_ARG;
+    if (mlp->hidden != H || mlp->obs_dim < 1 || mlp->obs_dim > 32 || mlp->act_dim < 1 || mlp->act_dim > 16) return SNG_ERR_UNSUPPORTED;
+    const int dp = (mlp->obs_dim + 3) / 4 * 4, ap = (mlp->act_dim + 3) / 4 * 4;
+    cudaStream_t st = (cudaStream_t)stream;
+#define SNG_POLICY_CASE(DP, AP) \
+    if (dp == DP && ap == AP) return launch<DP, AP>(*mlp, obs, noise, low, high, raw_actions, actions, values, log_probs, n_envs, st);
+    SNG_POLICY_CASE(20, 8)    // N = 4:  D = 17, A = 5
+    SNG_POLICY_CASE(28, 12)   // N = 8:  D = 25, A = 9
+    SNG_POLICY_CASE(32, 12)   // N = 10: D = 29, A = 11
+#undef SNG_POLICY_CASE
+    return SNG_ERR_UNSUPPORTED;
+}

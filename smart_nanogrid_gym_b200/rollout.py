@@ -3,8 +3,9 @@
 The reference trains with Stable-Baselines3 PPO on ONE env (solvers/RL/ppo_train.py:89-102): SB3's
 `collect_rollouts` loops `policy(obs) -> clip -> env.step -> buffer.add` and then computes GAE.  Here the
 same loop runs for E envs without leaving the GPU: the step kernel writes observations / rewards / dones
-straight into the rollout-buffer slices (zero-copy `out=`), the policy is a torch MLP of SB3's default
-MlpPolicy shape (tanh 64-64 actor and critic, state-independent log-std), and advantages / returns come
+straight into the rollout-buffer slices (zero-copy `out=`), the policy is a torch module of SB3's default
+MlpPolicy shape (tanh 64-64 actor and critic, state-independent log-std) whose inference runs as ONE fused
+kernel (`sng_policy_forward`; plain torch ops as the fallback and for training), and advantages / returns come
 from the `sng_gae` kernel.  Not a trainer: it is the caller-side row next to the hot path.
 """
 from __future__ import annotations
@@ -42,6 +43,34 @@ class MlpPolicy(nn.Module):
     def predict_values(self, obs: torch.Tensor) -> torch.Tensor:
         return self.value_net(self.vf(obs)).squeeze(-1)
 
+    # ---- fused inference (libsng.so: sng_policy_forward) ----------------------------------
+    def _mlp_struct(self):
+        """ctypes view of the parameters (rebuilt on every call: optimisers may replace .data)."""
+        m = nat.SngMlp()
+        m.struct_size = C.sizeof(nat.SngMlp)
+        m.obs_dim, m.hidden, m.act_dim = self.pi[0].in_features, self.pi[0].out_features, self.action_net.out_features
+        ptr = lambda t: t.detach().data_ptr()  # noqa: E731
+        m.w_pi0, m.b_pi0, m.w_pi1, m.b_pi1 = ptr(self.pi[0].weight), ptr(self.pi[0].bias), ptr(self.pi[2].weight), ptr(self.pi[2].bias)
+        m.w_act, m.b_act, m.log_std = ptr(self.action_net.weight), ptr(self.action_net.bias), ptr(self.log_std)
+        m.w_vf0, m.b_vf0, m.w_vf1, m.b_vf1 = ptr(self.vf[0].weight), ptr(self.vf[0].bias), ptr(self.vf[2].weight), ptr(self.vf[2].bias)
+        m.w_val, m.b_val = ptr(self.value_net.weight), ptr(self.value_net.bias)
+        return m
+
+    def fused_supported(self) -> bool:
+        p = self.pi[0].weight
+        return (p.is_cuda and p.dtype == torch.float32 and self.pi[0].out_features == 64 and
+                (self.pi[0].in_features, self.action_net.out_features) in ((17, 5), (25, 9), (29, 11)))
+
+    @torch.no_grad()
+    def fused_forward(self, obs, noise, low, high, raw_actions, actions, values, log_probs):
+        """One launch: values, sampled + clipped actions and log-probs written into the given [E, ...] buffers
+        (noise None = deterministic; actions None = values only).  Inference only (no autograd graph)."""
+        p = lambda t: None if t is None else C.c_void_p(t.data_ptr())  # noqa: E731
+        m = self._mlp_struct()
+        stream = C.c_void_p(torch.cuda.current_stream(obs.device).cuda_stream)
+        nat.check(nat.lib().sng_policy_forward(C.byref(m), p(obs), p(noise), p(low), p(high), p(raw_actions), p(actions),
+                                               p(values), p(log_probs), obs.shape[0], stream))
+
 
 class RolloutBuffer:
     """[n_steps, E, ...] device tensors, SB3 RolloutBuffer field for field.  `observations` has n_steps + 1
@@ -77,27 +106,34 @@ class RolloutBuffer:
 
 @torch.no_grad()
 def collect_rollout(env, policy: MlpPolicy, buf: RolloutBuffer, obs: torch.Tensor, episode_starts: torch.Tensor,
-                    generator: torch.Generator | None = None, deterministic: bool = False):
+                    generator: torch.Generator | None = None, deterministic: bool = False, fused: bool = True):
     """SB3 OnPolicyAlgorithm.collect_rollouts for a BatchedSmartNanogridEnv: n_steps policy + env steps,
     then GAE.  `obs` [E, D] is the current observation (from reset() or the previous rollout),
     `episode_starts` [E] u8.  Returns (last_obs, last_dones) to carry into the next call."""
     low, high = env.action_low.float(), env.action_high.float()
     buf.observations[0].copy_(obs)
     starts = episode_starts.to(torch.uint8)
+    fused = fused and policy.fused_supported()
     for s in range(buf.n_steps):
         o = buf.observations[s]
         noise = None if deterministic else torch.randn(buf.n_envs, buf.actions.shape[2], device=o.device, generator=generator)
-        a, v, lp = policy(o, noise)
-        buf.raw_actions[s].copy_(a)
-        torch.clamp(a, low, high, out=buf.actions[s])          # SB3 clips Box actions before env.step
-        buf.values[s].copy_(v)
-        buf.log_probs[s].copy_(lp)
+        if fused:      # one kernel: both networks, heads, sampling, clipping, log-probs, straight into the buffer slabs
+            policy.fused_forward(o, noise, low, high, buf.raw_actions[s], buf.actions[s], buf.values[s], buf.log_probs[s])
+        else:
+            a, v, lp = policy(o, noise)
+            buf.raw_actions[s].copy_(a)
+            torch.clamp(a, low, high, out=buf.actions[s])      # SB3 clips Box actions before env.step
+            buf.values[s].copy_(v)
+            buf.log_probs[s].copy_(lp)
         buf.episode_starts[s].copy_(starts)
         # the kernel writes the next observation, the reward and the done flag into the buffer slabs
         env.step(buf.actions[s], out=(buf.observations[s + 1], buf.rewards[s], buf.dones[s]))
         starts = buf.dones[s]
     last_obs = buf.observations[buf.n_steps]
-    buf.last_values.copy_(policy.predict_values(last_obs))
+    if fused:
+        policy.fused_forward(last_obs, None, None, None, None, None, buf.last_values, None)
+    else:
+        buf.last_values.copy_(policy.predict_values(last_obs))
     buf.compute_returns_and_advantage(buf.last_values, buf.dones[buf.n_steps - 1])
     return last_obs, buf.dones[buf.n_steps - 1]
 
@@ -107,7 +143,7 @@ class GraphedRollout:
     replayed: at 65,536 envs the eager loop is bound by ~20 small launches per step, the graph is not.
     Sampling noise comes from torch's default CUDA generator (graph-safe); `deterministic=True` uses the mean."""
 
-    def __init__(self, env, policy: MlpPolicy, buf: RolloutBuffer, deterministic: bool = False):
+    def __init__(self, env, policy: MlpPolicy, buf: RolloutBuffer, deterministic: bool = False, fused: bool = True):
         dev = buf.rewards.device
         self.env, self.policy, self.buf = env, policy, buf
         self.obs_in = torch.zeros(buf.n_envs, buf.observations.shape[2], device=dev)
@@ -116,12 +152,12 @@ class GraphedRollout:
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):                     # warm-up outside capture (lazy inits, cuBLAS workspaces)
             self.obs_in.copy_(env.obs)
-            collect_rollout(env, policy, buf, self.obs_in, self.starts_in, deterministic=deterministic)
+            collect_rollout(env, policy, buf, self.obs_in, self.starts_in, deterministic=deterministic, fused=fused)
         torch.cuda.current_stream(dev).wait_stream(side)
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.last_obs, self.last_dones = collect_rollout(env, policy, buf, self.obs_in, self.starts_in,
-                                                             deterministic=deterministic)
+                                                             deterministic=deterministic, fused=fused)
 
     def __call__(self, obs: torch.Tensor, episode_starts: torch.Tensor):
         self.obs_in.copy_(obs)

@@ -40,7 +40,7 @@ def test_collect_rollout_is_zero_copy_and_matches_manual_stepping():
     assert torch.equal(obs, obs_twin)
     g = torch.Generator(device="cuda:0").manual_seed(5)
     starts = torch.ones(E, dtype=torch.uint8, device="cuda:0")
-    last_obs, last_dones = collect_rollout(env, policy, buf, obs, starts, generator=g)
+    last_obs, last_dones = collect_rollout(env, policy, buf, obs, starts, generator=g, fused=False)
     assert ptrs == (buf.observations.data_ptr(), buf.rewards.data_ptr(), buf.dones.data_ptr())   # nothing reallocated
     lo, hi = env.action_low, env.action_high
     assert (buf.actions >= lo).all() and (buf.actions <= hi).all()
@@ -56,6 +56,14 @@ def test_collect_rollout_is_zero_copy_and_matches_manual_stepping():
     assert torch.equal(last_obs, buf.observations[n]) and torch.equal(last_dones, buf.dones[n - 1])
     with torch.no_grad():
         assert torch.allclose(buf.values[7], policy.predict_values(buf.observations[7]), atol=1e-5)
+    # the fused policy kernel fills the buffer the same way (same noise stream, float32 rounding apart)
+    buf2 = RolloutBuffer(n, E, env.cfg.obs_dim, env.cfg.act_dim, "cuda:0")
+    env2 = BatchedSmartNanogridEnv(E, seed=3, **KW)
+    collect_rollout(env2, policy, buf2, env2.reset(), starts, generator=torch.Generator(device="cuda:0").manual_seed(5), fused=True)
+    assert torch.allclose(buf2.raw_actions[0], buf.raw_actions[0], rtol=1e-4, atol=2e-5)
+    assert torch.allclose(buf2.values[0], buf.values[0], rtol=1e-4, atol=2e-5)
+    assert torch.equal(buf2.episode_starts, buf.episode_starts) and torch.equal(buf2.dones, buf.dones)
+    env2.close()
     adv_ref, ret_ref = gae_reference(buf.rewards, buf.values, buf.episode_starts, buf.last_values, last_dones,
                                      buf.gamma, buf.gae_lambda)
     assert torch.allclose(buf.advantages.double(), adv_ref, rtol=1e-5, atol=1e-3)
@@ -124,3 +132,38 @@ def test_sb3_style_vec_env_protocol():
     assert venv.env_is_wrapped(object) == [False] * E and len(venv.get_attr("num_envs")) == E
     venv.close()
     twin.close()
+
+
+@pytest.mark.parametrize("n_spots,obs_dim,act_dim", [(10, 29, 11), (4, 17, 5), (8, 25, 9)])
+def test_fused_policy_kernel_matches_torch_modules(n_spots, obs_dim, act_dim):
+    """sng_policy_forward (one launch) == the torch nn.Module forward (float32): values, sampled and clipped actions,
+    log-probabilities; value-only mode; ragged batch."""
+    from smart_nanogrid_gym_b200.rollout import MlpPolicy
+    E = 5000 + 7
+    torch.manual_seed(n_spots)
+    policy = MlpPolicy(obs_dim, act_dim).to("cuda:0")
+    with torch.no_grad():
+        policy.log_std.copy_(torch.linspace(-1.0, 0.5, act_dim))
+    assert policy.fused_supported()
+    g = torch.Generator(device="cuda:0").manual_seed(1)
+    obs = torch.rand(E, obs_dim, device="cuda:0", generator=g) * 1.5
+    noise = torch.randn(E, act_dim, device="cuda:0", generator=g)
+    low = torch.zeros(act_dim, device="cuda:0")
+    low[-1] = -1.0
+    high = torch.ones(act_dim, device="cuda:0")
+    raw, act = torch.empty(E, act_dim, device="cuda:0"), torch.empty(E, act_dim, device="cuda:0")
+    val, lp = torch.empty(E, device="cuda:0"), torch.empty(E, device="cuda:0")
+    policy.fused_forward(obs, noise, low, high, raw, act, val, lp)
+    with torch.no_grad():
+        a_ref, v_ref, lp_ref = policy(obs, noise)
+    assert torch.allclose(raw, a_ref, rtol=1e-4, atol=2e-5)
+    assert torch.allclose(act, torch.minimum(torch.maximum(a_ref, low), high), rtol=1e-4, atol=2e-5)
+    assert torch.allclose(val, v_ref, rtol=1e-4, atol=2e-5) and torch.allclose(lp, lp_ref, rtol=1e-5, atol=1e-4)
+    val2 = torch.empty(E, device="cuda:0")
+    policy.fused_forward(obs, None, None, None, None, None, val2, None)
+    assert torch.equal(val2, val)
+    raw_d, act_d, lp_d = torch.empty_like(raw), torch.empty_like(act), torch.empty_like(lp)
+    policy.fused_forward(obs, None, low, high, raw_d, act_d, val2, lp_d)          # deterministic: the mean action
+    with torch.no_grad():
+        mean_ref, _, lp0_ref = policy(obs, None)
+    assert torch.allclose(raw_d, mean_ref, rtol=1e-4, atol=2e-5) and torch.allclose(lp_d, lp0_ref, rtol=1e-5, atol=1e-4)
