@@ -187,7 +187,8 @@ def rollout_leg(env, n_steps, dev):
     ms = ev0.elapsed_time(ev1)
     return {"value": env.num_envs * n_steps * reps / (ms * 1e-3), "unit": UNIT, "n_steps": n_steps, "envs": env.num_envs,
             "launch": "one CUDA graph per rollout",
-            "policy": "tanh MLP %d-64-64-%d (torch), actions clipped to the Box, GAE by sng_gae" % (env.cfg.obs_dim, env.cfg.act_dim),
+            "policy": "tanh MLP %d-64-64-%d actor + critic%s, actions clipped to the Box, GAE by sng_gae" % (
+                env.cfg.obs_dim, env.cfg.act_dim, " (fused sng_policy_forward kernel)" if policy.fused_supported() else " (torch ops)"),
             "mean_step_reward": float(buf.rewards.mean())}
 
 

@@ -22,9 +22,9 @@ namespace {
 constexpr int H = 64;          // hidden width of SB3's default MlpPolicy
 constexpr int kThreads = 128;
 
-struct Net {                   // one tanh H-H network + linear head, as laid out in shared memory
-    const float *w0, *b0, *w1, *b1, *wh, *bh;
-};
+// tanh(x) = 1 - 2 / (exp(2x) + 1) on the special-function unit (EX2 + RCP): absolute error ~1e-7, saturates
+// correctly for large |x|.  libm's tanhf costs ~30 instructions with branches -- as much as a whole layer-0 row.
+__device__ __forceinline__ float fast_tanh(float x) { return 1.0f - __fdividef(2.0f, __expf(2.0f * x) + 1.0f); }
 
 // y[j] = tanh(b0[j] + sum_k w0[j][k] x[k]) for j < H; w0 rows padded to DP floats in shared memory.
 template <int DP> __device__ __forceinline__ void layer0(const float *w0, const float *b0, const float (&x)[DP], float (&h)[H])
@@ -41,7 +41,7 @@ template <int DP> __device__ __forceinline__ void layer0(const float *w0, const 
             acc = fmaf(v.z, x[4 * k + 2], acc);
             acc = fmaf(v.w, x[4 * k + 3], acc);
         }
-        h[j] = tanhf(acc);
+        h[j] = fast_tanh(acc);
     }
 }
 
@@ -64,7 +64,7 @@ template <int AP> __device__ __forceinline__ void layer1_and_head(const float *w
             acc0 = fmaf(v.z, h[4 * k + 2], acc0);
             acc1 = fmaf(v.w, h[4 * k + 3], acc1);
         }
-        const float g = tanhf(acc0 + acc1);
+        const float g = fast_tanh(acc0 + acc1);
         const float4 *t = reinterpret_cast<const float4 *>(wh_t + j * AP);
 #pragma unroll
         for (int a = 0; a < AP / 4; ++a) {
@@ -91,7 +91,6 @@ __global__ void __launch_bounds__(kThreads) policy_forward_kernel(const sng_mlp 
     // ---- weights into shared memory, rows padded: [H][DP] | [H] | [H][H] | [H] | head^T [H][AP or 4] | head bias ----
     float *p_w0 = sm, *p_b0 = p_w0 + H * DP, *p_w1 = p_b0 + H, *p_b1 = p_w1 + H * H, *p_wh = p_b1 + H, *p_bh = p_wh + H * AP;
     float *v_w0 = p_bh + AP, *v_b0 = v_w0 + H * DP, *v_w1 = v_b0 + H, *v_b1 = v_w1 + H * H, *v_wh = v_b1 + H, *v_bh = v_wh + H * 4;
-    float *tile = v_bh + 4;                     // per-warp obs tile [32][D]
     const int tid = threadIdx.x;
     for (int i = tid; i < H * DP; i += kThreads) {
         const int j = i / DP, k = i - j * DP;
@@ -109,20 +108,13 @@ __global__ void __launch_bounds__(kThreads) policy_forward_kernel(const sng_mlp 
     if (tid < 4) v_bh[tid] = tid == 0 ? m.b_val[0] : 0.f;
     __syncthreads();
 
-    const int lane = tid & 31, warp = tid >> 5;
-    float *rows = tile + warp * (32 * D);
-    const long long n_blocks = (n_envs + 31) / 32;
-    for (long long blk = (long long)blockIdx.x * (kThreads / 32) + warp; blk < n_blocks; blk += (long long)gridDim.x * (kThreads / 32)) {
-        const long long e0 = blk * 32;
-        const int n_valid = (int)((n_envs - e0) < 32 ? (n_envs - e0) : 32);
-        __syncwarp();
-        for (int i = lane; i < n_valid * D; i += 32) rows[i] = obs[e0 * D + i];      // coalesced; rows then read per thread
-        __syncwarp();
-        if (lane >= n_valid) continue;
-        const long long e = e0 + lane;
+    // One thread per env.  The observation row is read straight from global memory: 29 strided 4-byte loads per
+    // thread hit each 128-byte line four times through L1 -- cheap next to the ~17k arithmetic instructions of the
+    // two networks, and it keeps shared memory to the weights alone (4 CTAs = 16 warps per SM).
+    for (long long e = (long long)blockIdx.x * kThreads + tid; e < n_envs; e += (long long)gridDim.x * kThreads) {
         float x[DP];
 #pragma unroll
-        for (int k = 0; k < DP; ++k) x[k] = k < D ? rows[lane * D + k] : 0.f;
+        for (int k = 0; k < DP; ++k) x[k] = k < D ? __ldg(obs + e * D + k) : 0.f;
         float h[H];
         // ---- critic ----
         float val[4];
@@ -157,7 +149,7 @@ int launch(const sng_mlp &m, const float *obs, const float *noise, const float *
            float *act, float *val, float *lp, long long n, cudaStream_t st)
 {
     auto kern = policy_forward_kernel<DP, AP>;
-    const size_t smem = sizeof(float) * ((size_t)2 * (H * DP + H + H * H + H) + H * AP + AP + H * 4 + 4 + (size_t)(kThreads / 32) * 32 * m.obs_dim);
+    const size_t smem = sizeof(float) * ((size_t)2 * (H * DP + H + H * H + H) + H * AP + AP + H * 4 + 4);
     static size_t set = 0;
     if (smem > set) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return SNG_ERR_CUDA;
