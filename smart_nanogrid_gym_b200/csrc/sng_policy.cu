@@ -26,59 +26,82 @@ constexpr int kThreads = 128;
 // correctly for large |x|.  libm's tanhf costs ~30 instructions with branches -- as much as a whole layer-0 row.
 __device__ __forceinline__ float fast_tanh(float x) { return 1.0f - __fdividef(2.0f, __expf(2.0f * x) + 1.0f); }
 
-// y[j] = tanh(b0[j] + sum_k w0[j][k] x[k]) for j < H; w0 rows padded to DP floats in shared memory.
-template <int DP> __device__ __forceinline__ void layer0(const float *w0, const float *b0, const float (&x)[DP], float (&h)[H])
+// Each thread carries NE envs: the kernel is bound by the broadcast LDS.128 reads of the weights (one per four
+// FMAs with one env per thread), so every weight vector fetched from shared memory is used for NE envs.
+//
+// y[n][j] = tanh(b0[j] + sum_k w0[j][k] x[n][k]) for j < H; w0 rows padded to DP floats in shared memory.
+template <int DP, int NE>
+__device__ __forceinline__ void layer0(const float *w0, const float *b0, const float (&x)[NE][DP], float (&h)[NE][H])
 {
 #pragma unroll
     for (int j = 0; j < H; ++j) {
-        float acc = b0[j];
+        float acc[NE];
+#pragma unroll
+        for (int n = 0; n < NE; ++n) acc[n] = b0[j];
         const float4 *w = reinterpret_cast<const float4 *>(w0 + j * DP);
 #pragma unroll
         for (int k = 0; k < DP / 4; ++k) {
             const float4 v = w[k];
-            acc = fmaf(v.x, x[4 * k], acc);
-            acc = fmaf(v.y, x[4 * k + 1], acc);
-            acc = fmaf(v.z, x[4 * k + 2], acc);
-            acc = fmaf(v.w, x[4 * k + 3], acc);
+#pragma unroll
+            for (int n = 0; n < NE; ++n) {
+                acc[n] = fmaf(v.x, x[n][4 * k], acc[n]);
+                acc[n] = fmaf(v.y, x[n][4 * k + 1], acc[n]);
+                acc[n] = fmaf(v.z, x[n][4 * k + 2], acc[n]);
+                acc[n] = fmaf(v.w, x[n][4 * k + 3], acc[n]);
+            }
         }
-        h[j] = fast_tanh(acc);
+#pragma unroll
+        for (int n = 0; n < NE; ++n) h[n][j] = fast_tanh(acc[n]);
     }
 }
 
 // out[a] = bh[a] + sum_j wh_t[j][a] * tanh(b1[j] + sum_k w1[j][k] h[k]); the second hidden layer is never stored.
 // wh_t is the head weight transposed and padded to AP floats per row.
-template <int AP> __device__ __forceinline__ void layer1_and_head(const float *w1, const float *b1, const float *wh_t,
-                                                                  const float *bh, const float (&h)[H], float (&out)[AP])
+template <int AP, int NE>
+__device__ __forceinline__ void layer1_and_head(const float *w1, const float *b1, const float *wh_t, const float *bh,
+                                                const float (&h)[NE][H], float (&out)[NE][AP])
 {
 #pragma unroll
-    for (int a = 0; a < AP; ++a) out[a] = bh[a];
+    for (int n = 0; n < NE; ++n)
+#pragma unroll
+        for (int a = 0; a < AP; ++a) out[n][a] = bh[a];
 #pragma unroll 2
     for (int j = 0; j < H; ++j) {
-        float acc0 = b1[j], acc1 = 0.f;           // two chains: halves the dependent-FMA latency
+        float acc0[NE], acc1[NE];                 // two chains per env: halves the dependent-FMA latency
+#pragma unroll
+        for (int n = 0; n < NE; ++n) { acc0[n] = b1[j]; acc1[n] = 0.f; }
         const float4 *w = reinterpret_cast<const float4 *>(w1 + j * H);
 #pragma unroll
         for (int k = 0; k < H / 4; ++k) {
             const float4 v = w[k];
-            acc0 = fmaf(v.x, h[4 * k], acc0);
-            acc1 = fmaf(v.y, h[4 * k + 1], acc1);
-            acc0 = fmaf(v.z, h[4 * k + 2], acc0);
-            acc1 = fmaf(v.w, h[4 * k + 3], acc1);
+#pragma unroll
+            for (int n = 0; n < NE; ++n) {
+                acc0[n] = fmaf(v.x, h[n][4 * k], acc0[n]);
+                acc1[n] = fmaf(v.y, h[n][4 * k + 1], acc1[n]);
+                acc0[n] = fmaf(v.z, h[n][4 * k + 2], acc0[n]);
+                acc1[n] = fmaf(v.w, h[n][4 * k + 3], acc1[n]);
+            }
         }
-        const float g = fast_tanh(acc0 + acc1);
+        float g[NE];
+#pragma unroll
+        for (int n = 0; n < NE; ++n) g[n] = fast_tanh(acc0[n] + acc1[n]);
         const float4 *t = reinterpret_cast<const float4 *>(wh_t + j * AP);
 #pragma unroll
         for (int a = 0; a < AP / 4; ++a) {
             const float4 v = t[a];
-            out[4 * a] = fmaf(v.x, g, out[4 * a]);
-            out[4 * a + 1] = fmaf(v.y, g, out[4 * a + 1]);
-            out[4 * a + 2] = fmaf(v.z, g, out[4 * a + 2]);
-            out[4 * a + 3] = fmaf(v.w, g, out[4 * a + 3]);
+#pragma unroll
+            for (int n = 0; n < NE; ++n) {
+                out[n][4 * a] = fmaf(v.x, g[n], out[n][4 * a]);
+                out[n][4 * a + 1] = fmaf(v.y, g[n], out[n][4 * a + 1]);
+                out[n][4 * a + 2] = fmaf(v.z, g[n], out[n][4 * a + 2]);
+                out[n][4 * a + 3] = fmaf(v.w, g[n], out[n][4 * a + 3]);
+            }
         }
     }
 }
 
 // DP: obs_dim padded to a multiple of 4 (<= 32); AP: act_dim padded to a multiple of 4 (<= 16).
-template <int DP, int AP>
+template <int DP, int AP, int NE>
 __global__ void __launch_bounds__(kThreads) policy_forward_kernel(const sng_mlp m, const float *__restrict__ obs,
                                                                  const float *__restrict__ noise,
                                                                  const float *__restrict__ low,
@@ -108,37 +131,49 @@ __global__ void __launch_bounds__(kThreads) policy_forward_kernel(const sng_mlp 
     if (tid < 4) v_bh[tid] = tid == 0 ? m.b_val[0] : 0.f;
     __syncthreads();
 
-    // One thread per env.  The observation row is read straight from global memory: 29 strided 4-byte loads per
-    // thread hit each 128-byte line four times through L1 -- cheap next to the ~17k arithmetic instructions of the
-    // two networks, and it keeps shared memory to the weights alone (4 CTAs = 16 warps per SM).
-    for (long long e = (long long)blockIdx.x * kThreads + tid; e < n_envs; e += (long long)gridDim.x * kThreads) {
-        float x[DP];
+    // NE envs per thread (env e + n * stride).  Observation rows are read straight from global memory: 29 strided
+    // 4-byte loads per thread hit each 128-byte line four times through L1 -- cheap next to the ~17k arithmetic
+    // instructions per env, and it keeps shared memory to the weights alone.
+    const long long stride = (long long)gridDim.x * kThreads;
+    for (long long e = (long long)blockIdx.x * kThreads + tid; e < n_envs; e += NE * stride) {
+        float x[NE][DP];
 #pragma unroll
-        for (int k = 0; k < DP; ++k) x[k] = k < D ? __ldg(obs + e * D + k) : 0.f;
-        float h[H];
+        for (int n = 0; n < NE; ++n) {
+            const long long en = e + n * stride < n_envs ? e + n * stride : e;    // a missing env repeats env e (not stored)
+#pragma unroll
+            for (int k = 0; k < DP; ++k) x[n][k] = k < D ? __ldg(obs + en * D + k) : 0.f;
+        }
+        float h[NE][H];
         // ---- critic ----
-        float val[4];
-        layer0<DP>(v_w0, v_b0, x, h);
-        layer1_and_head<4>(v_w1, v_b1, v_wh, v_bh, h, val);
-        values[e] = val[0];
+        float val[NE][4];
+        layer0<DP, NE>(v_w0, v_b0, x, h);
+        layer1_and_head<4, NE>(v_w1, v_b1, v_wh, v_bh, h, val);
+#pragma unroll
+        for (int n = 0; n < NE; ++n)
+            if (e + n * stride < n_envs) values[e + n * stride] = val[n][0];
         if (actions == nullptr) continue;        // value-only call (bootstrap value of the last observation)
         // ---- actor ----
-        float mean[AP];
-        layer0<DP>(p_w0, p_b0, x, h);
-        layer1_and_head<AP>(p_w1, p_b1, p_wh, p_bh, h, mean);
-        float lp = 0.f;
+        float mean[NE][AP];
+        layer0<DP, NE>(p_w0, p_b0, x, h);
+        layer1_and_head<AP, NE>(p_w1, p_b1, p_wh, p_bh, h, mean);
 #pragma unroll
-        for (int a = 0; a < AP; ++a) {
-            if (a < A) {
-                const float ls = __ldg(m.log_std + a);
-                const float z = noise ? noise[e * A + a] : 0.f;
-                const float act = fmaf(z, expf(ls), mean[a]);          // DiagGaussian sample
-                raw_actions[e * A + a] = act;
-                actions[e * A + a] = fminf(fmaxf(act, __ldg(low + a)), __ldg(high + a));   // SB3 clips Box actions before env.step
-                lp += -0.5f * z * z - ls - 0.91893853320467274f;      // log N(act; mean, std), 0.5 * log(2 pi)
+        for (int n = 0; n < NE; ++n) {
+            const long long en = e + n * stride;
+            if (en >= n_envs) continue;
+            float lp = 0.f;
+#pragma unroll
+            for (int a = 0; a < AP; ++a) {
+                if (a < A) {
+                    const float ls = __ldg(m.log_std + a);
+                    const float z = noise ? noise[en * A + a] : 0.f;
+                    const float act = fmaf(z, expf(ls), mean[n][a]);      // DiagGaussian sample
+                    raw_actions[en * A + a] = act;
+                    actions[en * A + a] = fminf(fmaxf(act, __ldg(low + a)), __ldg(high + a));   // SB3 clips Box actions before env.step
+                    lp += -0.5f * z * z - ls - 0.91893853320467274f;     // log N(act; mean, std), 0.5 * log(2 pi)
+                }
             }
+            log_probs[en] = lp;
         }
-        log_probs[e] = lp;
     }
 }
 
@@ -148,7 +183,8 @@ template <int DP, int AP>
 int launch(const sng_mlp &m, const float *obs, const float *noise, const float *low, const float *high, float *raw,
            float *act, float *val, float *lp, long long n, cudaStream_t st)
 {
-    auto kern = policy_forward_kernel<DP, AP>;
+    constexpr int NE = 2;      // envs per thread
+    auto kern = policy_forward_kernel<DP, AP, NE>;
     const size_t smem = sizeof(float) * ((size_t)2 * (H * DP + H + H * H + H) + H * AP + AP + H * 4 + 4);
     static size_t set = 0;
     if (smem > set) {
@@ -160,7 +196,7 @@ int launch(const sng_mlp &m, const float *obs, const float *noise, const float *
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem);
     long long grid = (long long)sms * (per_sm > 0 ? per_sm : 1);
-    const long long need = (n + kThreads - 1) / kThreads;
+    const long long need = (n + (long long)kThreads * NE - 1) / ((long long)kThreads * NE);
     if (grid > need) grid = need;
     kern<<<(unsigned)grid, kThreads, smem, st>>>(m, obs, noise, low, high, raw, act, val, lp, n);
     return cudaGetLastError() == cudaSuccess ? SNG_OK : SNG_ERR_CUDA;
