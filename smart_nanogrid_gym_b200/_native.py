@@ -69,7 +69,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", "Makefile"))] + [HEADER]
     stale = (not os.path.exists(LIB_PATH)) or any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in srcs)
     if stale or force:
-        cmd = ["make", "-C", CSRC] + (["-B"] if force else [])
+        cmd = ["make", "-j4", "-C", CSRC] + (["-B"] if force else [])
         res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
         if verbose or res.returncode != 0:
             print(res.stdout)
