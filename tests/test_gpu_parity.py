@@ -605,3 +605,26 @@ def test_single_env_reload_of_last_schedule_follows_quirk_q7():
     first_r, again_r = rewards[True]
     # with the requested SoC restored the penalties come back (pv_shift is redrawn on reset, so costs differ slightly)
     assert min(again_r) < -1.0
+
+
+@pytest.mark.parametrize("kw,ref_mean,ref_std,ref_episodes", [
+    (dict(number_of_chargers=10), -403.3, 99.5, 3000),
+    (dict(number_of_chargers=10, pv_system_available_in_model=False, battery_system_available_in_model=False), -397.3, 93.8, 3000),
+    (dict(number_of_chargers=4), -173.3, 62.2, 3000),
+    (dict(number_of_chargers=10, vehicle_to_everything=True), -3074.4, 500.1, 1500),
+])
+def test_random_policy_returns_match_the_reference_statistics(kw, ref_mean, ref_std, ref_episodes):
+    """Statistical known answers of the LIVE reference under uniform random actions (BASELINE.md section 2 /
+    SURVEY section 6): in-kernel sampling + fused auto-reset + step reproduce the episode-return distribution
+    (mean within 4 standard errors of the reference's own estimate, spread within 6 %)."""
+    E = 131072
+    env = _env(E, "float32", seed=0, **kw)
+    env.reset()
+    g = torch.Generator(device="cuda:0").manual_seed(0)
+    for _ in range(24):
+        env.step(env.sample_actions(g))
+    ret = env.last_return.double()
+    se = ref_std / np.sqrt(ref_episodes)
+    assert abs(ret.mean().item() - ref_mean) < 4 * se + 0.5, (ret.mean().item(), ref_mean)
+    assert abs(ret.std().item() / ref_std - 1) < 0.06, (ret.std().item(), ref_std)
+    env.close()
