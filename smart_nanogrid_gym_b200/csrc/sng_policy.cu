@@ -28,73 +28,77 @@ __device__ __forceinline__ float fast_tanh(float x) { return 1.0f - __fdividef(2
 
 // Each thread carries NE envs: the kernel is bound by the broadcast LDS.128 reads of the weights (one per four
 // FMAs with one env per thread), so every weight vector fetched from shared memory is used for NE envs.
+// The multiply-adds are Blackwell's packed FP32 pairs (__ffma2_rn, SASS FFMA2): a pair accumulates the even-k and
+// the odd-k half of a dot product, so the weight pairs come straight out of the float4 loads and the activation
+// pairs are adjacent registers -- half the FMA instructions, no packing moves.
 //
-// y[n][j] = tanh(b0[j] + sum_k w0[j][k] x[n][k]) for j < H; w0 rows padded to DP floats in shared memory.
+// y[n][j] = tanh(b0[j] + sum_k w0[j][k] x[n][k]) for j < H; w0 rows padded to DP floats in shared memory;
+// x and y are held as (even, odd) pairs.
 template <int DP, int NE>
-__device__ __forceinline__ void layer0(const float *w0, const float *b0, const float (&x)[NE][DP], float (&h)[NE][H])
+__device__ __forceinline__ void layer0(const float *w0, const float *b0, const float2 (&x)[NE][DP / 2], float2 (&h)[NE][H / 2])
 {
 #pragma unroll
     for (int j = 0; j < H; ++j) {
-        float acc[NE];
+        float2 acc[NE];
 #pragma unroll
-        for (int n = 0; n < NE; ++n) acc[n] = b0[j];
+        for (int n = 0; n < NE; ++n) acc[n] = make_float2(b0[j], 0.f);
         const float4 *w = reinterpret_cast<const float4 *>(w0 + j * DP);
 #pragma unroll
         for (int k = 0; k < DP / 4; ++k) {
             const float4 v = w[k];
 #pragma unroll
             for (int n = 0; n < NE; ++n) {
-                acc[n] = fmaf(v.x, x[n][4 * k], acc[n]);
-                acc[n] = fmaf(v.y, x[n][4 * k + 1], acc[n]);
-                acc[n] = fmaf(v.z, x[n][4 * k + 2], acc[n]);
-                acc[n] = fmaf(v.w, x[n][4 * k + 3], acc[n]);
+                acc[n] = __ffma2_rn(make_float2(v.x, v.y), x[n][2 * k], acc[n]);
+                acc[n] = __ffma2_rn(make_float2(v.z, v.w), x[n][2 * k + 1], acc[n]);
             }
         }
 #pragma unroll
-        for (int n = 0; n < NE; ++n) h[n][j] = fast_tanh(acc[n]);
+        for (int n = 0; n < NE; ++n) {
+            const float y = fast_tanh(acc[n].x + acc[n].y);
+            if (j & 1) h[n][j / 2].y = y; else h[n][j / 2].x = y;
+        }
     }
 }
 
 // out[a] = bh[a] + sum_j wh_t[j][a] * tanh(b1[j] + sum_k w1[j][k] h[k]); the second hidden layer is never stored.
-// wh_t is the head weight transposed and padded to AP floats per row.
+// wh_t is the head weight transposed and padded to AP floats per row; out is held as pairs.
 template <int AP, int NE>
 __device__ __forceinline__ void layer1_and_head(const float *w1, const float *b1, const float *wh_t, const float *bh,
-                                                const float (&h)[NE][H], float (&out)[NE][AP])
+                                                const float2 (&h)[NE][H / 2], float2 (&out)[NE][AP / 2])
 {
 #pragma unroll
     for (int n = 0; n < NE; ++n)
 #pragma unroll
-        for (int a = 0; a < AP; ++a) out[n][a] = bh[a];
+        for (int a = 0; a < AP / 2; ++a) out[n][a] = make_float2(bh[2 * a], bh[2 * a + 1]);
 #pragma unroll 2
     for (int j = 0; j < H; ++j) {
-        float acc0[NE], acc1[NE];                 // two chains per env: halves the dependent-FMA latency
+        float2 acc0[NE], acc1[NE];                // two pair chains per env: four independent FMA chains
 #pragma unroll
-        for (int n = 0; n < NE; ++n) { acc0[n] = b1[j]; acc1[n] = 0.f; }
+        for (int n = 0; n < NE; ++n) { acc0[n] = make_float2(b1[j], 0.f); acc1[n] = make_float2(0.f, 0.f); }
         const float4 *w = reinterpret_cast<const float4 *>(w1 + j * H);
 #pragma unroll
         for (int k = 0; k < H / 4; ++k) {
             const float4 v = w[k];
 #pragma unroll
             for (int n = 0; n < NE; ++n) {
-                acc0[n] = fmaf(v.x, h[n][4 * k], acc0[n]);
-                acc1[n] = fmaf(v.y, h[n][4 * k + 1], acc1[n]);
-                acc0[n] = fmaf(v.z, h[n][4 * k + 2], acc0[n]);
-                acc1[n] = fmaf(v.w, h[n][4 * k + 3], acc1[n]);
+                acc0[n] = __ffma2_rn(make_float2(v.x, v.y), h[n][2 * k], acc0[n]);
+                acc1[n] = __ffma2_rn(make_float2(v.z, v.w), h[n][2 * k + 1], acc1[n]);
             }
         }
-        float g[NE];
+        float2 g[NE];
 #pragma unroll
-        for (int n = 0; n < NE; ++n) g[n] = fast_tanh(acc0[n] + acc1[n]);
-        const float4 *t = reinterpret_cast<const float4 *>(wh_t + j * AP);
+        for (int n = 0; n < NE; ++n) {
+            const float t = fast_tanh((acc0[n].x + acc0[n].y) + (acc1[n].x + acc1[n].y));
+            g[n] = make_float2(t, t);
+        }
+        const float4 *t4 = reinterpret_cast<const float4 *>(wh_t + j * AP);
 #pragma unroll
         for (int a = 0; a < AP / 4; ++a) {
-            const float4 v = t[a];
+            const float4 v = t4[a];
 #pragma unroll
             for (int n = 0; n < NE; ++n) {
-                out[n][4 * a] = fmaf(v.x, g[n], out[n][4 * a]);
-                out[n][4 * a + 1] = fmaf(v.y, g[n], out[n][4 * a + 1]);
-                out[n][4 * a + 2] = fmaf(v.z, g[n], out[n][4 * a + 2]);
-                out[n][4 * a + 3] = fmaf(v.w, g[n], out[n][4 * a + 3]);
+                out[n][2 * a] = __ffma2_rn(make_float2(v.x, v.y), g[n], out[n][2 * a]);
+                out[n][2 * a + 1] = __ffma2_rn(make_float2(v.z, v.w), g[n], out[n][2 * a + 1]);
             }
         }
     }
@@ -136,24 +140,25 @@ __global__ void __launch_bounds__(kThreads) policy_forward_kernel(const sng_mlp 
     // instructions per env, and it keeps shared memory to the weights alone.
     const long long stride = (long long)gridDim.x * kThreads;
     for (long long e = (long long)blockIdx.x * kThreads + tid; e < n_envs; e += NE * stride) {
-        float x[NE][DP];
+        float2 x[NE][DP / 2];
 #pragma unroll
         for (int n = 0; n < NE; ++n) {
             const long long en = e + n * stride < n_envs ? e + n * stride : e;    // a missing env repeats env e (not stored)
 #pragma unroll
-            for (int k = 0; k < DP; ++k) x[n][k] = k < D ? __ldg(obs + en * D + k) : 0.f;
+            for (int k = 0; k < DP / 2; ++k)
+                x[n][k] = make_float2(2 * k < D ? __ldg(obs + en * D + 2 * k) : 0.f, 2 * k + 1 < D ? __ldg(obs + en * D + 2 * k + 1) : 0.f);
         }
-        float h[NE][H];
+        float2 h[NE][H / 2];
         // ---- critic ----
-        float val[NE][4];
+        float2 val[NE][2];
         layer0<DP, NE>(v_w0, v_b0, x, h);
         layer1_and_head<4, NE>(v_w1, v_b1, v_wh, v_bh, h, val);
 #pragma unroll
         for (int n = 0; n < NE; ++n)
-            if (e + n * stride < n_envs) values[e + n * stride] = val[n][0];
+            if (e + n * stride < n_envs) values[e + n * stride] = val[n][0].x;
         if (actions == nullptr) continue;        // value-only call (bootstrap value of the last observation)
         // ---- actor ----
-        float mean[NE][AP];
+        float2 mean[NE][AP / 2];
         layer0<DP, NE>(p_w0, p_b0, x, h);
         layer1_and_head<AP, NE>(p_w1, p_b1, p_wh, p_bh, h, mean);
 #pragma unroll
@@ -166,7 +171,8 @@ __global__ void __launch_bounds__(kThreads) policy_forward_kernel(const sng_mlp 
                 if (a < A) {
                     const float ls = __ldg(m.log_std + a);
                     const float z = noise ? noise[en * A + a] : 0.f;
-                    const float act = fmaf(z, expf(ls), mean[n][a]);      // DiagGaussian sample
+                    const float mu = (a & 1) ? mean[n][a / 2].y : mean[n][a / 2].x;
+                    const float act = fmaf(z, expf(ls), mu);               // DiagGaussian sample
                     raw_actions[en * A + a] = act;
                     actions[en * A + a] = fminf(fmaxf(act, __ldg(low + a)), __ldg(high + a));   // SB3 clips Box actions before env.step
                     lp += -0.5f * z * z - ls - 0.91893853320467274f;     // log N(act; mean, std), 0.5 * log(2 pi)
