@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define SNG_ABI_VERSION 2
+#define SNG_ABI_VERSION 3
 #define SNG_MAX_VEHICLES 8   /* schedule slots per spot and day */
 #define SNG_MAX_SPOTS 255
 #define SNG_MAX_TABLE 512    /* entries of the shared PV / price tables (two days) */
@@ -118,6 +118,9 @@ typedef struct {
     uint32_t *err;          /* optional [E] sticky SNG_FLAG_* bits */
     void *diag;             /* optional [E][diag_count] real per-step diagnostics */
     void *last_return;      /* optional [E] real: return of the most recently finished episode */
+    void *spot_power;       /* optional [E][n_spots] real per-step diagnostics: power of every charging spot
+                             * (charger_power_values, utils/charging_station.py:283-300; logged by the
+                             * reference's step as 'Charger_power_values', envs/smart_nanogrid_environment.py:161) */
 } sng_buffers;
 
 enum { /* diagnostics row, subset of central_management_system.py:128-155 */
@@ -151,7 +154,9 @@ int sng_bind(sng_env *env, const sng_buffers *buffers);
 
 /* Start new episodes (sampling mode).  mask: optional DEVICE pointer [E] (1 = reset this env).
  * reset_battery != 0 also sets the battery SoC to b_soc0 (the reference never does after
- * construction, quirk Q8).  Writes the reset observation of the selected envs to `obs`. */
+ * construction, quirk Q8).  Writes the reset observation of the selected envs to `obs`.
+ * A masked reset leaves the handle-wide settings alone: it needs sampling mode (not a replayed schedule) and
+ * the seed of the last full reset, otherwise SNG_ERR_STATE. */
 int sng_reset(sng_env *env, uint64_t seed, const uint8_t *mask, int reset_battery, void *stream);
 
 /* Replay mode: upload a schedule (host arrays), rewind to t = 0 and write the reset obs.
@@ -206,6 +211,10 @@ typedef struct {
 int sng_policy_forward(const sng_mlp *mlp, const float *obs, const float *noise, const float *low, const float *high,
                        float *raw_actions, float *actions, float *values, float *log_probs, int64_t n_envs,
                        void *stream);
+
+/* Launches an EMPTY kernel on `stream`: lets a caller measure the device's kernel-to-kernel launch latency (the
+ * floor under one sng_step per step for batches that live in L2; bench.py reports it beside those numbers). */
+int sng_null_launch(void *stream);
 
 /* Kernels launched by this handle so far (bench.py's gpu_launches claim). */
 int64_t sng_launch_count(const sng_env *env);

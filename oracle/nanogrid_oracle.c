@@ -278,12 +278,12 @@ void ngo_step(const ngo_config *c, ngo_state *s, const double *actions, float *o
                  diag ? diag + e * NGO_D_COUNT : (double *)0);
 }
 
-/* solvers/RBC/rbc.py:6-29 with generic offsets: departure obs index 4(1+pv)+N+i,
- * radiation obs[0], next-step radiation obs[2]; battery action 0. */
+/* solvers/RBC/rbc.py:6-29 with generic offsets: departure obs index (1+pv)(1+H)+N+i (the reference's
+ * literal 8+N is PV on, H = 3), radiation obs[0], next-step radiation obs[2]; battery action 0. */
 void ngo_rbc_actions(const ngo_config *c, int64_t n_envs, const float *obs, double *actions)
 {
     const int N = c->n_spots, A = ngo_act_dim(c), D = ngo_obs_dim(c);
-    const int off = (c->pv ? 8 : 4) + N;
+    const int off = (1 + (c->pv ? 1 : 0)) * (1 + c->horizon) + N;
     for (int64_t e = 0; e < n_envs; e++) {
         const float *o = obs + e * D;
         double *a = actions + e * A;

@@ -21,7 +21,7 @@ DIAG = ("total_ch", "total_dis", "solar", "batt_power", "grid_power", "grid_cost
 
 EXPORTS = ("sng_abi_version", "sng_sizeof", "sng_last_error", "sng_query_layout", "sng_create", "sng_destroy", "sng_bind",
            "sng_reset", "sng_load_schedule", "sng_step", "sng_rollout", "sng_step_host", "sng_sample_plan",
-           "sng_error_flags", "sng_launch_count", "sng_set_tuning", "sng_set_pipeline", "sng_gae", "sng_policy_forward")
+           "sng_error_flags", "sng_launch_count", "sng_set_tuning", "sng_set_pipeline", "sng_gae", "sng_policy_forward", "sng_null_launch")
 
 
 class SngConfig(C.Structure):
@@ -46,7 +46,7 @@ class SngLayout(C.Structure):
 class SngBuffers(C.Structure):
     _fields_ = [("struct_size", C.c_uint32), ("_pad", C.c_uint32)] + [(n, C.c_void_p) for n in (
         "actions", "obs", "reward", "done", "terminal_obs", "spot", "envst", "plan", "err", "diag",
-        "last_return")]
+        "last_return", "spot_power")]
 
 
 class SngScheduleView(C.Structure):
@@ -107,9 +107,10 @@ def lib():
         L.sng_launch_count.restype = C.c_int64
         L.sng_set_tuning.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
         L.sng_set_pipeline.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.sng_null_launch.argtypes = [C.c_void_p]
         L.sng_gae.argtypes = [C.c_void_p] * 7 + [C.c_int, C.c_int64, C.c_float, C.c_float, C.c_void_p]
         L.sng_policy_forward.argtypes = [C.POINTER(SngMlp)] + [C.c_void_p] * 8 + [C.c_int64, C.c_void_p]
-        if L.sng_abi_version() != 2:
+        if L.sng_abi_version() != 3:
             raise NativeError("libsng.so ABI version mismatch")
         for which, st in enumerate((SngConfig, SngLayout, SngBuffers, SngScheduleView)):
             if L.sng_sizeof(which) != C.sizeof(st):

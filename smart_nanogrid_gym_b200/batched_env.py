@@ -76,6 +76,7 @@ class BatchedSmartNanogridEnv:
         self._plan = None
         self.err = z(E, dtype=torch.int32)
         self.diag = z(E, self.layout.diag_count, dtype=self.real) if want_diagnostics else None
+        self.spot_power = z(E, N, dtype=self.real) if want_diagnostics else None   # per-spot power of the last step
         self.last_return = z(E, dtype=self.real)
         self.truncated = z(E, dtype=torch.bool)
         low, high = cfg.action_bounds()
@@ -102,6 +103,7 @@ class BatchedSmartNanogridEnv:
         b.actions, b.obs, b.reward, b.done = (_ptr(self._bound_actions), _ptr(obs), _ptr(rew), _ptr(done))
         b.terminal_obs, b.spot, b.envst = _ptr(self.terminal_obs), _ptr(self._spot), _ptr(self._envst)
         b.plan, b.err, b.diag, b.last_return = _ptr(self._plan), _ptr(self.err), _ptr(self.diag), _ptr(self.last_return)
+        b.spot_power = _ptr(self.spot_power)
         nat.check(self._lib.sng_bind(self._h, C.byref(b)))
 
     def _ensure_plan(self):
@@ -168,7 +170,9 @@ class BatchedSmartNanogridEnv:
     def reset(self, seed: Optional[int] = None, mask: Optional[torch.Tensor] = None, reset_battery: bool = False):
         """Start a new sampled episode in every env (or in the envs selected by `mask`).
         Returns the observation tensor [E, D] (reference: reset() -> (obs, {}), …environment.py:311-351).
-        The battery SoC is kept across resets like the reference does."""
+        The battery SoC is kept across resets like the reference does.
+        A masked reset leaves the handle-wide settings alone: it cannot change the seed and is refused while a
+        loaded schedule is being replayed (the other envs would silently switch to sampling)."""
         self.cfg.validate_modes()
         if seed is not None:
             self.seed_value = int(seed)
@@ -359,7 +363,7 @@ class BatchedSmartNanogridEnv:
         (SURVEY 8c): per spot 0 if no vehicle, 1 if it departs within 3 h, else the mean of the current
         and next-step normalised radiation; battery action 0."""
         cfg = self.cfg
-        off = (8 if cfg.pv else 4) + cfg.n_spots
+        off = (1 + int(cfg.pv)) * (1 + cfg.hours_ahead) + cfg.n_spots     # departure entries follow the SoC entries
         dep = obs[:, off:off + cfg.n_spots].to(torch.float64)
         rad = ((obs[:, 0].to(torch.float64) + obs[:, 2].to(torch.float64)) / 2)[:, None].expand_as(dep)
         a = torch.where(dep == 0, torch.zeros_like(dep), torch.where(dep < 0.16667, torch.ones_like(dep), rad))

@@ -42,6 +42,8 @@ __global__ void __launch_bounds__(256) gae_kernel(const float *__restrict__ rewa
     }
 }
 
+static __global__ void null_kernel() {}
+
 struct sng_env {
     sng::EngineBase *eng;
 };
@@ -172,6 +174,12 @@ int sng_error_flags(sng_env *env, uint32_t *host_out, void *stream)
     return done(env, env->eng->error_flags(host_out, (cudaStream_t)stream));
 }
 
+int sng_null_launch(void *stream)
+{
+    null_kernel<<<1, 32, 0, (cudaStream_t)stream>>>();
+    return cudaGetLastError() == cudaSuccess ? SNG_OK : fail(SNG_ERR_CUDA, "sng_null_launch failed");
+}
+
 int64_t sng_launch_count(const sng_env *env) { return (env && env->eng) ? env->eng->launches : 0; }
 
 int sng_set_tuning(sng_env *env, int warps_per_cta, int use_generic_kernel, int use_bulk_copy, int host_chunks)
@@ -187,10 +195,15 @@ int sng_gae(const float *rewards, const float *values, const uint8_t *episode_st
     if (!rewards || !values || !episode_starts || !last_values || !last_dones || !advantages || !returns || n_steps < 1 ||
         n_envs < 1)
         return fail(SNG_ERR_ARG, "sng_gae: bad arguments");
+    int prev = -1, dev = -1;                       // launch on the device that owns the buffers
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, rewards) == cudaSuccess && at.type == cudaMemoryTypeDevice) dev = at.device;
+    const bool switched = dev >= 0 && cudaGetDevice(&prev) == cudaSuccess && prev != dev && cudaSetDevice(dev) == cudaSuccess;
     gae_kernel<<<(unsigned)((n_envs + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
         rewards, values, episode_starts, last_values, last_dones, advantages, returns, n_steps, (long long)n_envs, gamma,
         gae_lambda);
     const cudaError_t e = cudaGetLastError();
+    if (switched) cudaSetDevice(prev);
     if (e != cudaSuccess) return fail(SNG_ERR_CUDA, std::string("sng_gae: ") + cudaGetErrorString(e));
     return SNG_OK;
 }

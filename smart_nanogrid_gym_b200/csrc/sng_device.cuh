@@ -92,6 +92,7 @@ template <typename real> struct Params {
     uint32_t *err;
     real *diag;
     real *last_ret;
+    real *spot_power;      // [E][N] or null: per-spot power of the step (diagnostics)
 };
 
 // ------------------------------------------------------------------------------------------
@@ -545,6 +546,7 @@ __device__ __forceinline__ Arrivals env_step(const Params<real> &p, long long e,
                 const PowerSoc<real> r = discharge_vehicle(a * p.ev_pmax * p.ev_eff, p.dt, s_prev, (real)((hd >> 16) & 0xFFu));
                 P = r.P;
                 s_new = r.soc;
+                if (p.spot_power) p.spot_power[(size_t)e * N + (i * L + sub)] = P;
                 if (EXACT) {
                     if (P < 0) cneg[nneg++] = (double)P;
                     if (P > 0) cpos[npos++] = (double)P;
@@ -588,6 +590,7 @@ __device__ __forceinline__ Arrivals env_step(const Params<real> &p, long long e,
         }
         sp[PL_SOC * kBlock] = real_to_word(r.soc);
         io.fix_soc(i, (float)r.soc);
+        if (p.spot_power) p.spot_power[(size_t)e * N + (i * L + sub)] = r.P;
     }
 
     // ---- env-level phase: CentralManagementSystem.manage_nanogrid (central_management_system.py:99-113) ----
@@ -645,6 +648,17 @@ __device__ __forceinline__ Arrivals env_step(const Params<real> &p, long long e,
     const real reward = -total_cost;                                      // ...environment.py:183
 
     if (lead) write_obs_env<real, NCT, ND>(p, obs, t, es.pv_shift, soc_b);   // obs at the pre-increment t, :173
+    if (p.spot_power) {
+        // diagnostics only (cold): the power of the charging / idle spots is a function of the action and of the
+        // header, which is unchanged until the arrivals are admitted below; discharging spots were written above
+        for (int i = 0; i < M; ++i) {
+            const uint32_t hd = (uint32_t)spot[(size_t)i * SP + PL_HDR * kBlock];
+            const real a = io.action(i, 0);
+            const bool present = (int)(hd & 0xFFu) <= t && t < (int)((hd >> 8) & 0xFFu);
+            if (!present || a >= (real)0)
+                p.spot_power[(size_t)e * N + (i * L + sub)] = present ? (EXACT ? a * kw * p.ev_eff : a * kw) : (real)0;
+        }
+    }
     if (lead && p.diag) {
         real *diag = p.diag + (size_t)e * D_COUNT;
         diag[D_TOTAL_CH] = pos; diag[D_TOTAL_DIS] = neg; diag[D_SOLAR] = solar;

@@ -37,6 +37,21 @@ struct EngineBase {
 EngineBase *make_engine_f32(const sng_config &cfg, int device, std::string &err);
 EngineBase *make_engine_f64(const sng_config &cfg, int device, std::string &err);
 
+// Makes `dev` the current device for the lifetime of the guard and restores the caller's afterwards
+// (a process may drive several GPUs, one handle each).
+struct DeviceGuard {
+    int prev = -1;
+    bool switched = false;
+    explicit DeviceGuard(int dev)
+    {
+        if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) switched = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard()
+    {
+        if (switched) cudaSetDevice(prev);
+    }
+};
+
 #define SNG_CUDA(call)                                                                          \
     do {                                                                                        \
         cudaError_t _e = (call);                                                                \
@@ -207,13 +222,20 @@ __global__ void __launch_bounds__(SNG_STEP_MAXT, (EXACT || NCT / L > 32) ? 2 : (
         StateRegs<real, NCT / L> st;
         float4 areg[AV];
         // ---- put everything this block needs in flight first ----
+        if (MULTI && s > 0) {
+            // the stages are reused: the previous step's bulk store must have read obs_s before any lane writes
+            // it again, and the admission queue's generic-proxy writes to act_s must be ordered before the copy
+            // engine overwrites it
+            if (tma_load) fence_proxy_async();
+            if (tma_store && lane == 0) bulk_wait_read<0>();
+            __syncwarp();
+        }
         if (tma_load) {
             if (lane == 0) {
                 if (s == 0) {
                     mbar_init(bar, 1);
                     fence_mbar_init();
                 }
-                if (MULTI && s > 0 && tma_store) bulk_wait_read<0>();   // the previous obs store has left shared memory
                 mbar_expect_tx(bar, act_bytes);
                 bulk_g2s(act_s, act_g, act_bytes, bar);
             }
@@ -383,7 +405,7 @@ public:
             error = "sng_create: the float64 validation build supports at most 128 spots";
             return SNG_ERR_UNSUPPORTED;
         }
-        SNG_CUDA(cudaSetDevice(dev));
+        DeviceGuard guard(dev);
         {
             int v = 0;
             SNG_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev));
@@ -433,6 +455,7 @@ public:
 
     ~Engine() override
     {
+        DeviceGuard guard(device);
         if (d_tables) cudaFree(d_tables);
         if (d_flag) cudaFree(d_flag);
         for (auto e : ev_in) cudaEventDestroy(e);
@@ -452,7 +475,7 @@ public:
         p.actions = (const real *)b->actions; p.obs = b->obs; p.reward = (real *)b->reward; p.done = b->done;
         p.tobs = b->terminal_obs; p.spot = (typename WordOf<real>::type *)b->spot;
         p.envst = (EnvSt<real> *)b->envst; p.plan = (const PlanRec<real> *)b->plan; p.err = b->err;
-        p.diag = (real *)b->diag; p.last_ret = (real *)b->last_return;
+        p.diag = (real *)b->diag; p.last_ret = (real *)b->last_return; p.spot_power = (real *)b->spot_power;
         bound = true;
         return SNG_OK;
     }
@@ -478,13 +501,23 @@ public:
     {
         int rc = check_ready(false);
         if (rc) return rc;
-        SNG_CUDA(cudaSetDevice(device));
+        DeviceGuard guard(device);
         const bool first = !started;
         if (first && mask) { error = "sng_reset: the first reset must cover all envs (mask = NULL)"; return SNG_ERR_STATE; }
-        p.seed_lo = (uint32_t)seed;
-        p.seed_hi = (uint32_t)(seed >> 32);
-        p.mode = MODE_SAMPLE;
-        p.has_req = p.req_soc;
+        if (mask) {
+            // seed, sampling / replay mode and the requested-SoC plane rule belong to the whole handle: a masked
+            // reset must not change them under the envs it leaves alone
+            if (p.mode != MODE_SAMPLE) { error = "sng_reset: a masked reset needs sampling mode (the handle replays a loaded schedule)"; return SNG_ERR_STATE; }
+            if (p.seed_lo != (uint32_t)seed || p.seed_hi != (uint32_t)(seed >> 32)) {
+                error = "sng_reset: a masked reset cannot change the seed";
+                return SNG_ERR_STATE;
+            }
+        } else {
+            p.seed_lo = (uint32_t)seed;
+            p.seed_hi = (uint32_t)(seed >> 32);
+            p.mode = MODE_SAMPLE;
+            p.has_req = p.req_soc;
+        }
         rc = launch_reset(mask, first ? 1 : 0, 1, reset_battery, st);
         if (rc == SNG_OK) started = true;
         return rc;
@@ -500,7 +533,7 @@ public:
             return SNG_ERR_ARG;
         }
         if (!buf.plan) { error = "sng_load_schedule: no `plan` buffer bound"; return SNG_ERR_STATE; }
-        SNG_CUDA(cudaSetDevice(device));
+        DeviceGuard guard(device);
         const long long E = p.n_envs;
         const int N = p.N, V = v->n_slots;
         std::vector<PlanRec<real>> plan((size_t)E * N * kMaxVehicles);
@@ -675,7 +708,9 @@ public:
         } else {
             // specialised kernels: the station sizes BASELINE.json names, with the reference's observation
             // shape (PV on, 3 steps ahead: 8 disturbance entries); everything else runs the generic kernel
-            if (!use_generic && q.off_soc == 8) {
+            // (keyed on the flags themselves: PV off with 7 steps ahead also has 8 disturbance entries, but a
+            // different layout -- eight prices)
+            if (!use_generic && q.pv && q.H == 3) {
                 switch (q.N) {
                 case 4: return launch_step_n<4, 8>(q, actions, obs, reward, done, n_steps, bulk, st);
                 case 8: return launch_step_n<8, 8>(q, actions, obs, reward, done, n_steps, bulk, st);
@@ -693,6 +728,7 @@ public:
     {
         int rc = check_ready(true);
         if (rc) return rc;
+        DeviceGuard guard(device);
         return launch_step(p, p.actions, p.obs, p.reward, p.done, 1, st);
     }
 
@@ -701,6 +737,7 @@ public:
         int rc = check_ready(true);
         if (rc) return rc;
         if (!actions || !obs || !reward || !done || n_steps < 1) { error = "sng_rollout: bad arguments"; return SNG_ERR_ARG; }
+        DeviceGuard guard(device);
         return launch_step(p, (const real *)actions, obs, (real *)reward, done, n_steps, st);
     }
 
@@ -717,6 +754,7 @@ public:
         if (q.err) q.err += e0;
         if (q.diag) q.diag += (size_t)e0 * D_COUNT;
         if (q.last_ret) q.last_ret += e0;
+        if (q.spot_power) q.spot_power += (size_t)e0 * src.N;
         return q;
     }
     Params<real> slice_params(long long e0, long long n) const { return slice_of(p, e0, n); }
@@ -729,6 +767,7 @@ public:
         int rc = check_ready(true);
         if (rc) return rc;
         if (!a || !obs || !rew || !done) { error = "sng_step_host: null host buffer"; return SNG_ERR_ARG; }
+        DeviceGuard guard(device);
         const long long E = p.n_envs;
         int chunks = host_chunks > 0 ? host_chunks : (E >= (1 << 16) ? 8 : 1);
         long long per = ((E + chunks - 1) / chunks + 1023) / 1024 * 1024;      // multiple of 32 (and of the TMA slab alignment)
@@ -787,6 +826,7 @@ public:
         if (rc) return rc;
         if (!buf.plan) { error = "sng_sample_plan: no `plan` buffer bound"; return SNG_ERR_STATE; }
         if (p.mode != MODE_SAMPLE) { error = "sng_sample_plan: handle is in replay mode"; return SNG_ERR_STATE; }
+        DeviceGuard guard(device);
         sample_plan_kernel<real><<<grid_for(p.n_envs * p.N), 256, 0, st>>>(p, (PlanRec<real> *)buf.plan);
         ++launches;
         SNG_CUDA(cudaGetLastError());
@@ -800,6 +840,7 @@ public:
         if (!out) { error = "sng_error_flags: null output"; return SNG_ERR_ARG; }
         *out = 0;
         if (!buf.err) return SNG_OK;
+        DeviceGuard guard(device);
         SNG_CUDA(cudaMemsetAsync(d_flag, 0, sizeof(uint32_t), st));
         or_reduce_kernel<<<148, 256, 0, st>>>(buf.err, p.n_envs, d_flag);
         ++launches;

@@ -11,7 +11,10 @@
 // env; tensor cores would need TF32/BF16 inputs and change the numerics of a trainer expecting FP32).
 #include <cmath>
 #include <cstdint>
+#include <map>
+#include <mutex>
 #include <string>
+#include <utility>
 
 #include <cuda_runtime.h>
 
@@ -183,7 +186,34 @@ __global__ void __launch_bounds__(kThreads) policy_forward_kernel(const sng_mlp 
     }
 }
 
-thread_local std::string g_err;
+// The dynamic shared-memory opt-in is a per-function, per-DEVICE attribute: raise it once per (device, kernel).
+int ensure_smem(int device, const void *kern, size_t smem)
+{
+    static std::mutex mu;
+    static std::map<std::pair<int, const void *>, size_t> limit;
+    std::lock_guard<std::mutex> lock(mu);
+    size_t &cur = limit[std::make_pair(device, kern)];
+    if (smem <= cur) return SNG_OK;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return SNG_ERR_CUDA;
+    cur = smem;
+    return SNG_OK;
+}
+
+// Makes the device that owns `ptr` current for the lifetime of the guard (a process may drive several GPUs).
+struct PointerDeviceGuard {
+    int prev = -1, dev = -1;
+    bool switched = false;
+    explicit PointerDeviceGuard(const void *ptr)
+    {
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, ptr) == cudaSuccess && at.type == cudaMemoryTypeDevice) dev = at.device;
+        if (dev >= 0 && cudaGetDevice(&prev) == cudaSuccess && prev != dev) switched = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~PointerDeviceGuard()
+    {
+        if (switched) cudaSetDevice(prev);
+    }
+};
 
 template <int DP, int AP>
 int launch(const sng_mlp &m, const float *obs, const float *noise, const float *low, const float *high, float *raw,
@@ -192,13 +222,9 @@ int launch(const sng_mlp &m, const float *obs, const float *noise, const float *
     constexpr int NE = 2;      // envs per thread
     auto kern = policy_forward_kernel<DP, AP, NE>;
     const size_t smem = sizeof(float) * ((size_t)2 * (H * DP + H + H * H + H) + H * AP + AP + H * 4 + 4);
-    static size_t set = 0;
-    if (smem > set) {
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return SNG_ERR_CUDA;
-        set = smem;
-    }
     int dev = 0, sms = 148, per_sm = 1;
-    cudaGetDevice(&dev);
+    cudaGetDevice(&dev);                     // the caller (sng_policy_forward) made the buffers' device current
+    if (ensure_smem(dev, (const void *)kern, smem) != SNG_OK) return SNG_ERR_CUDA;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem);
     long long grid = (long long)sms * (per_sm > 0 ? per_sm : 1);
@@ -219,6 +245,7 @@ extern "C" int sng_policy_forward(const sng_mlp *mlp, const float *obs, const fl
     if (mlp->hidden != H || mlp->obs_dim < 1 || mlp->obs_dim > 32 || mlp->act_dim < 1 || mlp->act_dim > 16) return SNG_ERR_UNSUPPORTED;
     const int dp = (mlp->obs_dim + 3) / 4 * 4, ap = (mlp->act_dim + 3) / 4 * 4;
     cudaStream_t st = (cudaStream_t)stream;
+    PointerDeviceGuard guard(obs);
 #define SNG_POLICY_CASE(DP, AP) \
     if (dp == DP && ap == AP) return launch<DP, AP>(*mlp, obs, noise, low, high, raw_actions, actions, values, log_probs, n_envs, st);
     SNG_POLICY_CASE(20, 8)    // N = 4:  D = 17, A = 5

@@ -43,6 +43,48 @@ class MlpPolicy(nn.Module):
     def predict_values(self, obs: torch.Tensor) -> torch.Tensor:
         return self.value_net(self.vf(obs)).squeeze(-1)
 
+    # ---- Stable-Baselines3 checkpoints (what solvers/RL/ppo_train.py:100-102 saves, predictor.py:72 loads) ----
+    # SB3 ActorCriticPolicy.state_dict() key -> attribute path here; the mapping is 1:1 and lossless.
+    SB3_KEYS = {
+        "mlp_extractor.policy_net.0.weight": "pi.0.weight", "mlp_extractor.policy_net.0.bias": "pi.0.bias",
+        "mlp_extractor.policy_net.2.weight": "pi.2.weight", "mlp_extractor.policy_net.2.bias": "pi.2.bias",
+        "mlp_extractor.value_net.0.weight": "vf.0.weight", "mlp_extractor.value_net.0.bias": "vf.0.bias",
+        "mlp_extractor.value_net.2.weight": "vf.2.weight", "mlp_extractor.value_net.2.bias": "vf.2.bias",
+        "action_net.weight": "action_net.weight", "action_net.bias": "action_net.bias",
+        "value_net.weight": "value_net.weight", "value_net.bias": "value_net.bias", "log_std": "log_std",
+    }
+
+    @classmethod
+    def from_sb3_state_dict(cls, sd) -> "MlpPolicy":
+        """Build the policy from an SB3 `policy.pth` state dict (MlpPolicy, default net_arch, tanh)."""
+        missing = [k for k in cls.SB3_KEYS if k not in sd]
+        extra = [k for k in sd if k not in cls.SB3_KEYS]
+        if missing or extra:
+            raise ValueError("not a default SB3 MlpPolicy state dict: missing %s, unexpected %s" % (missing, extra))
+        w0 = sd["mlp_extractor.policy_net.0.weight"]
+        pol = cls(int(w0.shape[1]), int(sd["action_net.weight"].shape[0]), hidden=int(w0.shape[0]))
+        own = pol.state_dict()
+        mapped = {dst: torch.as_tensor(sd[src]).to(own[dst].dtype) for src, dst in cls.SB3_KEYS.items()}
+        for k, v in mapped.items():
+            if tuple(v.shape) != tuple(own[k].shape):
+                raise ValueError("shape of %s does not fit: %s vs %s" % (k, tuple(v.shape), tuple(own[k].shape)))
+        pol.load_state_dict(mapped, strict=True)
+        return pol
+
+    @classmethod
+    def from_sb3_zip(cls, path: str) -> "MlpPolicy":
+        """Load the policy of a Stable-Baselines3 PPO checkpoint (`model.save(...)` zip, e.g. the reference's
+        solvers/RL/models/PPO-b-pv-bounded-sparse-4ch-1h/999600.zip): reads `policy.pth` only."""
+        import io
+        import zipfile
+        with zipfile.ZipFile(path) as z:
+            sd = torch.load(io.BytesIO(z.read("policy.pth")), map_location="cpu", weights_only=True)
+        return cls.from_sb3_state_dict(sd)
+
+    def to_sb3_state_dict(self):
+        own = self.state_dict()
+        return {src: own[dst].detach().clone() for src, dst in self.SB3_KEYS.items()}
+
     # ---- fused inference (libsng.so: sng_policy_forward) ----------------------------------
     def _mlp_struct(self):
         """ctypes view of the parameters (rebuilt on every call: optimisers may replace .data)."""

@@ -2,9 +2,9 @@
 
 The reference appends 26 diagnostics per step (envs/smart_nanogrid_environment.py:143-171) and dumps
 them at every episode end (:239-309) for its plotting notebooks.  The CUDA step keeps only what enters
-the reward plus an optional 8-entry diagnostics row; `EpisodeRecorder` rebuilds the reference's series
-for ONE chosen env from that row, the observation and the decoded spot state, and writes the same
-JSON keys.  It is a debugging / notebook aid for single envs, not part of the hot path.
+the reward plus an optional 8-entry diagnostics row and the per-spot powers; `EpisodeRecorder` rebuilds the
+reference's series for ONE chosen env from those, the observation and the decoded spot state, and writes
+the same JSON keys.  It is a debugging / notebook aid for single envs, not part of the hot path.
 Series that the reference computes but never feeds into the reward and that are identically zero in
 its current code (needless-charging, overcharging, low-utilisation penalties: penaliser_old.py
 :34,53-56,100-104 are commented out) are written as zeros.
@@ -41,34 +41,21 @@ class EpisodeRecorder:
             "Battery_power_value", "Battery_SOC_below_DoD_penalties", "Insufficiently_charged_vehicle_penalties",
             "Battery_calculated_power_value", "DisCharging_nonexistent_vehicles_penalties")}
 
-    def _spot_powers(self, a, st):
-        """Per-spot power of this step from the pre-step state: Charger.charge_vehicle / discharge_vehicle
-        (utils/charger.py:58-140), float64 on the host."""
-        cfg, t, i = self.cfg, self.t, self.i
-        P = np.zeros(cfg.n_spots)
-        nonexistent = 0.0
-        for s in range(cfg.n_spots):
-            arr, dep, cap = int(st["arr"][i, s]), int(st["dep"][i, s]), float(st["cap"][i, s])
-            present = arr != 255 and arr <= t < dep
-            if not present:
-                nonexistent += 100.0 if a[s] != 0 else 0.0            # charger.py:146-156
-                continue
-            if a[s] > 0:
-                P[s] = a[s] * cfg.ev_max_power * cfg.ev_efficiency
-            elif a[s] < 0:
-                power = a[s] * cfg.ev_max_power * cfg.ev_efficiency
-                s_prev = float(st["soc"][i, s])
-                calc = s_prev + power * cfg.dt / cap
-                P[s] = -(s_prev * cap) / cfg.dt if calc >= 0 else power   # quirk Q1, charger.py:122-132
-        return P, nonexistent
+    def _nonexistent_penalty(self, a, st):
+        """100 per non-zero action sent to an empty spot (Charger.reset_info_values, utils/charger.py:146-156)."""
+        t, i = self.t, self.i
+        arr, dep = st["arr"][i], st["dep"][i]
+        present = (arr != 255) & (arr <= t) & (t < dep)
+        return 100.0 * float(np.count_nonzero(~present & (a != 0)))
 
     def step(self, actions: torch.Tensor):
         """env.step(actions) + one row of every series for env `index`."""
         env, cfg, i = self.env, self.cfg, self.i
         st = env.spot_state()
         a = actions[i].detach().double().cpu().numpy()
-        P, nonexistent = self._spot_powers(a[:cfg.n_spots], st)
+        nonexistent = self._nonexistent_penalty(a[:cfg.n_spots], st)
         out = env.step(actions)
+        P = env.spot_power[i].double().cpu().numpy()      # written by the step kernel itself
         obs, rew = out[0][i].cpu().numpy(), float(out[1][i])
         d = env.diag[i].double().cpu().numpy()
         D = {name: d[k] for k, name in enumerate(nat.DIAG)}
@@ -95,7 +82,10 @@ class EpisodeRecorder:
         S["Total_discharging_power"].append(float(D["total_dis"]))
         S["Charger_power_values"].append(P.tolist())
         S["Battery_power_value"].append(float(D["batt_power"]))
-        S["Battery_calculated_power_value"].append(float(D["batt_power"]))
+        # the reference records the power the action asked for, before the over-discharge limit
+        # (battery_energy_storage_system.py:49,79; 0 when the action is 0, :31-33)
+        a_b = float(a[cfg.n_spots]) if cfg.batt else 0.0
+        S["Battery_calculated_power_value"].append(a_b * cfg.bess_max_power * cfg.bess_efficiency if a_b != 0 else 0.0)
         S["DisCharging_nonexistent_vehicles_penalties"].append(nonexistent)
         self.t += 1
         return out

@@ -14,6 +14,9 @@ instead.  Everything written here is data produced by the unmodified reference c
   ref_c1_rbc_n10.npz          BASELINE config 1: N=10 default env driven by the RBC rule
   ref_c2_n10_e256.npz         BASELINE config 2 (first 256 of the 4,096 envs): uniform actions
   ref_return_stats.json       random-policy episode-return statistics (for the sampler tests)
+  sb3_ppo_4ch_policy.npz      the weights of the reference's shipped PPO checkpoint (policy.pth of
+                              solvers/RL/models/PPO-b-pv-bounded-sparse-4ch-1h/999600.zip), SB3 key names
+                              (`python tests/golden/generate_golden.py policy` regenerates only this one)
 """
 import json
 import os
@@ -223,9 +226,26 @@ def gen_return_stats():
         json.dump(stats, fp, indent=2)
 
 
+SHIPPED_CHECKPOINT = "solvers/RL/models/PPO-b-pv-bounded-sparse-4ch-1h/999600.zip"
+
+
+def gen_shipped_policy():
+    """The reference's trained policy (C3 "for N=4, the shipped checkpoint"): a data file of the
+    reference, stored as plain arrays because the zip cannot travel to the GPU box."""
+    import io
+    import zipfile
+    import torch
+    with zipfile.ZipFile(os.path.join(rl.REFERENCE_ROOT, SHIPPED_CHECKPOINT)) as z:
+        sd = torch.load(io.BytesIO(z.read("policy.pth")), map_location="cpu", weights_only=True)
+    np.savez_compressed(os.path.join(HERE, "sb3_ppo_4ch_policy.npz"), **{k: v.numpy() for k, v in sd.items()})
+
+
 if __name__ == "__main__":
     assert rl.reference_available(), "needs /root/reference"
     os.environ["PYTHONBREAKPOINT"] = "0"
+    if sys.argv[1:] == ["policy"]:
+        gen_shipped_policy()
+        sys.exit(0)
     random.seed(0)
     copy_recorded_episodes()
     gen_tables()
@@ -234,5 +254,6 @@ if __name__ == "__main__":
     gen_c1_rbc()
     gen_c2()
     gen_return_stats()
+    gen_shipped_policy()
     for f in sorted(os.listdir(HERE)):
         print("%9d  %s" % (os.path.getsize(os.path.join(HERE, f)), f))

@@ -59,3 +59,32 @@ def assert_close_f32(name, got, want, rtol=1e-5, atol=0.0, mask=None):
         idx = np.argwhere(bad)[0]
         raise AssertionError("%s: %d mismatches, first at %s: got %r want %r" %
                              (name, bad.sum(), tuple(idx), got[tuple(idx)], want[tuple(idx)]))
+
+
+def penalty_margin_table(ob: OracleBatch):
+    """Per vehicle, for the step the oracle is ABOUT to take: distance |s - 0.95 r| to the penalty threshold
+    (inf outside the check set) and the size of the jump ((r - s) * 10)^2 the penalty makes there."""
+    E, N, W = ob.soc.shape
+    col = np.where(ob.t == 0, W - 1, ob.t - 1).astype(np.int64)[:, None, None]
+    s = np.take_along_axis(ob.soc, col, axis=2)[:, :, 0]
+    r = np.take_along_axis(ob.req, col, axis=2)[:, :, 0]
+    d = np.abs(s - (r - ob.cfg.soc_margin_ratio * r))
+    live = ob.check.astype(bool) & (r > 0)
+    return np.where(live, d, np.inf), np.where(live, ((r - s) * 10.0) ** 2, 0.0)
+
+
+def assert_only_threshold_side_differs(name, got, want, dist, jump, near_tol=1e-5, rtol=1e-5, atol=1e-4):
+    """Env-steps masked as "near the penalty threshold" may differ from the oracle ONLY by the penalty jump of
+    some of their near-threshold vehicles (float32 landed on the other side of s = 0.95 r): |got - want| must be
+    a subset sum of those jumps."""
+    from itertools import combinations
+    got = np.asarray(got, np.float64)
+    want = np.asarray(want, np.float64)
+    for e in np.flatnonzero(dist.min(axis=1) < near_tol):
+        jumps = jump[e][dist[e] < near_tol]
+        delta = abs(got[e] - want[e])
+        tol = atol + rtol * abs(want[e])
+        sums = [0.0] + [sum(c) for k in range(1, len(jumps) + 1) for c in combinations(jumps.tolist(), k)]
+        if not any(abs(delta - x) <= tol for x in sums):
+            raise AssertionError("%s: env %d near the penalty threshold differs by %r, not by a jump of %r" %
+                                 (name, e, delta, jumps.tolist()))

@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_ctypes_mirrors_match_compiled_structs():
     L = nat.lib()
-    assert L.sng_abi_version() == 2
+    assert L.sng_abi_version() == 3
     for which, st in enumerate((nat.SngConfig, nat.SngLayout, nat.SngBuffers, nat.SngScheduleView)):
         assert L.sng_sizeof(which) == C.sizeof(st)
 

@@ -183,6 +183,8 @@ def test_config2_sampled_episodes_with_auto_reset(precision, n_envs):
     dict(number_of_chargers=10, hours_ahead=5),                                   # forecast horizon
     dict(number_of_chargers=6, hours_ahead=1, pv_system_available_in_model=False, price_model=2),
     dict(number_of_chargers=32, time_interval="30min", price_model=4, vehicle_uncharged_penalty_mode="dense"),
+    # PV off with 7 steps ahead has 8 disturbance entries like the reference's shape, but they are 8 prices
+    dict(number_of_chargers=10, pv_system_available_in_model=False, hours_ahead=7),
 ])
 @pytest.mark.parametrize("precision", ["float32", "float64"])
 def test_variants_sampled_vs_oracle(kw, precision):

@@ -167,3 +167,54 @@ def test_fused_policy_kernel_matches_torch_modules(n_spots, obs_dim, act_dim):
     with torch.no_grad():
         mean_ref, _, lp0_ref = policy(obs, None)
     assert torch.allclose(raw_d, mean_ref, rtol=1e-4, atol=2e-5) and torch.allclose(lp_d, lp0_ref, rtol=1e-5, atol=1e-4)
+
+
+def test_shipped_sb3_policy_on_the_recorded_episode():
+    """the reference's shipped PPO checkpoint (tests/golden/sb3_ppo_4ch_policy.npz) drives the
+    N = 4 station: on the observations of the reference's recorded episode G1 the fused kernel's deterministic
+    actions and values equal the torch forward of the same weights, and a whole rollout runs with it."""
+    import json
+    import os
+    from smart_nanogrid_gym_b200 import BatchedSmartNanogridEnv, load_initial_values_json
+    from smart_nanogrid_gym_b200.rollout import GraphedRollout, MlpPolicy, RolloutBuffer
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    z = np.load(os.path.join(gold, "sb3_ppo_4ch_policy.npz"))
+    policy = MlpPolicy.from_sb3_state_dict({k: torch.tensor(z[k]) for k in z.files}).to("cuda:0")
+    assert policy.fused_supported()
+    kw = dict(KW, number_of_chargers=4)
+    # G1's observations: replay the recorded schedule and actions
+    rec = load_initial_values_json(os.path.join(gold, "g1_initial_values.json"))
+    with open(os.path.join(gold, "g1_prediction_results.json")) as fp:
+        p = json.load(fp)
+    env = BatchedSmartNanogridEnv(1, auto_reset=False, **kw)
+    obs = [env.load_schedule(rec, pv_shift=0.02, soc_b=p["Initial_battery_state_of_charge"]).clone()]
+    for t in range(23):
+        a = torch.tensor([p["Charger_actions"][t] + [p["Battery_action"][t]]], device="cuda:0", dtype=torch.float32)
+        obs.append(env.step(a)[0].clone())
+    env.close()
+    obs = torch.cat(obs)                                                       # [24, 17]
+    low = torch.tensor([0., 0, 0, 0, -1], device="cuda:0")
+    high = torch.ones(5, device="cuda:0")
+    raw, act = torch.empty(24, 5, device="cuda:0"), torch.empty(24, 5, device="cuda:0")
+    val, lp = torch.empty(24, device="cuda:0"), torch.empty(24, device="cuda:0")
+    policy.fused_forward(obs, None, low, high, raw, act, val, lp)
+    with torch.no_grad():
+        mean_ref, v_ref, _ = policy(obs, None)
+    assert torch.allclose(raw, mean_ref, rtol=1e-4, atol=2e-5) and torch.allclose(val, v_ref, rtol=1e-4, atol=1e-4)
+    assert torch.equal(act, torch.minimum(torch.maximum(raw, low), high))
+    # the trained policy charges: its clipped actions are not all at the lower bound on this episode
+    assert (act[:, :4] > 0).any()
+    # ... and collects rollouts over a batch
+    E = 4096
+    env = BatchedSmartNanogridEnv(E, seed=2, **kw)
+    buf = RolloutBuffer(24, E, 17, 5, "cuda:0")
+    o = env.reset()
+    collect = GraphedRollout(env, policy, buf, deterministic=True)
+    collect(o, torch.ones(E, dtype=torch.uint8, device="cuda:0"))
+    torch.cuda.synchronize()
+    random_policy_return = -173.3                                              # tests/golden/ref_return_stats.json, N = 4
+    ret = buf.rewards.sum(0).mean().item()
+    # the trained policy beats random actions by far: -54.8 +- 16.5 per episode with the float64 oracle in the loop
+    assert -70 < ret < -40 and ret > random_policy_return
+    assert env.error_flags() == 0
+    env.close()
