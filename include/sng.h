@@ -212,6 +212,17 @@ int sng_policy_forward(const sng_mlp *mlp, const float *obs, const float *noise,
                        float *raw_actions, float *actions, float *values, float *log_probs, int64_t n_envs,
                        void *stream);
 
+/* The same forward pass on the 5th-generation tensor cores (tcgen05.mma, activations in tensor memory, FP32 kept
+ * by a 3-term tf32 split; sng_policy_tc.cu): the production path of rollout collection.  The weights are split and
+ * laid out for the tensor cores once per weight update by sng_policy_pack into a caller-owned device buffer of
+ * sng_policy_packed_bytes() bytes (16-byte aligned); sng_policy_forward_packed then takes that image instead of the
+ * nn.Linear tensors.  Arguments otherwise as for sng_policy_forward; obs_dim <= 30, act_dim <= 16, hidden = 64. */
+size_t sng_policy_packed_bytes(void);
+int sng_policy_pack(const sng_mlp *mlp, void *packed, void *stream);
+int sng_policy_forward_packed(const void *packed, int obs_dim, int act_dim, const float *obs, const float *noise,
+                              const float *low, const float *high, float *raw_actions, float *actions, float *values,
+                              float *log_probs, int64_t n_envs, void *stream);
+
 /* Launches an EMPTY kernel on `stream`: lets a caller measure the device's kernel-to-kernel launch latency (the
  * floor under one sng_step per step for batches that live in L2; bench.py reports it beside those numbers). */
 int sng_null_launch(void *stream);

@@ -99,19 +99,51 @@ class MlpPolicy(nn.Module):
         return m
 
     def fused_supported(self) -> bool:
+        """The tensor-core kernel (sng_policy_forward_packed) takes any observation width up to 30 and action width up
+        to 16 with SB3's hidden width of 64."""
         p = self.pi[0].weight
         return (p.is_cuda and p.dtype == torch.float32 and self.pi[0].out_features == 64 and
-                (self.pi[0].in_features, self.action_net.out_features) in ((17, 5), (25, 9), (29, 11)))
+                self.pi[0].in_features <= 30 and self.action_net.out_features <= 16)
+
+    def cuda_core_supported(self) -> bool:
+        """Shapes of the FP32 CUDA-core kernel (sng_policy_forward), kept as an independent second implementation."""
+        return self.fused_supported() and (self.pi[0].in_features, self.action_net.out_features) in ((17, 5), (25, 9), (29, 11))
+
+    def fused_kind(self) -> str:
+        return "tcgen05 tf32x3, activations in TMEM"
 
     @torch.no_grad()
-    def fused_forward(self, obs, noise, low, high, raw_actions, actions, values, log_probs):
-        """One launch: values, sampled + clipped actions and log-probs written into the given [E, ...] buffers
-        (noise None = deterministic; actions None = values only).  Inference only (no autograd graph)."""
-        p = lambda t: None if t is None else C.c_void_p(t.data_ptr())  # noqa: E731
+    def pack_weights(self):
+        """Split the FP32 weights into tf32 hi / lo parts in the tensor cores' operand layout (sng_policy_pack: one
+        tiny launch).  Call after every weight update; collect_rollout does it once per rollout."""
+        lib = nat.lib()
+        dev = self.pi[0].weight.device
+        if getattr(self, "_packed", None) is None or self._packed.device != dev:
+            self._packed = torch.empty(lib.sng_policy_packed_bytes() // 4, dtype=torch.float32, device=dev)
         m = self._mlp_struct()
+        stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        nat.check(lib.sng_policy_pack(C.byref(m), C.c_void_p(self._packed.data_ptr()), stream))
+        return self._packed
+
+    @torch.no_grad()
+    def fused_forward(self, obs, noise, low, high, raw_actions, actions, values, log_probs, repack: bool = True,
+                      cuda_cores: bool = False):
+        """One launch: values, sampled + clipped actions and log-probs written into the given [E, ...] buffers
+        (noise None = deterministic; actions None = values only).  Inference only (no autograd graph).
+        repack=False reuses the weight image of the last pack_weights() (weights unchanged since);
+        cuda_cores=True runs the FP32 CUDA-core kernel instead of the tensor-core one."""
+        p = lambda t: None if t is None else C.c_void_p(t.data_ptr())  # noqa: E731
         stream = C.c_void_p(torch.cuda.current_stream(obs.device).cuda_stream)
-        nat.check(nat.lib().sng_policy_forward(C.byref(m), p(obs), p(noise), p(low), p(high), p(raw_actions), p(actions),
-                                               p(values), p(log_probs), obs.shape[0], stream))
+        if cuda_cores:
+            m = self._mlp_struct()
+            nat.check(nat.lib().sng_policy_forward(C.byref(m), p(obs), p(noise), p(low), p(high), p(raw_actions), p(actions),
+                                                   p(values), p(log_probs), obs.shape[0], stream))
+            return
+        if repack or getattr(self, "_packed", None) is None:
+            self.pack_weights()
+        nat.check(nat.lib().sng_policy_forward_packed(p(self._packed), self.pi[0].in_features, self.action_net.out_features,
+                                                      p(obs), p(noise), p(low), p(high), p(raw_actions), p(actions),
+                                                      p(values), p(log_probs), obs.shape[0], stream))
 
 
 class RolloutBuffer:
@@ -156,11 +188,13 @@ def collect_rollout(env, policy: MlpPolicy, buf: RolloutBuffer, obs: torch.Tenso
     buf.observations[0].copy_(obs)
     starts = episode_starts.to(torch.uint8)
     fused = fused and policy.fused_supported()
+    if fused:
+        policy.pack_weights()          # once per rollout: the weights do not change while it is collected
     for s in range(buf.n_steps):
         o = buf.observations[s]
         noise = None if deterministic else torch.randn(buf.n_envs, buf.actions.shape[2], device=o.device, generator=generator)
         if fused:      # one kernel: both networks, heads, sampling, clipping, log-probs, straight into the buffer slabs
-            policy.fused_forward(o, noise, low, high, buf.raw_actions[s], buf.actions[s], buf.values[s], buf.log_probs[s])
+            policy.fused_forward(o, noise, low, high, buf.raw_actions[s], buf.actions[s], buf.values[s], buf.log_probs[s], repack=False)
         else:
             a, v, lp = policy(o, noise)
             buf.raw_actions[s].copy_(a)
@@ -173,7 +207,7 @@ def collect_rollout(env, policy: MlpPolicy, buf: RolloutBuffer, obs: torch.Tenso
         starts = buf.dones[s]
     last_obs = buf.observations[buf.n_steps]
     if fused:
-        policy.fused_forward(last_obs, None, None, None, None, None, buf.last_values, None)
+        policy.fused_forward(last_obs, None, None, None, None, None, buf.last_values, None, repack=False)
     else:
         buf.last_values.copy_(policy.predict_values(last_obs))
     buf.compute_returns_and_advantage(buf.last_values, buf.dones[buf.n_steps - 1])
