@@ -56,13 +56,22 @@ def run(obs_dim, act_dim, E, seed=0, time_it=False):
                 continue
             raw, act, val, lp = out[kind]
             f = lambda: policy.fused_forward(obs, noise, low, high, raw, act, val, lp, repack=False, cuda_cores=kind == "cc")  # noqa: E731
-            for _ in range(5):
-                f()
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(5):
+                    f()
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()            # replayed from a graph: the host's launch cost stays out of the number
+            with torch.cuda.graph(graph):
+                for _ in range(20):
+                    f()
+            graph.replay()
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             torch.cuda.synchronize()
             ev0.record()
-            for _ in range(200):
-                f()
+            for _ in range(10):
+                graph.replay()
             ev1.record()
             torch.cuda.synchronize()
             us = 1e3 * ev0.elapsed_time(ev1) / 200

@@ -33,13 +33,15 @@
 
 namespace {
 using namespace sng;
+long long *g_trace = nullptr;      // debugging aid: sng_policy_debug_trace
 
 constexpr int H = 64;        // hidden width of SB3's default MlpPolicy
 constexpr int KP = 32;       // observation width padded to the K of layer 0 (obs_dim <= 30; columns 30, 31 = 1.0)
 constexpr int NH = 16;       // head width padded to the smallest N of an M = 128 MMA
 constexpr int TILE = 128;    // envs per tile = MMA M = TMEM lanes
-constexpr int GROUPS = 2;    // tiles in flight per CTA
-constexpr int THREADS = GROUPS * TILE;
+constexpr int CB = 4;        // warps per 32 TMEM lanes: each takes 64 / CB of a layer's columns in the epilogues
+constexpr int THREADS = CB * TILE;   // compute threads (16 warps); one more warp issues the MMAs
+constexpr float kTanhScale = 2.8853900817779268f;   // 2 log2(e), folded into the hidden layers' weights and biases
 
 // ---- packed weight image (floats), per network ----
 constexpr int OFF_W0HI = 0;
@@ -56,8 +58,9 @@ constexpr int IMG_FLOATS = OFF_STD + 32;
 constexpr uint32_t IMG_SMEM_BYTES = 2u * NET_FLOATS * sizeof(float);   // the part staged in shared memory
 static_assert(IMG_SMEM_BYTES % 16 == 0, "bulk copies move multiples of 16 bytes");
 
-// TMEM columns of one group (256 of the SM's 512)
-constexpr uint32_t C_XHI = 0, C_XLO = 32, C_P = 64, C_Q = 128, C_S = 192, GROUP_COLS = 256;
+// TMEM columns (all 512 of the SM): two X buffers (tile i and tile i + 1), and per network P | Q | S
+constexpr uint32_t C_X0 = 0, C_X1 = 448, C_NET0 = 64, C_NETSTRIDE = 192, C_P = 0, C_Q = 64, C_S = 128;
+__device__ __forceinline__ uint32_t x_cols(int buf) { return buf ? C_X1 : C_X0; }      // hi at +0, lo at +32
 
 __device__ __forceinline__ uint32_t tf32_rna(float x)
 {
@@ -98,16 +101,16 @@ __global__ void __launch_bounds__(256) policy_pack_kernel(const sng_mlp m, float
             const int q = r < OFF_W0LO ? r : r - OFF_W0LO;
             lo = r >= OFF_W0LO;
             const int kc = q / (H * 4), n = (q / 4) % H, k = kc * 4 + (q & 3);
-            v = k < D ? w0[n * D + k] : (k == KP - 2 ? b0[n] : 0.f);
+            v = kTanhScale * (k < D ? w0[n * D + k] : (k == KP - 2 ? b0[n] : 0.f));
         } else if (r < OFF_B1) {                     // layer 1: [64][64]
             const int q = r < OFF_W1LO ? r - OFF_W1HI : r - OFF_W1LO;
             lo = r >= OFF_W1LO;
             const int kc = q / (H * 4), n = (q / 4) % H, k = kc * 4 + (q & 3);
-            v = w1[n * H + k];
+            v = kTanhScale * w1[n * H + k];
         } else if (r < OFF_WHHI) {                   // bias step of layer 1: k = 6 -> hi(b1), k = 7 -> lo(b1)
             const int q = r - OFF_B1;
             const int kc = q / (H * 4), n = (q / 4) % H, k = kc * 4 + (q & 3);
-            v = (k >= 6) ? b1[n] : 0.f;
+            v = (k >= 6) ? kTanhScale * b1[n] : 0.f;
             lo = k == 7;
             if (k < 6) { img[idx] = 0.f; continue; }
         } else if (r < OFF_BH) {                     // head: [16][64]
@@ -175,6 +178,26 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32
         : "memory");
 }
 
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16])
+{
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+        SNG_W8(v, 0), SNG_W8(v, 8)
+        : "memory");
+}
+
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8])
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), SNG_W8(v, 0) : "memory");
+}
+__device__ __forceinline__ uint32_t tmem_ld1(uint32_t taddr)
+{
+    uint32_t v;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(taddr) : "memory");
+    return v;
+}
+
 // Shared-memory matrix descriptor of a K-major [N][8] tf32 slice in the canonical no-swizzle layout: start address,
 // leading-dimension byte offset (between the two 16-byte K chunks) = N * 16, stride byte offset (between 8-row
 // groups) = 128, descriptor version 1 (sm_100), no swizzle.  All fields in 16-byte units.
@@ -187,269 +210,388 @@ __device__ __forceinline__ uint64_t b_desc(uint32_t smem_addr, uint32_t n_rows)
 // Instruction descriptor: D = F32, A = B = TF32, both K-major, M = 128, N = n.
 __host__ __device__ constexpr uint32_t i_desc(uint32_t n) { return (1u << 4) | (2u << 7) | (2u << 10) | ((n >> 3) << 17) | ((128u >> 4) << 24); }
 
-// D[tmem] (+)= A[tmem] * B[smem]^T, one K = 8 step; issued by ONE thread for the whole 128-row tile
-__device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+// D[tmem] (+)= A[tmem] * B[smem]^T, one K = 8 step.  Executed by a WHOLE warp with warp-uniform operands; the elected
+// lane (`elected` != 0 in exactly one lane) issues it for the 128-row tile.  (Issued from divergent code -- if (t == 0) --
+// the compiler wraps every UTCHMMA in an election loop: ~45 cycles per MMA, more than an N = 64 MMA takes to execute.)
+__device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate,
+                                            uint32_t elected)
 {
     asm volatile(
-        "{\n\t.reg .pred p;\n\t"
+        "{\n\t.reg .pred p, q;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
-        "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        "setp.ne.b32 q, %5, 0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(elected)
         : "memory");
 }
+__device__ __forceinline__ uint32_t elect_one()
+{
+    uint32_t el;
+    asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\tselp.u32 %0, 1, 0, q;\n\t}" : "=r"(el));
+    return el;
+}
 // arrives on the mbarrier when every MMA issued so far by this thread has completed (implies fence::before_thread_sync)
-__device__ __forceinline__ void mma_commit(uint64_t *bar)
+__device__ __forceinline__ void mma_commit(uint32_t bar_smem_addr, uint32_t elected)
 {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar_smem_addr), "r"(elected) : "memory");
 }
 
-// One layer: D = (A_hi + A_lo) * (W_hi + W_lo)^T without the lo * lo term [+ the bias step], K = 8 * ksteps.
+// One layer: D = (A_hi + A_lo) * (W_hi + W_lo)^T without the lo * lo term [+ the bias step], K = 8 * KSTEPS, N columns.
 // w_hi / w_lo / bias: shared-memory byte addresses of the canonical [K/4][N][4] images (bias = 0: none).
-__device__ __forceinline__ void issue_layer(uint32_t d, uint32_t a_hi, uint32_t a_lo, uint32_t w_hi, uint32_t w_lo, int ksteps,
-                                            uint32_t n, uint32_t x_ones, uint32_t bias)
+template <int KSTEPS, int N>
+__device__ __forceinline__ void issue_layer(uint32_t d, uint32_t a_hi, uint32_t a_lo, uint32_t w_hi, uint32_t w_lo, uint32_t x_ones,
+                                            uint32_t bias, uint32_t elected)
 {
-    const uint32_t idesc = i_desc(n);
-    const uint32_t kbytes = 2u * n * 16u;            // one K = 8 step = two 16-byte chunk planes
-#pragma unroll 1
-    for (int s = 0; s < ksteps; ++s) {
-        const uint64_t dh = b_desc(w_hi + s * kbytes, n), dl = b_desc(w_lo + s * kbytes, n);
-        mma_tf32_ts(d, a_hi + 8u * s, dh, idesc, s > 0 ? 1u : 0u);
-        mma_tf32_ts(d, a_lo + 8u * s, dh, idesc, 1u);
-        mma_tf32_ts(d, a_hi + 8u * s, dl, idesc, 1u);
+    constexpr uint32_t idesc = i_desc(N);
+    constexpr uint32_t kstep16 = 2u * N;             // one K = 8 step = two 16-byte chunk planes of N rows, in 16-byte units
+    const uint64_t dh0 = b_desc(w_hi, N), dl0 = b_desc(w_lo, N);
+#pragma unroll
+    for (int s = 0; s < KSTEPS; ++s) {
+        const uint64_t dh = dh0 + (uint64_t)(s * kstep16), dl = dl0 + (uint64_t)(s * kstep16);
+        mma_tf32_ts(d, a_hi + 8u * s, dh, idesc, s > 0 ? 1u : 0u, elected);
+        mma_tf32_ts(d, a_lo + 8u * s, dh, idesc, 1u, elected);
+        mma_tf32_ts(d, a_hi + 8u * s, dl, idesc, 1u, elected);
     }
-    if (bias) mma_tf32_ts(d, x_ones, b_desc(bias, n), idesc, 1u);
+    if (bias) mma_tf32_ts(d, x_ones, b_desc(bias, N), idesc, 1u, elected);
 }
 
-// tanh(x) = 1 - 2 / (exp(2x) + 1) on the special-function unit (EX2 + RCP): absolute error ~1e-7, saturates correctly
-__device__ __forceinline__ float fast_tanh(float x)
+// tanh of a PAIR of pre-activations and the tf32 split of the results.  The pack kernel scales the hidden layers' weights and
+// biases by 2 log2(e), so the accumulator holds u = 2 log2(e) x and tanh(x) = 1 - 2 / (2^u + 1):
+//   one MUFU.EX2 per element; the reciprocal is computed on the FMA pipe (magic-constant seed, 5 % error, one cubic and one
+//   quadratic Newton step: 8e-8) with Blackwell's packed FP32 pairs (FFMA2) -- with EX2 + RCP the epilogue is bound by the
+//   16-lane special-function unit (2 x 8 cycles per warp and element).  |error| < 3e-7 absolute.
+__device__ __forceinline__ void tanh2_split(uint32_t &a, uint32_t &b, uint32_t &lo_a, uint32_t &lo_b)
 {
-    float e, r;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 2.8853900817779268f));
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.0f));
-    return fmaf(-2.0f, r, 1.0f);
+    float e0, e1;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(fminf(__uint_as_float(a), 26.0f)));   // 2^26 + 1: tanh = 1 - 3e-8
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(fminf(__uint_as_float(b), 26.0f)));
+    const float2 one = make_float2(1.0f, 1.0f);
+    const float2 nd = __ffma2_rn(make_float2(e0, e1), make_float2(-1.0f, -1.0f), make_float2(-1.0f, -1.0f));   // -(e + 1)
+    // 1 / d seed: bits(r0) = 0x7EF311C7 - bits(d); with the sign bit of -d folded into the constant
+    float2 r = make_float2(__uint_as_float(0xFEF311C7u - __float_as_uint(nd.x)), __uint_as_float(0xFEF311C7u - __float_as_uint(nd.y)));
+    float2 err = __ffma2_rn(nd, r, one);                 // 1 - d r
+    r = __ffma2_rn(r, __ffma2_rn(err, err, err), r);     // cubic step: r (1 + err + err^2)
+    err = __ffma2_rn(nd, r, one);
+    r = __ffma2_rn(r, err, r);                           // quadratic step
+    const float2 y = __ffma2_rn(r, make_float2(-2.0f, -2.0f), one);
+    const uint32_t ha = __float_as_uint(y.x) & 0xFFFFE000u, hb = __float_as_uint(y.y) & 0xFFFFE000u;   // tf32 by truncation: lo < 2^-10 |y|
+    const float2 l = __fadd2_rn(y, make_float2(-__uint_as_float(ha), -__uint_as_float(hb)));
+    a = ha; b = hb;
+    lo_a = __float_as_uint(l.x); lo_b = __float_as_uint(l.y);
 }
 
-__device__ __forceinline__ void group_barrier(int g) { asm volatile("bar.sync %0, %1;" ::"r"(1 + g), "r"(TILE) : "memory"); }
+__device__ __forceinline__ void compute_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(THREADS) : "memory"); }
 
-// hidden-layer epilogue: accumulator columns [src, src + 64) -> tanh -> hi part written back in place (it becomes
-// the A operand of the next layer), lo part to [dst_lo, dst_lo + 64)
+// hidden-layer epilogue of one warp: 16 accumulator columns [src, src + 16) of its 32 lanes -> tanh -> hi part written back
+// in place (it becomes the A operand of the next layer), lo part to [dst_lo, dst_lo + 16)
 __device__ __forceinline__ void tanh_epilogue(uint32_t src, uint32_t dst_lo)
 {
-    __syncwarp();                      // the .sync.aligned TMEM accesses below need the whole warp (lane 0 issued the MMAs)
+    __syncwarp();                      // the .sync.aligned TMEM accesses below need the whole warp
+    uint32_t v[16], w[16];
+    tmem_ld16(src, v);
+    tmem_wait_ld();
 #pragma unroll
-    for (int c = 0; c < H; c += 32) {
-        uint32_t v[32], w[32];
-        tmem_ld32(src + c, v);
-        tmem_wait_ld();
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            split_tf32(fast_tanh(__uint_as_float(v[j])), v[j], w[j]);
-        }
-        tmem_st32(src + c, v);
-        tmem_st32(dst_lo + c, w);
-    }
+    for (int j = 0; j < 16; j += 2) tanh2_split(v[j], v[j + 1], w[j], w[j + 1]);
+    tmem_st16(src, v);
+    tmem_st16(dst_lo, w);
     tmem_wait_st();
 }
 
 struct Smem {
     // byte offsets into dynamic shared memory
-    uint32_t obs_stage, row_stage, group_bytes, bars;
+    uint32_t obs_stage, row_stage, stages, bars;
 };
 __host__ __device__ inline Smem smem_plan(int D, int A)
 {
     Smem s;
     s.obs_stage = align128((uint32_t)(TILE * D * sizeof(float)));
     s.row_stage = align128((uint32_t)(TILE * A * sizeof(float)));
-    s.group_bytes = s.obs_stage + 3 * s.row_stage;                      // obs | noise | raw actions | clipped actions
-    s.bars = align128(IMG_SMEM_BYTES) + GROUPS * s.group_bytes;
+    s.stages = align128(IMG_SMEM_BYTES);                                // obs x 2 | noise | raw actions | clipped actions
+    s.bars = s.stages + 2 * s.obs_stage + 3 * s.row_stage;
     return s;
 }
 
-__global__ void __launch_bounds__(THREADS, 1)
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// Layer `phase` (0: layer 0, X -> P;  1: layer 1, (P, Q) -> S;  2: head, (S, Q) -> `head_out`) of the network whose TMEM
+// columns start at `tn` and whose weight image starts at shared-memory address `wn`; executed by the whole issuer warp
+// with warp-uniform arguments.  `x` = columns of the tile's X buffer.
+__device__ __forceinline__ void issue_phase(int phase, uint32_t tn, uint32_t x, uint32_t head_out, uint32_t wn, uint32_t done_bar)
+{
+    tc_fence_after();
+    const uint32_t elected = elect_one();     // taken right here: ptxas then knows the predicate holds in ONE lane
+    if (phase == 0)
+        issue_layer<KP / 8, H>(tn + C_P, x, x + 32, wn + OFF_W0HI * 4, wn + OFF_W0LO * 4, 0, 0, elected);
+    else if (phase == 1)
+        issue_layer<H / 8, H>(tn + C_S, tn + C_P, tn + C_Q, wn + OFF_W1HI * 4, wn + OFF_W1LO * 4, x + (KP - 8), wn + OFF_B1 * 4, elected);
+    else
+        issue_layer<H / 8, NH>(head_out, tn + C_S, tn + C_Q, wn + OFF_WHHI * 4, wn + OFF_WHLO * 4, x + (KP - 8), wn + OFF_BH * 4, elected);
+    mma_commit(done_bar, elected);
+    __syncwarp();
+}
+
+// ------------------------------------------------------------------------------------------
+// The forward kernel.  One CTA per SM, persistent over tiles of 128 envs.
+//   warps 0..15  compute: warp w owns TMEM lanes 32 (w % 4) .. + 31 (the envs of those rows) and column block w / 4
+//                (16 of a layer's 64 columns) in the epilogues -- four warps per scheduler partition, which is what the
+//                tanh epilogue needs to hide its dependent FMA chains;
+//   warp 16      issues every tcgen05.mma (one elected lane), in the order the operands become ready.
+// Critic and actor are two independent chains of  MMA -> tanh epilogue -> MMA -> ...; the compute warps alternate
+// between them, so while they run the epilogue of one network the tensor pipe runs the layer of the other:
+//     tensor pipe   c0 a0 | c1      | a1      | ch      | ah  c0' a0' | ...
+//     compute             | E(c0)   | E(a0)   | E(c1)   | E(a1)  X'   | value, actions | E(c0') ...
+// (c0 = critic layer 0, ch = critic head, ' = next tile).  The next tile's X is converted into the other X buffer while
+// the heads run, so the pipeline never drains between tiles.  Synchronisation: `rbar` (512 arrivals: "operands of the
+// next layer are in TMEM") compute -> issuer, `mbar[net]` (tcgen05.commit) issuer -> compute.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(THREADS + 32, 1)
     policy_tc_kernel(const float *__restrict__ img, const float *__restrict__ obs, const float *__restrict__ noise,
                      const float *__restrict__ low, const float *__restrict__ high, float *raw_actions, float *actions,
-                     float *values, float *log_probs, long long n_envs, int D, int A, int aligned)
+                     float *values, float *log_probs, long long n_envs, int D, int A, int aligned, long long *trace)
 {
+    int tr = 0;
+#define TRACE() do { if (trace && blockIdx.x == 0 && threadIdx.x == 0 && tr < 64) trace[tr++] = clock64(); } while (0)
+    if (trace && blockIdx.x == 0 && threadIdx.x == 0) trace[255] = clock64();
     extern __shared__ __align__(128) unsigned char smem[];
     const Smem sp = smem_plan(D, A);
-    const int g = threadIdx.x / TILE, t = threadIdx.x % TILE, warp = threadIdx.x >> 5;
-    unsigned char *gbase = smem + align128(IMG_SMEM_BYTES) + (size_t)g * sp.group_bytes;
-    float *obs_s = reinterpret_cast<float *>(gbase);
-    float *noise_s = reinterpret_cast<float *>(gbase + sp.obs_stage);
-    float *raw_s = reinterpret_cast<float *>(gbase + sp.obs_stage + sp.row_stage);
-    float *act_s = reinterpret_cast<float *>(gbase + sp.obs_stage + 2 * sp.row_stage);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool issuer = warp == THREADS / 32;
+    const int cb = warp >> 2;                               // column block of this warp in the epilogues
+    const int t = (warp & 3) * 32 + lane;                   // row of the tile = TMEM lane = env
+    float *obs_s0 = reinterpret_cast<float *>(smem + sp.stages);
+    float *noise_s = reinterpret_cast<float *>(smem + sp.stages + 2 * sp.obs_stage);
+    float *raw_s = reinterpret_cast<float *>(smem + sp.stages + 2 * sp.obs_stage + sp.row_stage);
+    float *act_s = reinterpret_cast<float *>(smem + sp.stages + 2 * sp.obs_stage + 2 * sp.row_stage);
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + sp.bars);
-    uint64_t *wbar = bars;                                  // the weight image has landed
-    uint64_t *obar = bars + 1 + 3 * g, *nbar = obar + 1, *mbar = obar + 2;   // obs rows | noise rows | MMAs of this group
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 1 + 3 * GROUPS);
+    uint64_t *wbar = bars;                                  // [3] weight image: critic layer 0 | rest of the critic | actor
+    uint64_t *obar = bars + 3;                              // [2] observation rows of the even / odd tiles have landed
+    uint64_t *nbar = bars + 5;                              // noise rows have landed
+    // compute -> issuer, 512 arrivals each: X of a tile is in TMEM | tanh(critic layer) is | tanh(actor layer) is.
+    // (One barrier per chain: a thread's next wait after arriving on a chain's barrier depends on that very phase, so a fast
+    //  warp can never arrive twice in one phase and complete it on behalf of a slow one.)
+    uint64_t *xbar = bars + 6, *rbar = bars + 7;            // rbar[2]: critic, actor
+    uint64_t *mbar = bars + 9;                              // [2] issuer -> compute: the critic's / the actor's layer is complete
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 11);
     const bool value_only = actions == nullptr;
+    const int n_nets = value_only ? 1 : 2;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < 1 + 3 * GROUPS; ++i) mbar_init(bars + i, 1);
+        for (int i = 0; i < 11; ++i) mbar_init(bars + i, (i >= 6 && i <= 8) ? THREADS : 1);
         fence_mbar_init();
-        // the weight image: one copy per CTA, shared by both groups
-        mbar_expect_tx(wbar, IMG_SMEM_BYTES);
-        for (uint32_t off = 0; off < IMG_SMEM_BYTES; off += 16384u) {
-            const uint32_t n = IMG_SMEM_BYTES - off < 16384u ? IMG_SMEM_BYTES - off : 16384u;
-            bulk_g2s(smem + off, reinterpret_cast<const unsigned char *>(img) + off, n, wbar);
+        // the weight image: one copy per CTA, in three pieces in the order they are needed (the first tile's critic
+        // layer 0 starts as soon as its 16 KB have landed)
+        const uint32_t cut[4] = {0u, (uint32_t)(OFF_W1HI * sizeof(float)), (uint32_t)(NET_FLOATS * sizeof(float)), IMG_SMEM_BYTES};
+        for (int piece = 0; piece < 3; ++piece) {
+            mbar_expect_tx(wbar + piece, cut[piece + 1] - cut[piece]);
+            for (uint32_t off = cut[piece]; off < cut[piece + 1]; off += 16384u) {
+                const uint32_t n = cut[piece + 1] - off < 16384u ? cut[piece + 1] - off : 16384u;
+                bulk_g2s(smem + off, reinterpret_cast<const unsigned char *>(img) + off, n, wbar + piece);
+            }
         }
     }
     if (warp == 0) tmem_alloc(tmem_slot, 512);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem = *tmem_slot + g * GROUP_COLS;                  // this group's columns, lane 0
-    const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16);   // ... as seen by this warp's 32 lanes
-    const uint32_t w_base = smem_u32(smem);
-
     const long long n_tiles = (n_envs + TILE - 1) / TILE;
-    const uint32_t obs_bytes = (uint32_t)(TILE * D * sizeof(float)), row_bytes = (uint32_t)(TILE * A * sizeof(float));
-    uint32_t o_phase = 0, n_phase = 0, m_phase = 0;
-    bool first = true, prefetched = false, stores_pending = false;
+    const long long stride = gridDim.x;
+    const long long first_tile = blockIdx.x;
+    const int my_tiles = first_tile < n_tiles ? (int)((n_tiles - 1 - first_tile) / stride + 1) : 0;
 
+    if (issuer) {
+        // ---- the MMA issuer ----
+        const uint32_t tm = *tmem_slot;
+        const uint32_t w_base = smem_u32(smem);
+        const uint32_t w_net1 = w_base + (uint32_t)(NET_FLOATS * sizeof(float));
+        const uint32_t mb0 = smem_u32(mbar), mb1 = mb0 + 8u;
+        const uint32_t tn0 = tm + C_NET0, tn1 = tn0 + C_NETSTRIDE;
+        uint32_t xp = 0u, cp = 0u, ap = 0u;
 #pragma unroll 1
-    for (long long tile = (long long)blockIdx.x * GROUPS + g; tile < n_tiles; tile += (long long)gridDim.x * GROUPS) {
-        const long long e0 = tile * TILE;
-        const int nv = (int)((n_envs - e0) < TILE ? (n_envs - e0) : TILE);
-        const bool full = aligned && nv == TILE;             // whole tile, 16-byte aligned rows: copy engine
-        const bool sample = !value_only && noise != nullptr;
-        // ---- stage this tile's observation rows (and noise rows) in shared memory ----
-        if (t == 0 && stores_pending) bulk_wait_read<0>();   // the previous tile's action rows have left their stages
-        if (full) {
-            if (t == 0) {
-                if (!prefetched) {
-                    mbar_expect_tx(obar, obs_bytes);
-                    bulk_g2s(obs_s, obs + e0 * D, obs_bytes, obar);
-                }
-                if (sample) {
-                    mbar_expect_tx(nbar, row_bytes);
-                    bulk_g2s(noise_s, noise + e0 * A, row_bytes, nbar);
-                }
+        for (int it = 0; it < my_tiles; ++it) {
+            const uint32_t x = tm + x_cols(it & 1);
+            // the heads write into the (by then unused) lo half of the tile's own X buffer: P is overwritten by the next
+            // tile's layer 0 before the compute warps get to read the heads
+            const uint32_t head0 = x + 32u, head1 = x + 48u;
+            mbar_wait(xbar, xp); xp ^= 1u;                             // X of this tile
+            if (it == 0) mbar_wait(wbar, 0);
+            issue_phase(0, tn0, x, 0, w_base, mb0);
+            if (n_nets == 2) {
+                if (it == 0) mbar_wait(wbar + 2, 0);
+                issue_phase(0, tn1, x, 0, w_net1, mb1);
             }
-            mbar_wait(obar, o_phase);
-            o_phase ^= 1u;
-        } else {
-            for (int k = t; k < nv * D; k += TILE) obs_s[k] = obs[e0 * D + k];
-            if (sample)
-                for (int k = t; k < nv * A; k += TILE) noise_s[k] = noise[e0 * A + k];
-            group_barrier(g);
+            mbar_wait(rbar, cp); cp ^= 1u;                             // tanh(critic layer 0)
+            if (it == 0) mbar_wait(wbar + 1, 0);
+            issue_phase(1, tn0, x, 0, w_base, mb0);
+            if (n_nets == 2) {
+                mbar_wait(rbar + 1, ap); ap ^= 1u;                     // tanh(actor layer 0)
+                issue_phase(1, tn1, x, 0, w_net1, mb1);
+            }
+            mbar_wait(rbar, cp); cp ^= 1u;                             // tanh(critic layer 1)
+            issue_phase(2, tn0, x, head0, w_base, mb0);
+            if (n_nets == 2) {
+                mbar_wait(rbar + 1, ap); ap ^= 1u;                     // tanh(actor layer 1)
+                issue_phase(2, tn1, x, head1, w_net1, mb1);
+            }
         }
-        // ---- X = [obs | 0 | 1 1] -> tf32 hi / lo -> TMEM (the A operand of layer 0) ----
-        {
-            uint32_t xh[32], xl[32];
+    } else if (my_tiles > 0) {
+        const uint32_t tmem = *tmem_slot;
+        const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16);   // ... as seen by this warp's 32 lanes
+        const uint32_t tc = tlane + C_NET0, ta = tc + C_NETSTRIDE;           // critic / actor regions
+        const uint32_t obs_bytes = (uint32_t)(TILE * D * sizeof(float)), row_bytes = (uint32_t)(TILE * A * sizeof(float));
+        const bool sample = !value_only && noise != nullptr;
+        uint32_t n_phase = 0, mc_phase = 0, ma_phase = 0;
+        bool stores_pending = false;
+        auto tile_full = [&](long long tile) { return aligned && tile < n_tiles && (n_envs - tile * TILE) >= TILE; };
+        // copy-engine fetch of a whole tile's observation rows into stage `buf` (thread 0)
+        auto fetch_obs = [&](long long tile, int buf) {
+            mbar_expect_tx(obar + buf, obs_bytes);
+            bulk_g2s(reinterpret_cast<unsigned char *>(obs_s0) + (size_t)buf * sp.obs_stage, obs + tile * TILE * D, obs_bytes, obar + buf);
+        };
+        // X = [obs | 0 | 1 1] of tile `tile` -> tf32 hi / lo -> X buffer `it & 1` in TMEM (the A operand of layer 0), then
+        // tell the issuer.  Each warp converts 8 of the 32 columns of its 32 rows.
+        auto stage_x = [&](long long tile, int it) {
+            const int buf = it & 1;
+            float *obs_s = reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(obs_s0) + (size_t)buf * sp.obs_stage);
+            const long long e0 = tile * TILE;
+            const int nv = (int)((n_envs - e0) < TILE ? (n_envs - e0) : TILE);
+            if (tile_full(tile)) {
+                mbar_wait(obar + buf, (uint32_t)((it >> 1) & 1));
+            } else {                                                     // ragged last tile / unaligned rows: plain loads
+                for (int k = threadIdx.x; k < nv * D; k += THREADS) obs_s[k] = obs[e0 * D + k];
+                compute_barrier();
+            }
+            uint32_t xh[8], xl[8];
             const float *row = obs_s + t * D;
 #pragma unroll
-            for (int k = 0; k < KP; ++k) {
+            for (int j = 0; j < 8; ++j) {
+                const int k = 8 * cb + j;
                 const float x = k < D ? (t < nv ? row[k] : 0.f) : (k >= KP - 2 ? 1.0f : 0.f);
-                split_tf32(x, xh[k], xl[k]);
+                split_tf32(x, xh[j], xl[j]);
             }
             __syncwarp();
-            tmem_st32(tlane + C_XHI, xh);
-            tmem_st32(tlane + C_XLO, xl);
+            tmem_st8(tlane + x_cols(buf) + 8 * cb, xh);
+            tmem_st8(tlane + x_cols(buf) + 32 + 8 * cb, xl);
             tmem_wait_st();
+            tc_fence_before();
+            mbar_arrive(xbar);
+        };
+
+        if (threadIdx.x == 0) {
+            if (tile_full(first_tile)) fetch_obs(first_tile, 0);
+            if (tile_full(first_tile + stride)) fetch_obs(first_tile + stride, 1);
         }
-        tc_fence_before();
-        group_barrier(g);
-        // the observation stage is free again: fetch the next tile's rows while this one is computed
-        const long long next = tile + (long long)gridDim.x * GROUPS;
-        prefetched = aligned && next < n_tiles && (n_envs - next * TILE) >= TILE;
-        if (t == 0 && prefetched) {
-            mbar_expect_tx(obar, obs_bytes);
-            bulk_g2s(obs_s, obs + next * TILE * D, obs_bytes, obar);
-        }
+        stage_x(first_tile, 0);
 
 #pragma unroll 1
-        for (int net = 0; net < (value_only ? 1 : 2); ++net) {           // 0 = critic, 1 = actor
-            const uint32_t wn = w_base + (uint32_t)(net * NET_FLOATS * sizeof(float));
-            // ---- layer 0 -> P ----
-            if (t == 0) {
-                if (first) { mbar_wait(wbar, 0); first = false; }
-                tc_fence_after();
-                issue_layer(tmem + C_P, tmem + C_XHI, tmem + C_XLO, wn + OFF_W0HI * 4, wn + OFF_W0LO * 4, KP / 8, H, 0, 0);
-                mma_commit(mbar);
+        for (int it = 0; it < my_tiles; ++it) {
+            const long long tile = first_tile + (long long)it * stride;
+            const long long e0 = tile * TILE;
+            const int nv = (int)((n_envs - e0) < TILE ? (n_envs - e0) : TILE);
+            const bool full = tile_full(tile);
+            TRACE();
+            if (sample) {
+                if (full) {
+                    if (threadIdx.x == 0) {                              // the previous tile's samples were taken before its barrier
+                        mbar_expect_tx(nbar, row_bytes);
+                        bulk_g2s(noise_s, noise + e0 * A, row_bytes, nbar);
+                    }
+                } else {
+                    for (int k = threadIdx.x; k < nv * A; k += THREADS) noise_s[k] = noise[e0 * A + k];
+                    compute_barrier();
+                }
             }
-            mbar_wait(mbar, m_phase);
-            m_phase ^= 1u;
-            tc_fence_after();
-            tanh_epilogue(tlane + C_P, tlane + C_Q);                      // R = (P, Q)
-            tc_fence_before();
-            group_barrier(g);
-            // ---- layer 1 -> S ----
-            if (t == 0) {
-                tc_fence_after();
-                issue_layer(tmem + C_S, tmem + C_P, tmem + C_Q, wn + OFF_W1HI * 4, wn + OFF_W1LO * 4, H / 8, H, tmem + C_XHI + (KP - 8),
-                            wn + OFF_B1 * 4);
-                mma_commit(mbar);
-            }
-            mbar_wait(mbar, m_phase);
-            m_phase ^= 1u;
-            tc_fence_after();
-            tanh_epilogue(tlane + C_S, tlane + C_Q);                      // R = (S, Q)
-            tc_fence_before();
-            group_barrier(g);
-            // ---- head -> P[0:16] ----
-            if (t == 0) {
-                tc_fence_after();
-                issue_layer(tmem + C_P, tmem + C_S, tmem + C_Q, wn + OFF_WHHI * 4, wn + OFF_WHLO * 4, H / 8, NH, tmem + C_XHI + (KP - 8),
-                            wn + OFF_BH * 4);
-                mma_commit(mbar);
-            }
-            mbar_wait(mbar, m_phase);
-            m_phase ^= 1u;
-            tc_fence_after();
-            uint32_t out[16];
-            __syncwarp();
-            tmem_ld16(tlane + C_P, out);
-            tmem_wait_ld();
-            if (net == 0) {
-                if (t < nv) values[e0 + t] = __uint_as_float(out[0]);
-                tc_fence_before();
-                group_barrier(g);          // every lane has read the critic's head before the actor's layer 0 overwrites P
-                continue;
-            }
-            // ---- DiagGaussian sample, clip to the Box, log-probability ----
-            if (sample && full) {
-                mbar_wait(nbar, n_phase);
-                n_phase ^= 1u;
-            }
-            float lp = 0.f;
+            // ---- hidden layers: the epilogue of one network overlaps the MMAs of the other ----
 #pragma unroll
-            for (int a = 0; a < NH; ++a) {
-                if (a < A) {
-                    const float sd = __ldg(img + OFF_STD + a), ls = __ldg(img + OFF_STD + 16 + a);
-                    const float z = sample ? noise_s[t * A + a] : 0.f;
-                    const float x = fmaf(z, sd, __uint_as_float(out[a]));
-                    raw_s[t * A + a] = x;
-                    act_s[t * A + a] = fminf(fmaxf(x, __ldg(low + a)), __ldg(high + a));   // SB3 clips Box actions before env.step
-                    lp += -0.5f * z * z - ls - 0.91893853320467274f;                        // log N(x; mean, std)
+            for (int layer = 0; layer < 2; ++layer) {
+                const uint32_t src = layer == 0 ? C_P : C_S;
+                mbar_wait(mbar, mc_phase); mc_phase ^= 1u;
+                tc_fence_after();
+                TRACE();
+                tanh_epilogue(tc + src + 16 * cb, tc + C_Q + 16 * cb);
+                if (layer == 0 && threadIdx.x == 0 && stores_pending) bulk_wait_read<0>();   // before anyone restages action rows
+                tc_fence_before();
+                mbar_arrive(rbar);
+                TRACE();
+                if (n_nets == 2) {
+                    mbar_wait(mbar + 1, ma_phase); ma_phase ^= 1u;
+                    tc_fence_after();
+                    TRACE();
+                    tanh_epilogue(ta + src + 16 * cb, ta + C_Q + 16 * cb);
+                    tc_fence_before();
+                    mbar_arrive(rbar + 1);
+                    TRACE();
                 }
             }
-            if (t < nv) log_probs[e0 + t] = lp;
-            if (full) {
-                fence_proxy_async();
-                group_barrier(g);
-                if (t == 0) {
-                    bulk_s2g(raw_actions + e0 * A, raw_s, row_bytes);
-                    bulk_s2g(actions + e0 * A, act_s, row_bytes);
-                    bulk_commit();
+            // ---- while the heads run: the next tile's X into the other buffer, then prefetch the tile after it ----
+            if (it + 1 < my_tiles) {
+                stage_x(tile + stride, it + 1);
+                // stage `it & 1` held this tile's rows: every warp read them before it arrived for X(it), and this tile's
+                // layers (observed complete above) were issued after all of those arrivals -- the stage is free
+                if (threadIdx.x == 0 && tile_full(tile + 2 * stride)) fetch_obs(tile + 2 * stride, it & 1);
+            }
+            TRACE();
+            // ---- heads: value (column 32 of the tile's X buffer), action means (columns 48..63) ----
+            const uint32_t xb = tlane + x_cols(it & 1);
+            mbar_wait(mbar, mc_phase); mc_phase ^= 1u;
+            tc_fence_after();
+            __syncwarp();
+            if (cb == 0) {                         // warp-uniform
+                const uint32_t v = tmem_ld1(xb + 32);
+                tmem_wait_ld();
+                if (t < nv) values[e0 + t] = __uint_as_float(v);
+            }
+            if (n_nets == 2) {
+                mbar_wait(mbar + 1, ma_phase); ma_phase ^= 1u;
+                tc_fence_after();
+                __syncwarp();
+                if (cb == 1) {                     // DiagGaussian sample, clip to the Box, log-probability
+                    uint32_t out[16];
+                    tmem_ld16(xb + 48, out);
+                    tmem_wait_ld();
+                    if (sample && full) mbar_wait(nbar, n_phase);
+                    float lp = 0.f;
+#pragma unroll
+                    for (int a = 0; a < NH; ++a) {
+                        if (a < A) {
+                            const float sd = __ldg(img + OFF_STD + a), ls = __ldg(img + OFF_STD + 16 + a);
+                            const float z = sample ? noise_s[t * A + a] : 0.f;
+                            const float x = fmaf(z, sd, __uint_as_float(out[a]));
+                            raw_s[t * A + a] = x;
+                            act_s[t * A + a] = fminf(fmaxf(x, __ldg(low + a)), __ldg(high + a));   // SB3 clips Box actions before env.step
+                            lp += -0.5f * z * z - ls - 0.91893853320467274f;                        // log N(x; mean, std)
+                        }
+                    }
+                    if (t < nv) log_probs[e0 + t] = lp;
                 }
-                stores_pending = true;
-            } else {
-                group_barrier(g);
-                for (int k = t; k < nv * A; k += TILE) {
-                    raw_actions[e0 * A + k] = raw_s[k];
-                    actions[e0 * A + k] = act_s[k];
+                if (sample && full) n_phase ^= 1u;
+                if (full) {
+                    fence_proxy_async();
+                    compute_barrier();
+                    if (threadIdx.x == 0) {
+                        bulk_s2g(raw_actions + e0 * A, raw_s, row_bytes);
+                        bulk_s2g(actions + e0 * A, act_s, row_bytes);
+                        bulk_commit();
+                    }
+                    stores_pending = true;
+                } else {
+                    compute_barrier();
+                    for (int k = threadIdx.x; k < nv * A; k += THREADS) {
+                        raw_actions[e0 * A + k] = raw_s[k];
+                        actions[e0 * A + k] = act_s[k];
+                    }
                 }
             }
+            tc_fence_before();
         }
-        // every lane's tcgen05.ld of this tile has completed (wait::ld above) before the next tile's X store and MMAs:
-        // ordered by the fence + group barrier that follows the X store
-        tc_fence_before();
+        if (threadIdx.x == 0 && stores_pending) bulk_wait_read<0>();
     }
-    if (t == 0 && stores_pending) bulk_wait_read<0>();
     tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(*tmem_slot, 512);
+    if (trace && blockIdx.x == 0 && threadIdx.x == 0) trace[254] = clock64();
 }
 
 int ensure_smem(int device, const void *kern, size_t smem)
@@ -484,6 +626,8 @@ bool aligned16(const void *p) { return p == nullptr || (reinterpret_cast<uintptr
 
 }  // namespace
 
+extern "C" void sng_policy_debug_trace(long long *device_buf) { g_trace = device_buf; }
+
 extern "C" size_t sng_policy_packed_bytes(void) { return (size_t)IMG_FLOATS * sizeof(float); }
 
 extern "C" int sng_policy_pack(const sng_mlp *mlp, void *packed, void *stream)
@@ -507,16 +651,16 @@ extern "C" int sng_policy_forward_packed(const void *packed, int obs_dim, int ac
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     const Smem sp = smem_plan(obs_dim, act_dim);
-    const size_t smem = sp.bars + 128;
+    const size_t smem = sp.bars + 128;   // 11 mbarriers + the TMEM address slot
     if (ensure_smem(dev, (const void *)policy_tc_kernel, smem) != SNG_OK) return SNG_ERR_CUDA;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const long long n_tiles = (n_envs + TILE - 1) / TILE;
-    long long grid = (n_tiles + GROUPS - 1) / GROUPS;
+    long long grid = n_tiles;
     if (grid > sms) grid = sms;
     const int aligned = aligned16(obs) && aligned16(noise) && aligned16(raw_actions) && aligned16(actions) && aligned16(packed);
     if (!aligned16(packed)) return SNG_ERR_ARG;
-    policy_tc_kernel<<<(unsigned)grid, THREADS, smem, (cudaStream_t)stream>>>(reinterpret_cast<const float *>(packed), obs, noise, low, high,
+    policy_tc_kernel<<<(unsigned)grid, THREADS + 32, smem, (cudaStream_t)stream>>>(reinterpret_cast<const float *>(packed), obs, noise, low, high,
                                                                              raw_actions, actions, values, log_probs,
-                                                                             (long long)n_envs, obs_dim, act_dim, aligned);
+                                                                             (long long)n_envs, obs_dim, act_dim, aligned, g_trace);
     return cudaGetLastError() == cudaSuccess ? SNG_OK : SNG_ERR_CUDA;
 }
