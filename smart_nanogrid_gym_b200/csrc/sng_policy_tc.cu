@@ -459,6 +459,7 @@ __global__ void __launch_bounds__(THREADS + 32, 1)
             const int nv = (int)((n_envs - e0) < TILE ? (n_envs - e0) : TILE);
             if (tile_full(tile)) {
                 mbar_wait(obar + buf, (uint32_t)((it >> 1) & 1));
+                TRACE();
             } else {                                                     // ragged last tile / unaligned rows: plain loads
                 for (int k = threadIdx.x; k < nv * D; k += THREADS) obs_s[k] = obs[e0 * D + k];
                 compute_barrier();
@@ -537,6 +538,7 @@ __global__ void __launch_bounds__(THREADS + 32, 1)
             const uint32_t xb = tlane + x_cols(it & 1);
             mbar_wait(mbar, mc_phase); mc_phase ^= 1u;
             tc_fence_after();
+            TRACE();
             __syncwarp();
             if (cb == 0) {                         // warp-uniform
                 const uint32_t v = tmem_ld1(xb + 32);
@@ -546,6 +548,7 @@ __global__ void __launch_bounds__(THREADS + 32, 1)
             if (n_nets == 2) {
                 mbar_wait(mbar + 1, ma_phase); ma_phase ^= 1u;
                 tc_fence_after();
+                TRACE();
                 __syncwarp();
                 if (cb == 1) {                     // DiagGaussian sample, clip to the Box, log-probability
                     uint32_t out[16];
@@ -570,6 +573,7 @@ __global__ void __launch_bounds__(THREADS + 32, 1)
                 if (full) {
                     fence_proxy_async();
                     compute_barrier();
+                    TRACE();
                     if (threadIdx.x == 0) {
                         bulk_s2g(raw_actions + e0 * A, raw_s, row_bytes);
                         bulk_s2g(actions + e0 * A, act_s, row_bytes);
