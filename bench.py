@@ -44,6 +44,16 @@ WORKLOADS = {
     "n4": dict(kw=dict(number_of_chargers=4, charging_mode="bounded", vehicle_uncharged_penalty_mode="sparse",
                        time_interval="1h"), envs=65536,
                name="N=4 spots, PV+battery, 24-step episodes (the station of the reference's shipped PPO checkpoint)"),
+    # SURVEY 8f row 4 (generalised station): configurations that run the generic runtime-N kernel
+    "c4_h5": dict(kw=dict(number_of_chargers=10, charging_mode="bounded", vehicle_uncharged_penalty_mode="sparse",
+                          time_interval="1h", hours_ahead=5), envs=1048576,
+                  name="C4 station with a 5-step forecast horizon (generic kernel)"),
+    "c4_pv2d": dict(kw=dict(number_of_chargers=10, charging_mode="bounded", vehicle_uncharged_penalty_mode="sparse",
+                            time_interval="1h", number_of_days_to_predict=2, cycle_pv_days=True), envs=1048576,
+                    name="C4 station with two-day PV (episode k reads day k % 2; generic kernel)"),
+    "c4_nopv": dict(kw=dict(number_of_chargers=10, charging_mode="bounded", vehicle_uncharged_penalty_mode="sparse",
+                            time_interval="1h", pv_system_available_in_model=False), envs=1048576,
+                    name="C4 station without PV (generic kernel)"),
 }
 ENV_KW = WORKLOADS["c4"]["kw"]
 METRIC = "batched env-steps/sec"
@@ -51,10 +61,10 @@ UNIT = "env-steps/s"
 L2_BYTES = 126e6
 
 
-def algorithmic_bytes_per_env_step(n_spots, batt, pv):
+def algorithmic_bytes_per_env_step(n_spots, batt, pv, horizon=3):
     """4A + 4D + 4 + 1 + 8N + 8b + 4 + 12N (float32 build)."""
     a = n_spots + batt
-    d = 4 * (1 + pv) + 2 * n_spots + batt
+    d = (1 + horizon) * (1 + pv) + 2 * n_spots + batt
     return 4 * a + 4 * d + 4 + 1 + 8 * n_spots + 8 * batt + 4 + 12 * n_spots
 
 
@@ -461,7 +471,7 @@ def launch_floor_us(ctx, n=2400):
 
 
 def roofline_of(ctx, wl_key, cfg, E, kernel_ms, floor_us=None):
-    bytes_step = algorithmic_bytes_per_env_step(cfg.n_spots, int(cfg.batt), int(cfg.pv))
+    bytes_step = algorithmic_bytes_per_env_step(cfg.n_spots, int(cfg.batt), int(cfg.pv), cfg.hours_ahead)
     achieved = bytes_step * E / (kernel_ms * 1e-3) / 1e9
     traffic = ncu_traffic_bytes(wl_key, E)
     r = {"bound": "hbm", "achieved": achieved, "peak": ctx.peak, "unit": "GB/s", "frac": achieved / ctx.peak,
@@ -705,7 +715,7 @@ def main():
     ap.add_argument("--variant", type=int, default=0, help="tuning: 0 default, 1 persistent pipelined kernel, 2 one lane per env even for large stations")
     ap.add_argument("--ctas", type=int, default=0, help="tuning: cap on resident CTAs per SM (pipelined kernel)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs")
-    ap.add_argument("--legs", default="all", help="'all', 'none' or a comma list of c4_strong,c5,c3,c3_sb3,c2,rollout_kernel")
+    ap.add_argument("--legs", default="all", help="'all', 'none' or a comma list of c4_strong,c5,c3,c3_sb3,c2,rollout_kernel,generic")
     ap.add_argument("--rollout", type=int, default=0, help="legacy: same as --legs c3 with this many steps per rollout")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -776,7 +786,7 @@ def main():
     want = args.legs
     if args.rollout > 0 and want in ("none", ""):
         want = "c3"
-    names = ["c4_strong", "c5", "c3", "c3_sb3", "c2", "rollout_kernel"] if want == "all" else [x for x in want.split(",") if x and x != "none"]
+    names = ["c4_strong", "c5", "c3", "c3_sb3", "c2", "rollout_kernel", "generic"] if want == "all" else [x for x in want.split(",") if x and x != "none"]
     legs = {}
     if names:
         floor_us = launch_floor_us(ctx)
@@ -802,6 +812,10 @@ def main():
                     legs[name]["what"] = "BASELINE config 2: 4,096 envs per GPU, one sng_step launch per step"
                     legs["c2_rollout_kernel"] = rollout_kernel_leg(ctx, "c4", 4096, floor_us, min_ms=100.0)
                     legs["c2_rollout_kernel"]["what"] = "BASELINE config 2 through sng_rollout (24 steps per launch)"
+                elif name == "generic":
+                    for wl in ("c4_h5", "c4_pv2d", "c4_nopv"):
+                        legs["generic_" + wl] = step_leg(ctx, wl, WORKLOADS[wl]["envs"], ctx.rank * WORKLOADS[wl]["envs"], floor_us, min_ms=120.0)
+                        legs["generic_" + wl]["what"] = "SURVEY 8f row 4: " + WORKLOADS[wl]["name"] + ", 1,048,576 envs per GPU"
                 elif name == "rollout_kernel":
                     for n in (65536, 131072):
                         legs["rollout_kernel_%d" % n] = rollout_kernel_leg(ctx, "c4", n, floor_us)

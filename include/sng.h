@@ -39,7 +39,7 @@ extern "C" {
 #define SNG_ABI_VERSION 3
 #define SNG_MAX_VEHICLES 8   /* schedule slots per spot and day */
 #define SNG_MAX_SPOTS 255
-#define SNG_MAX_TABLE 512    /* entries of the shared PV / price tables (two days) */
+#define SNG_MAX_TABLE 512    /* entries of the shared PV / price tables (two days; pv_days + 1 days with multi-day PV) */
 
 typedef struct sng_env sng_env;
 
@@ -72,6 +72,11 @@ typedef struct {
     int32_t req_soc;        /* enable_requested_state_of_charge */
     int32_t default_cap;    /* 40 kWh */
     int32_t auto_reset;     /* 1: a finished env is reset inside the same step (VecEnv semantics) */
+    int32_t pv_days;        /* 1 (the reference: NUMBER_OF_DAYS_TO_PREDICT = 1, ...environment.py:51, and row 0 of
+                             * solar_irradiance_2 only, pv_system_manager.py:81-91).  D > 1: episode k reads the PV tables
+                             * at offset (k % D) * n_steps, i.e. day k % D of a (D + 1)-day series; table_len must then
+                             * be >= (D + 1) * n_steps */
+    int32_t _reserved;
     double dt;              /* hours per step */
     double ev_pmax, ev_eff; /* 22 kW, 0.95 */
     double b_cap, b_pmax, b_eff, b_dod, b_soc0; /* 80 kWh, 44 kW, 0.95, 0.15, 0.5 */

@@ -81,11 +81,12 @@ static void observe_one(const ngo_config *c, ngo_state *s, int64_t e, float *obs
     if (!obs) return;
     int k = 0;
     const double shift = s->pv_shift[e];
+    const int pvo = s->pv_base ? s->pv_base[e] : 0;
     const int lo = t + 1, hi = lo + c->horizon; /* ...environment.py:191-192 */
     if (c->pv) {
-        obs[k++] = (float)(c->irr_norm[t] * shift);  /* central_management_system.py:58 */
+        obs[k++] = (float)(c->irr_norm[pvo + t] * shift);  /* central_management_system.py:58 */
         obs[k++] = (float)(c->price_norm[t]);        /* :53 */
-        for (int j = lo; j < hi; j++) obs[k++] = (float)(c->irr_norm[j] * shift); /* :59-60 */
+        for (int j = lo; j < hi; j++) obs[k++] = (float)(c->irr_norm[pvo + j] * shift); /* :59-60 */
         for (int j = lo; j < hi; j++) obs[k++] = (float)(c->price_norm[j]);       /* :54-55 */
     } else {
         obs[k++] = (float)(c->price_norm[t]);
@@ -195,7 +196,7 @@ static void step_one(const ngo_config *c, ngo_state *s, int64_t e, const double 
 
     /* central_management_system.py:99-103 */
     double solar = 0.0;
-    if (c->pv) solar = c->pv_power[t] * s->pv_shift[e];
+    if (c->pv) solar = c->pv_power[(s->pv_base ? s->pv_base[e] : 0) + t] * s->pv_shift[e];
 
     const double total_power = total_ch + total_dis; /* :105 */
     /* calculate_grid_power, :157-185 */
@@ -392,6 +393,7 @@ void ngo_sample_episode(const ngo_config *c, ngo_state *s, int64_t e, uint64_t s
         ngo_philox4x32_10(ctr, key, x);
         const uint32_t k = (uint32_t)(((uint64_t)x[0] * 181u) >> 32);
         s->pv_shift[e] = (double)((float)k / 100.0f);
+        if (s->pv_base) s->pv_base[e] = c->pv_days > 1 ? (int32_t)(episode % (uint32_t)c->pv_days) * c->n_steps : 0;
     }
     s->t[e] = 0;
 }

@@ -33,7 +33,7 @@ def build(force=False):
 class _Cfg(C.Structure):
     _fields_ = [("n_spots", C.c_int32), ("n_steps", C.c_int32), ("dt", C.c_double),
                 ("pv", C.c_int32), ("batt", C.c_int32), ("v2x", C.c_int32), ("penalty_mode", C.c_int32),
-                ("horizon", C.c_int32), ("diff_cap", C.c_int32), ("req_soc", C.c_int32), ("_pad", C.c_int32),
+                ("horizon", C.c_int32), ("diff_cap", C.c_int32), ("req_soc", C.c_int32), ("pv_days", C.c_int32),
                 ("ev_pmax", C.c_double), ("ev_eff", C.c_double), ("b_cap", C.c_double), ("b_pmax", C.c_double),
                 ("b_eff", C.c_double), ("b_dod", C.c_double), ("sell_coeff", C.c_double),
                 ("cost_weight", C.c_double), ("batt_pen_w", C.c_double), ("margin", C.c_double),
@@ -44,7 +44,7 @@ class _Cfg(C.Structure):
 
 class _State(C.Structure):
     _fields_ = [("n_envs", C.c_int64)] + [(n, C.c_void_p) for n in (
-        "occ", "soc", "cap", "req", "arr", "dep", "n_veh", "check", "t", "pv_shift", "soc_b", "err")]
+        "occ", "soc", "cap", "req", "arr", "dep", "n_veh", "check", "t", "pv_shift", "soc_b", "err", "pv_base")]
 
 
 _lib = None
@@ -53,8 +53,7 @@ _lib = None
 def lib():
     global _lib
     if _lib is None:
-        if not os.path.exists(_LIB_PATH):
-            build()
+        build()          # no-op unless the sources are newer than the library
         L = C.CDLL(_LIB_PATH)
         L.ngo_obs_dim.restype = C.c_int
         L.ngo_act_dim.restype = C.c_int
@@ -94,6 +93,7 @@ class OracleBatch:
         c.horizon = cfg.hours_ahead
         c.diff_cap = int(cfg.enable_different_vehicle_battery_capacities)
         c.req_soc = int(cfg.enable_requested_state_of_charge)
+        c.pv_days = int(cfg.pv_days) if (cfg.pv and getattr(cfg, "cycle_pv_days", False)) else 1
         c.ev_pmax, c.ev_eff = cfg.ev_max_power, cfg.ev_efficiency
         c.b_cap, c.b_pmax, c.b_eff, c.b_dod = (cfg.bess_capacity, cfg.bess_max_power, cfg.bess_efficiency,
                                                cfg.bess_depth_of_discharge)
@@ -115,9 +115,10 @@ class OracleBatch:
         self.pv_shift = np.ones(E)
         self.soc_b = np.full(E, cfg.bess_initial_soc if cfg.batt else 0.0)
         self.err = np.zeros(E, np.uint32)
+        self.pv_base = np.zeros(E, np.int32)     # offset of the episode's day in the PV tables (multi-day PV)
         s = _State()
         s.n_envs = E
-        for n in ("occ", "soc", "cap", "req", "arr", "dep", "n_veh", "check", "t", "pv_shift", "soc_b", "err"):
+        for n in ("occ", "soc", "cap", "req", "arr", "dep", "n_veh", "check", "t", "pv_shift", "soc_b", "err", "pv_base"):
             setattr(s, n, getattr(self, n).ctypes.data)
         self._s = s
         self.obs_dim = lib().ngo_obs_dim(C.byref(c))

@@ -30,6 +30,7 @@ class SngConfig(C.Structure):
                 ("n_spots", C.c_int32), ("n_steps", C.c_int32), ("horizon", C.c_int32), ("table_len", C.c_int32),
                 ("pv", C.c_int32), ("batt", C.c_int32), ("v2x", C.c_int32), ("penalty_mode", C.c_int32),
                 ("diff_cap", C.c_int32), ("req_soc", C.c_int32), ("default_cap", C.c_int32), ("auto_reset", C.c_int32),
+                ("pv_days", C.c_int32), ("_reserved", C.c_int32),
                 ("dt", C.c_double), ("ev_pmax", C.c_double), ("ev_eff", C.c_double),
                 ("b_cap", C.c_double), ("b_pmax", C.c_double), ("b_eff", C.c_double), ("b_dod", C.c_double),
                 ("b_soc0", C.c_double),
@@ -145,6 +146,7 @@ def make_config(cfg, n_envs: int, env_gid0: int = 0, precision: int = SNG_F32, a
     c.req_soc = int(cfg.enable_requested_state_of_charge)
     c.default_cap = int(cfg.default_vehicle_capacity)
     c.auto_reset = int(auto_reset)
+    c.pv_days = int(cfg.pv_days) if (cfg.pv and getattr(cfg, "cycle_pv_days", False)) else 1
     c.dt = cfg.dt
     c.ev_pmax, c.ev_eff = cfg.ev_max_power, cfg.ev_efficiency
     c.b_cap, c.b_pmax, c.b_eff, c.b_dod, c.b_soc0 = (cfg.bess_capacity, cfg.bess_max_power, cfg.bess_efficiency,

@@ -51,8 +51,8 @@ def _price_day_hourly(price_model: int) -> np.ndarray:
     raise ValueError("price_model must be 0..4 (model 5 raises in the reference as well)")
 
 
-def build_price_table(price_model: int, dt: float, n_steps: int):
-    """Two-day price table + its max.  For dt >= 1 h this is the reference's hard-coded
+def build_price_table(price_model: int, dt: float, n_steps: int, days: int = 1):
+    """(days + 1)-day price table (the reference's two days for days = 1; the tariff repeats daily) + its max.  For dt >= 1 h this is the reference's hard-coded
     hourly table used verbatim (accountant.py:49-56,69-73: it is indexed by *step*, quirk Q9).
     For dt < 1 h (no runnable reference) model 0 follows the reference's own
     dt-parameterised (dead-code) rule `low if i < 7/dt or i > 19/dt else high`
@@ -65,9 +65,12 @@ def build_price_table(price_model: int, dt: float, n_steps: int):
         else:
             day = np.repeat(day, int(round(1.0 / dt)))
     two_days = np.concatenate([day, day], axis=0)
-    need = 2 * n_steps
+    need = (days + 1) * n_steps
     if two_days.shape[0] < need:
-        two_days = np.resize(two_days, need)
+        if two_days.shape[0] < 2 * n_steps:
+            two_days = np.resize(two_days, 2 * n_steps)     # 2 h steps: the reference's 48-entry table, indexed by step
+        else:
+            two_days = np.concatenate([two_days] + [day] * (days - 1), axis=0)
     price_max = two_days.max(where=(two_days >= 0), initial=0)  # accountant.py:51
     return two_days.astype(np.float64), float(price_max)
 
@@ -78,12 +81,16 @@ def load_irradiance_1min() -> np.ndarray:
     return np.load(os.path.join(_DATA_DIR, "solar_irradiance_1min.npy"))
 
 
-def build_pv_tables(dt: float, n_steps: int, irradiance_1min: Optional[np.ndarray] = None):
-    """PVSystemManager.__init__, utils/pv_system_manager.py:10-22: per-step irradiance means
-    over a 2-day padded window (:34-44), max (:20), PV power = irr*A*eta/1000*1.5/dt (:67-73,87-88)."""
+def build_pv_tables(dt: float, n_steps: int, irradiance_1min: Optional[np.ndarray] = None, days: int = 1):
+    """PVSystemManager(days, dt).__init__, utils/pv_system_manager.py:10-22: per-step irradiance means
+    over a (days + 1)-day padded window (:11-15, 34-44), max (:20), PV power = irr*A*eta/1000*1.5/dt (:67-73,87-88).
+    The flat series returned here is `solar_irradiance[0]` / `available_solar_power[0]`; row d of the reference's
+    `solar_irradiance_2` (:46-65, "repeated middle" reshape) is its window [d * n_steps, (d + 2) * n_steps)."""
     irr_1min = load_irradiance_1min() if irradiance_1min is None else np.asarray(irradiance_1min, np.float64)
     step_min = int(60 * dt)
-    padded = n_steps * 2
+    padded = n_steps * (days + 1)
+    if padded * step_min > irr_1min.shape[0]:
+        raise ValueError("the irradiance file holds %d minutes: too short for %d day(s) + 1 of padding" % (irr_1min.shape[0], days))
     irr = np.zeros(padded)
     for k in range(padded):
         irr[k] = np.mean(irr_1min[k * step_min:(k + 1) * step_min])
@@ -124,6 +131,9 @@ class NanogridConfig:
     battery_penalty_weight: float = 0.8 # penaliser.py:181
     soc_margin_ratio: float = 0.05      # penaliser.py:7
     hours_ahead: int = 3                # ...environment.py:52
+    number_of_days_to_predict: int = 1  # ...environment.py:51 (NUMBER_OF_DAYS_TO_PREDICT -> PVSystemManager(days, dt))
+    cycle_pv_days: bool = False         # extension: episode k sees day k % days of the irradiance series (the reference
+                                        # always reads row 0 of solar_irradiance_2, pv_system_manager.py:81-91)
     departure_normaliser: float = 24.0  # ...environment.py:208 (a literal, not 24/dt)
 
     def __post_init__(self):
@@ -142,10 +152,13 @@ class NanogridConfig:
         self.v2x = bool(self.vehicle_to_everything)
         self.act_dim = self.n_spots + int(self.batt)                      # ...environment.py:101-118
         self.obs_dim = (1 + int(self.pv)) * (1 + self.hours_ahead) + 2 * self.n_spots + int(self.batt)  # :90-96
-        self.price, self.price_max = build_price_table(self.price_model, self.dt, self.n_steps)
+        self.pv_days = int(self.number_of_days_to_predict)
+        if self.pv_days < 1:
+            raise ValueError("number_of_days_to_predict must be >= 1")
+        self.price, self.price_max = build_price_table(self.price_model, self.dt, self.n_steps, self.pv_days)
         self.price_norm = self.price / self.price_max                      # accountant.py:41-46
         if self.pv:
-            self.irr, self.irr_max, self.pv_power = build_pv_tables(self.dt, self.n_steps)
+            self.irr, self.irr_max, self.pv_power = build_pv_tables(self.dt, self.n_steps, days=self.pv_days)
             self.irr_norm = self.irr / self.irr_max                        # pv_system_manager.py:81-85
         else:
             n = self.price.shape[0]

@@ -74,6 +74,7 @@ template <typename real> struct Params {
     int i4, i10, i1;  // int(4/dt), int(10/dt), int(1/dt): charging_station.py:271-279
     int off_soc, off_dep, off_batt;
     int max_togo;     // penalty-check window: 0 none, 1 on_departure, 3 sparse, 1<<20 dense
+    int pv_days;      // 1 (the reference), or D > 1: episode k reads the PV tables at offset (k % D) * T (generic kernel only)
     int has_req;      // 0: every vehicle requests SoC 1.0 (sampling without enable_requested_state_of_charge): the
                       //    requested-SoC plane is neither read nor written
     real dt, ev_pmax, ev_eff, b_cap, b_pmax, b_eff, b_dod, b_soc0, sell, cost_w, batt_w, margin;
@@ -284,11 +285,19 @@ template <int NCT, int ND> struct Offsets {
     template <typename real> static __device__ __forceinline__ int batt(const Params<real> &p) { return (NCT && ND) ? ND + 2 * NCT : p.off_batt; }
 };
 
+// Offset of the episode's day in the PV tables.  The reference always reads row 0 of solar_irradiance_2
+// (pv_system_manager.py:81-91); with pv_days = D > 1 episode k reads day k % D of the (D + 1)-day series.  Only the
+// generic instantiation (NCT == 0) supports it: the dispatch keeps such configurations off the specialised kernels.
+template <int NCT, typename real> __device__ __forceinline__ int pv_day_offset(const Params<real> &p, uint32_t episode)
+{
+    return (NCT == 0 && p.pv_days > 1) ? (int)(episode % (uint32_t)p.pv_days) * p.T : 0;
+}
+
 // Env-level part of the observation (envs/smart_nanogrid_environment.py:197-205,
 // central_management_system.py:53-60): disturbances now and `H` steps ahead, battery SoC.
 // ND == 8 is the reference's own shape (PV on, NUMBER_OF_HOURS_AHEAD = 3).
 template <typename real, int NCT, int ND>
-__device__ __forceinline__ void write_obs_env(const Params<real> &p, float *obs, int t, real shift, real soc_b)
+__device__ __forceinline__ void write_obs_env(const Params<real> &p, float *obs, int t, real shift, real soc_b, int pvo = 0)
 {
     if (NCT && ND == 8) {
 #pragma unroll
@@ -298,9 +307,9 @@ __device__ __forceinline__ void write_obs_env(const Params<real> &p, float *obs,
     } else {
         int k = 0;
         if (p.pv) {
-            obs[k++] = (float)(__ldg(p.irr_norm + t) * shift);
+            obs[k++] = (float)(__ldg(p.irr_norm + pvo + t) * shift);
             obs[k++] = (float)__ldg(p.price_norm + t);
-            for (int j = 1; j <= p.H; ++j) obs[k++] = (float)(__ldg(p.irr_norm + t + j) * shift);
+            for (int j = 1; j <= p.H; ++j) obs[k++] = (float)(__ldg(p.irr_norm + pvo + t + j) * shift);
             for (int j = 1; j <= p.H; ++j) obs[k++] = (float)__ldg(p.price_norm + t + j);
         } else {
             obs[k++] = (float)__ldg(p.price_norm + t);
@@ -338,7 +347,7 @@ __device__ __forceinline__ void begin_episode(const Params<real> &p, int N, long
         obs[off_soc + i] = present ? (float)v.soc0 : 0.0f;
         obs[off_dep + i] = present ? dep_lookup<SMEM>(p, dep_base, (int)((v.hdr >> 8) & 0xFFu)) : 0.0f;
     }
-    if (L == 1 || sub == 0) write_obs_env<real, NCT, ND>(p, obs, 0, shift, soc_b);   // battery SoC survives resets (quirk Q8)
+    if (L == 1 || sub == 0) write_obs_env<real, NCT, ND>(p, obs, 0, shift, soc_b, pv_day_offset<NCT>(p, episode));   // battery SoC survives resets (quirk Q8)
 }
 
 // Spots whose state loads are issued together (and, in the pipelined kernel, one block ahead).
@@ -608,7 +617,8 @@ __device__ __forceinline__ Arrivals env_step(const Params<real> &p, long long e,
     const real pen_veh = pen_e + pen_o;
     const real total_power = pos + neg;                                   // :105
     if (total_power < (real)0 && !p.v2x) err |= FLAG_NEG_DEMAND;          // reference raises, :158-159
-    const real solar = p.pv ? __ldg(p.pv_power + t) * es.pv_shift : (real)0;   // :99-103
+    const int pvo = pv_day_offset<NCT>(p, episode);
+    const real solar = p.pv ? __ldg(p.pv_power + pvo + t) * es.pv_shift : (real)0;   // :99-103
     real rem = total_power - solar;                                       // :167
     real soc_b = es.soc_b, batt_power = 0, pen_b = 0;
     if (p.batt) {                                                         // battery_energy_storage_system.py:30-106
@@ -647,7 +657,7 @@ __device__ __forceinline__ Arrivals env_step(const Params<real> &p, long long e,
     const real total_cost = p.cost_w * fabs(cost) + total_pen;            // accountant.py:35
     const real reward = -total_cost;                                      // ...environment.py:183
 
-    if (lead) write_obs_env<real, NCT, ND>(p, obs, t, es.pv_shift, soc_b);   // obs at the pre-increment t, :173
+    if (lead) write_obs_env<real, NCT, ND>(p, obs, t, es.pv_shift, soc_b, pvo);   // obs at the pre-increment t, :173
     if (p.spot_power) {
         // diagnostics only (cold): the power of the charging / idle spots is a function of the action and of the
         // header, which is unchanged until the arrivals are admitted below; discharging spots were written above

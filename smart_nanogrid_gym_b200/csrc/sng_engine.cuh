@@ -401,6 +401,11 @@ public:
             error = "sng_create: invalid configuration";
             return SNG_ERR_ARG;
         }
+        if (c.pv_days < 0 || c.pv_days > 255 ||
+            (c.pv_days > 1 && c.table_len < (c.pv_days - 1) * c.n_steps + c.n_steps + c.horizon)) {
+            error = "sng_create: pv_days needs PV tables of at least (pv_days - 1) * n_steps + n_steps + horizon entries";
+            return SNG_ERR_ARG;
+        }
         if (EXACT && c.n_spots > 128) {
             error = "sng_create: the float64 validation build supports at most 128 spots";
             return SNG_ERR_UNSUPPORTED;
@@ -425,6 +430,7 @@ public:
         p.pen_mode = c.penalty_mode; p.diff_cap = c.diff_cap != 0; p.req_soc = c.req_soc != 0;
         p.max_togo = c.penalty_mode == PEN_DENSE ? (1 << 20) : (c.penalty_mode == PEN_SPARSE ? 3 : (c.penalty_mode == PEN_ON_DEPARTURE ? 1 : 0));
         p.default_cap = c.default_cap; p.auto_reset = c.auto_reset != 0; p.mode = MODE_SAMPLE;
+        p.pv_days = (c.pv && c.pv_days > 1) ? c.pv_days : 1;
         p.i4 = (int)(4.0 / c.dt); p.i10 = (int)(10.0 / c.dt); p.i1 = (int)(1.0 / c.dt);
         p.dt = (real)c.dt; p.ev_pmax = (real)c.ev_pmax; p.ev_eff = (real)c.ev_eff;
         p.b_cap = (real)c.b_cap; p.b_pmax = (real)c.b_pmax; p.b_eff = (real)c.b_eff; p.b_dod = (real)c.b_dod;
@@ -710,7 +716,7 @@ public:
             // shape (PV on, 3 steps ahead: 8 disturbance entries); everything else runs the generic kernel
             // (keyed on the flags themselves: PV off with 7 steps ahead also has 8 disturbance entries, but a
             // different layout -- eight prices)
-            if (!use_generic && q.pv && q.H == 3) {
+            if (!use_generic && q.pv && q.H == 3 && q.pv_days == 1) {
                 switch (q.N) {
                 case 4: return launch_step_n<4, 8>(q, actions, obs, reward, done, n_steps, bulk, st);
                 case 8: return launch_step_n<8, 8>(q, actions, obs, reward, done, n_steps, bulk, st);

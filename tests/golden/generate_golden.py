@@ -9,6 +9,7 @@ instead.  Everything written here is data produced by the unmodified reference c
   g1_*.json / g2_*.json       the reference's own recorded episodes (copied data files,
                               solvers/RL/{training_files,single_prediction_files}/)
   ref_tables.npz              PV / price tables for every runnable (dt, price model)
+  ref_tables_multiday.npz     PVSystemManager(2, dt): flat 3-day series, per-day rows, max, power (dt = 1 h, 2 h)
   ref_schedules_seeded.npz    schedules from the reference generator under np.random.seed(s)
   ref_variants.npz            32 flag variants x 2 episodes, branchy float64 actions
   ref_c1_rbc_n10.npz          BASELINE config 1: N=10 default env driven by the RBC rule
@@ -226,6 +227,22 @@ def gen_return_stats():
         json.dump(stats, fp, indent=2)
 
 
+def gen_multiday_tables():
+    """PVSystemManager(days, dt) for days > 1 (the env hard-codes NUMBER_OF_DAYS_TO_PREDICT = 1,
+    envs/smart_nanogrid_environment.py:51; the manager itself takes any number the 3-day irradiance file covers)."""
+    rl.load_reference()
+    from smart_nanogrid_gym.utils.pv_system_manager import PVSystemManager
+    out = {}
+    for ti, dt in (("1h", 1.0), ("2h", 2.0)):
+        pvm = PVSystemManager(2, dt)
+        k = "%s_d2_" % ti
+        out[k + "irr_flat"] = np.array(pvm.solar_irradiance[0], dtype=np.float64)
+        out[k + "irr_rows"] = np.array(pvm.solar_irradiance_2, dtype=np.float64)
+        out[k + "irr_max"] = np.float64(pvm.max_radiation)
+        out[k + "pv_power"] = np.array(pvm.available_solar_power[0], dtype=np.float64)
+    np.savez_compressed(os.path.join(HERE, "ref_tables_multiday.npz"), **out)
+
+
 SHIPPED_CHECKPOINT = "solvers/RL/models/PPO-b-pv-bounded-sparse-4ch-1h/999600.zip"
 
 
@@ -246,6 +263,9 @@ if __name__ == "__main__":
     if sys.argv[1:] == ["policy"]:
         gen_shipped_policy()
         sys.exit(0)
+    if sys.argv[1:] == ["multiday"]:
+        gen_multiday_tables()
+        sys.exit(0)
     random.seed(0)
     copy_recorded_episodes()
     gen_tables()
@@ -255,5 +275,6 @@ if __name__ == "__main__":
     gen_c2()
     gen_return_stats()
     gen_shipped_policy()
+    gen_multiday_tables()
     for f in sorted(os.listdir(HERE)):
         print("%9d  %s" % (os.path.getsize(os.path.join(HERE, f)), f))

@@ -202,6 +202,27 @@ def test_variants_sampled_vs_oracle(kw, precision):
     env.close()
 
 
+@pytest.mark.parametrize("cycle", [False, True])
+@pytest.mark.parametrize("precision", ["float32", "float64"])
+def test_multiday_pv_vs_oracle(cycle, precision):
+    """NUMBER_OF_DAYS_TO_PREDICT = 2 (envs/smart_nanogrid_environment.py:51, pv_system_manager.py:10-65):
+    the reference-faithful form (three days loaded and normalised, day 0 read) runs the specialised kernel; with
+    cycle_pv_days episode k reads day k % 2 (generic kernel) -- three episodes cover both days and the wrap."""
+    from oracle.oracle import OracleBatch
+    seed, E = 78, 512
+    env = _env(E, precision, seed=seed, number_of_chargers=10, number_of_days_to_predict=2, cycle_pv_days=cycle)
+    cfg = env.cfg
+    assert cfg.irr.shape[0] == 3 * cfg.n_steps
+    ob = OracleBatch(cfg, E, n_threads=8)
+    obs0 = env.reset().cpu().numpy()
+    ob.sample(seed, 0, 0)
+    assert np.allclose(obs0, ob.observe(), rtol=1e-5, atol=1e-6)
+    _lockstep(env, ob, cfg, 2 * cfg.n_steps + 7, np.random.default_rng(6), seed, f64=precision == "float64")
+    assert np.all(ob.pv_base == 0)      # episode 2: day 0 again (2 % 2), or never left it
+    assert env.error_flags() == 0
+    env.close()
+
+
 def test_sampler_matches_cpu_mirror_bit_exact():
     """sng_sample_plan (GPU, Philox4x32-10) == oracle mirror, record for record; and the in-step lazy
     sampler follows the same plan (covered by the lockstep tests)."""

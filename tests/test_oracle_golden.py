@@ -206,3 +206,49 @@ def test_philox_known_answers():
     assert [hex(x) for x in philox4x32_10([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344],
                                           [0xa4093822, 0x299f31d0])] == \
         ["0xd16cfe09", "0x94fdcceb", "0x5001e420", "0x24126ea1"]
+
+
+def test_multiday_pv_tables_match_reference():
+    """NUMBER_OF_DAYS_TO_PREDICT > 1 (envs/smart_nanogrid_environment.py:51 -> PVSystemManager(days, dt),
+    utils/pv_system_manager.py:10-65): the flat (days + 1)-day series, its maximum and the PV power equal the
+    reference's, and row d of its `solar_irradiance_2` is the window [d * T, (d + 2) * T) of the flat series."""
+    z = np.load(os.path.join(GOLD, "ref_tables_multiday.npz"))
+    for ti in ("1h", "2h"):
+        cfg = NanogridConfig(number_of_chargers=4, time_interval=ti, charging_mode="bounded",
+                             vehicle_uncharged_penalty_mode="sparse", number_of_days_to_predict=2)
+        k, T = "%s_d2_" % ti, cfg.n_steps
+        assert cfg.pv_days == 2 and cfg.irr.shape[0] == 3 * T
+        assert np.array_equal(cfg.irr, z[k + "irr_flat"]) and cfg.irr_max == float(z[k + "irr_max"])
+        assert np.array_equal(cfg.pv_power, z[k + "pv_power"])
+        rows = z[k + "irr_rows"]
+        assert rows.shape == (2, 2 * T)
+        for d in range(2):
+            assert np.array_equal(rows[d], cfg.irr[d * T:(d + 2) * T])
+        assert cfg.price.shape[0] >= 3 * T and np.array_equal(cfg.price[:T], cfg.price[2 * T:3 * T])
+        # one-day tables are a prefix: the first two days do not depend on how many days are loaded
+        one = NanogridConfig(number_of_chargers=4, time_interval=ti, charging_mode="bounded",
+                             vehicle_uncharged_penalty_mode="sparse")
+        assert np.array_equal(one.irr, cfg.irr[:2 * T]) and np.array_equal(one.pv_power, cfg.pv_power[:2 * T])
+    with pytest.raises(ValueError):
+        NanogridConfig(number_of_chargers=4, time_interval="1h", number_of_days_to_predict=3)   # the file holds 3 days
+
+
+def test_oracle_cycles_pv_days():
+    """cycle_pv_days (extension): episode k of the oracle reads day k % D of the PV tables -- solar power and
+    the irradiance entries of the observation; the reference-faithful default keeps day 0."""
+    kw = dict(number_of_chargers=4, time_interval="1h", charging_mode="bounded", vehicle_uncharged_penalty_mode="sparse",
+              number_of_days_to_predict=2)
+    for cyc in (False, True):
+        cfg = NanogridConfig(cycle_pv_days=cyc, **kw)
+        ob = OracleBatch(cfg, 3)
+        T = cfg.n_steps
+        for episode in range(3):
+            ob.sample(5, 0, episode)
+            base = (episode % 2) * T if cyc else 0
+            assert np.all(ob.pv_base == base)
+            irr = lambda t: (cfg.irr_norm[base + t + np.arange(4)] * ob.pv_shift[:, None]).astype(np.float32)  # noqa: E731
+            assert np.array_equal(ob.observe()[:, [0, 2, 3, 4]], irr(0))
+            for t in range(T):
+                obs, r, d, pw, dg = ob.step(np.zeros((3, cfg.act_dim)), want_diag=True)
+                assert np.array_equal(obs[:, [0, 2, 3, 4]], irr(t))      # the step's observation is taken before t += 1 (Q5)
+                assert np.array_equal(dg["solar"], cfg.pv_power[base + t] * ob.pv_shift)
