@@ -228,6 +228,17 @@ int sng_policy_forward_packed(const void *packed, int obs_dim, int act_dim, cons
                               const float *low, const float *high, float *raw_actions, float *actions, float *values,
                               float *log_probs, int64_t n_envs, void *stream);
 
+/* The same forward pass with the exploration noise drawn INSIDE the kernel (no noise tensor, no separate RNG launch per
+ * rollout step): z ~ N(0, 1) per (env, action) from Philox4x32-10 keyed by (seed, step), counter = (env_gid0 + env,
+ * action / 4) and Box-Muller, so a sharded rollout draws the same noise as an unsharded one.  step = *step_counter (a
+ * DEVICE word, so that a captured CUDA graph advances between replays: add the rollout length to it after each rollout)
+ * + step_offset (the position inside the rollout).  noise_out (optional, [E][act_dim]) receives the z that were used.
+ * Reference caller: SB3's DiagGaussianDistribution.sample() inside PPO.collect_rollouts (solvers/RL/ppo_train.py:89-102). */
+int sng_policy_forward_sampled(const void *packed, int obs_dim, int act_dim, const float *obs, uint64_t seed,
+                               const uint64_t *step_counter, uint64_t step_offset, uint64_t env_gid0, const float *low,
+                               const float *high, float *raw_actions, float *actions, float *values, float *log_probs,
+                               float *noise_out, int64_t n_envs, void *stream);
+
 /* Launches an EMPTY kernel on `stream`: lets a caller measure the device's kernel-to-kernel launch latency (the
  * floor under one sng_step per step for batches that live in L2; bench.py reports it beside those numbers). */
 int sng_null_launch(void *stream);

@@ -74,7 +74,7 @@ template <typename real> struct Params {
     int i4, i10, i1;  // int(4/dt), int(10/dt), int(1/dt): charging_station.py:271-279
     int off_soc, off_dep, off_batt;
     int max_togo;     // penalty-check window: 0 none, 1 on_departure, 3 sparse, 1<<20 dense
-    int pv_days;      // 1 (the reference), or D > 1: episode k reads the PV tables at offset (k % D) * T (generic kernel only)
+    int pv_days;      // 1 (the reference), or D > 1: episode k reads the PV tables at offset (k % D) * T (ND == 0 kernels only)
     int has_req;      // 0: every vehicle requests SoC 1.0 (sampling without enable_requested_state_of_charge): the
                       //    requested-SoC plane is neither read nor written
     real dt, ev_pmax, ev_eff, b_cap, b_pmax, b_eff, b_dod, b_soc0, sell, cost_w, batt_w, margin;
@@ -287,10 +287,11 @@ template <int NCT, int ND> struct Offsets {
 
 // Offset of the episode's day in the PV tables.  The reference always reads row 0 of solar_irradiance_2
 // (pv_system_manager.py:81-91); with pv_days = D > 1 episode k reads day k % D of the (D + 1)-day series.  Only the
-// generic instantiation (NCT == 0) supports it: the dispatch keeps such configurations off the specialised kernels.
-template <int NCT, typename real> __device__ __forceinline__ int pv_day_offset(const Params<real> &p, uint32_t episode)
+// instantiations with runtime observation offsets (ND == 0) support it: the dispatch keeps such configurations off
+// the kernels specialised for the reference's observation shape.
+template <int ND, typename real> __device__ __forceinline__ int pv_day_offset(const Params<real> &p, uint32_t episode)
 {
-    return (NCT == 0 && p.pv_days > 1) ? (int)(episode % (uint32_t)p.pv_days) * p.T : 0;
+    return (ND == 0 && p.pv_days > 1) ? (int)(episode % (uint32_t)p.pv_days) * p.T : 0;
 }
 
 // Env-level part of the observation (envs/smart_nanogrid_environment.py:197-205,
@@ -347,7 +348,7 @@ __device__ __forceinline__ void begin_episode(const Params<real> &p, int N, long
         obs[off_soc + i] = present ? (float)v.soc0 : 0.0f;
         obs[off_dep + i] = present ? dep_lookup<SMEM>(p, dep_base, (int)((v.hdr >> 8) & 0xFFu)) : 0.0f;
     }
-    if (L == 1 || sub == 0) write_obs_env<real, NCT, ND>(p, obs, 0, shift, soc_b, pv_day_offset<NCT>(p, episode));   // battery SoC survives resets (quirk Q8)
+    if (L == 1 || sub == 0) write_obs_env<real, NCT, ND>(p, obs, 0, shift, soc_b, pv_day_offset<ND>(p, episode));   // battery SoC survives resets (quirk Q8)
 }
 
 // Spots whose state loads are issued together (and, in the pipelined kernel, one block ahead).
@@ -617,7 +618,7 @@ __device__ __forceinline__ Arrivals env_step(const Params<real> &p, long long e,
     const real pen_veh = pen_e + pen_o;
     const real total_power = pos + neg;                                   // :105
     if (total_power < (real)0 && !p.v2x) err |= FLAG_NEG_DEMAND;          // reference raises, :158-159
-    const int pvo = pv_day_offset<NCT>(p, episode);
+    const int pvo = pv_day_offset<ND>(p, episode);
     const real solar = p.pv ? __ldg(p.pv_power + pvo + t) * es.pv_shift : (real)0;   // :99-103
     real rem = total_power - solar;                                       // :167
     real soc_b = es.soc_b, batt_power = 0, pen_b = 0;

@@ -230,6 +230,9 @@ __global__ void __launch_bounds__(SNG_STEP_MAXT, (EXACT || NCT / L > 32) ? 2 : (
             if (tma_store && lane == 0) bulk_wait_read<0>();
             __syncwarp();
         }
+        // the state loads go first: they have the longest way (DRAM), and every instruction ahead of them is time
+        // the warp holds its slot with nothing in flight
+        if (valid) load_state<real, NCT / L, L>(p, e, spot, st);
         if (tma_load) {
             if (lane == 0) {
                 if (s == 0) {
@@ -246,7 +249,6 @@ __global__ void __launch_bounds__(SNG_STEP_MAXT, (EXACT || NCT / L > 32) ? 2 : (
                 if (k < act_vec) areg[j] = reinterpret_cast<const float4 *>(act_g)[k];
             }
         }
-        if (valid) load_state<real, NCT / L, L>(p, e, spot, st);
         if (s == 0) publish_dep_table(p);     // CTA barrier; also orders the mbarrier init before the other lanes' waits
         if (!active) return;
         // ---- action rows into shared memory ----
@@ -290,8 +292,22 @@ __global__ void __launch_bounds__(SNG_STEP_MAXT, (EXACT || NCT / L > 32) ? 2 : (
             __syncwarp();
             const float4 *src = reinterpret_cast<const float4 *>(obs_s);
             float4 *dst = reinterpret_cast<float4 *>(obs_g);
+            if (NCT && ND) {
+                // D = ND + 2 NCT (+ 1 with a battery): the trip count is known up to the tail, so the loop is
+                // straight-line code with one predicated store at the end (a runtime bound costs a peeled
+                // remainder loop that only some lanes take)
+                constexpr int DV0 = (EPW / 4) * (ND + 2 * NCT), FULL = DV0 / 32;
+#pragma unroll
+                for (int j = 0; j < FULL; ++j) dst[lane + 32 * j] = src[lane + 32 * j];
+#pragma unroll
+                for (int j = FULL; j < FULL + 2; ++j) {
+                    const int k = lane + 32 * j;
+                    if (k < (EPW / 4) * D) dst[k] = src[k];
+                }
+            } else {
 #pragma unroll 4
-            for (int k = lane; k < (EPW / 4) * D; k += 32) dst[k] = src[k];
+                for (int k = lane; k < (EPW / 4) * D; k += 32) dst[k] = src[k];
+            }
             if (MULTI) __syncwarp();
         } else {
             __syncwarp();
@@ -723,6 +739,18 @@ public:
                 case 10: return launch_step_n<10, 8>(q, actions, obs, reward, done, n_steps, bulk, st);
                 case 32: return launch_step_n<32, 8>(q, actions, obs, reward, done, n_steps, bulk, st);
                 case 64: return launch_step_n<64, 8>(q, actions, obs, reward, done, n_steps, bulk, st);
+                default: break;
+                }
+            }
+            // the same station sizes with any other observation shape (forecast horizon != 3, no PV, multi-day PV):
+            // compile-time spot count, observation offsets read from the parameters
+            if (!use_generic) {
+                switch (q.N) {
+                case 4: return launch_step_n<4, 0>(q, actions, obs, reward, done, n_steps, bulk, st);
+                case 8: return launch_step_n<8, 0>(q, actions, obs, reward, done, n_steps, bulk, st);
+                case 10: return launch_step_n<10, 0>(q, actions, obs, reward, done, n_steps, bulk, st);
+                case 32: return launch_step_n<32, 0>(q, actions, obs, reward, done, n_steps, bulk, st);
+                case 64: return launch_step_n<64, 0>(q, actions, obs, reward, done, n_steps, bulk, st);
                 default: break;
                 }
             }

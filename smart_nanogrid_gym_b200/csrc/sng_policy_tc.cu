@@ -168,6 +168,13 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16])
         : "r"(taddr)
         : "memory");
 }
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t (&v)[4])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3])
+                 : "r"(taddr)
+                 : "memory");
+}
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32])
 {
     asm volatile(
@@ -280,6 +287,33 @@ __device__ __forceinline__ void tanh2_split(uint32_t &a, uint32_t &b, uint32_t &
     lo_a = __float_as_uint(l.x); lo_b = __float_as_uint(l.y);
 }
 
+// ---- in-kernel exploration noise: Philox4x32-10 (Salmon et al., SC'11) keyed by (seed, step), counter = (global env, column
+//      block); one block yields the four standard normals of a thread's four action columns (Box-Muller) ----
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t (&out)[4])
+{
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+// u in (0, 1): 24 random bits, centred; z0 = sqrt(-2 ln u1) cos(2 pi u2), z1 = ... sin(2 pi u2)
+__device__ __forceinline__ void box_muller(uint32_t x1, uint32_t x2, float &z0, float &z1)
+{
+    const float u1 = ((float)(x1 >> 8) + 0.5f) * 5.9604644775390625e-08f;
+    const float u2 = ((float)(x2 >> 8) + 0.5f) * 5.9604644775390625e-08f;
+    const float r = sqrtf(-2.0f * __logf(u1));
+    float sn, cs;
+    __sincosf(6.283185307179586f * u2, &sn, &cs);
+    z0 = r * cs;
+    z1 = r * sn;
+}
+
 __device__ __forceinline__ void compute_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(THREADS) : "memory"); }
 
 // hidden-layer epilogue of one warp: 16 accumulator columns [src, src + 16) of its 32 lanes -> tanh -> hi part written back
@@ -299,7 +333,7 @@ __device__ __forceinline__ void tanh_epilogue(uint32_t src, uint32_t dst_lo)
 
 struct Smem {
     // byte offsets into dynamic shared memory
-    uint32_t obs_stage, row_stage, stages, bars;
+    uint32_t obs_stage, row_stage, stages, consts, lp, bars;
 };
 __host__ __device__ inline Smem smem_plan(int D, int A)
 {
@@ -307,7 +341,9 @@ __host__ __device__ inline Smem smem_plan(int D, int A)
     s.obs_stage = align128((uint32_t)(TILE * D * sizeof(float)));
     s.row_stage = align128((uint32_t)(TILE * A * sizeof(float)));
     s.stages = align128(IMG_SMEM_BYTES);                                // obs x 2 | noise | raw actions | clipped actions
-    s.bars = s.stages + 2 * s.obs_stage + 3 * s.row_stage;
+    s.consts = s.stages + 2 * s.obs_stage + 3 * s.row_stage;      // std | log_std | low | high, 16 floats each
+    s.lp = s.consts + 4 * NH * (uint32_t)sizeof(float);           // partial log-probabilities [CB][TILE]
+    s.bars = s.lp + CB * TILE * (uint32_t)sizeof(float);
     return s;
 }
 
@@ -350,7 +386,9 @@ __device__ __forceinline__ void issue_phase(int phase, uint32_t tn, uint32_t x, 
 __global__ void __launch_bounds__(THREADS + 32, 1)
     policy_tc_kernel(const float *__restrict__ img, const float *__restrict__ obs, const float *__restrict__ noise,
                      const float *__restrict__ low, const float *__restrict__ high, float *raw_actions, float *actions,
-                     float *values, float *log_probs, long long n_envs, int D, int A, int aligned, long long *trace)
+                     float *values, float *log_probs, long long n_envs, int D, int A, int aligned, long long *trace,
+                     const unsigned long long *rng_step, unsigned long long rng_offset, unsigned long long rng_seed,
+                     unsigned long long rng_gid0, float *noise_out)
 {
     int tr = 0;
 #define TRACE() do { if (trace && blockIdx.x == 0 && threadIdx.x == 0 && tr < 64) trace[tr++] = clock64(); } while (0)
@@ -365,6 +403,8 @@ __global__ void __launch_bounds__(THREADS + 32, 1)
     float *noise_s = reinterpret_cast<float *>(smem + sp.stages + 2 * sp.obs_stage);
     float *raw_s = reinterpret_cast<float *>(smem + sp.stages + 2 * sp.obs_stage + sp.row_stage);
     float *act_s = reinterpret_cast<float *>(smem + sp.stages + 2 * sp.obs_stage + 2 * sp.row_stage);
+    float *const_s = reinterpret_cast<float *>(smem + sp.consts);
+    float *lp_s = reinterpret_cast<float *>(smem + sp.lp);
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + sp.bars);
     uint64_t *wbar = bars;                                  // [3] weight image: critic layer 0 | rest of the critic | actor
     uint64_t *obar = bars + 3;                              // [2] observation rows of the even / odd tiles have landed
@@ -391,6 +431,12 @@ __global__ void __launch_bounds__(THREADS + 32, 1)
                 bulk_g2s(smem + off, reinterpret_cast<const unsigned char *>(img) + off, n, wbar + piece);
             }
         }
+    }
+    if (threadIdx.x >= 64 && threadIdx.x < 64 + 4 * NH && actions != nullptr) {   // per-action constants of the sampling epilogue
+        const int q = (threadIdx.x - 64) / NH, a = (threadIdx.x - 64) % NH;
+        float v = 0.f;
+        if (a < A) v = q == 0 ? img[OFF_STD + a] : (q == 1 ? img[OFF_STD + 16 + a] : (q == 2 ? low[a] : high[a]));
+        const_s[q * NH + a] = v;
     }
     if (warp == 0) tmem_alloc(tmem_slot, 512);
     tc_fence_before();
@@ -441,9 +487,10 @@ __global__ void __launch_bounds__(THREADS + 32, 1)
         const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16);   // ... as seen by this warp's 32 lanes
         const uint32_t tc = tlane + C_NET0, ta = tc + C_NETSTRIDE;           // critic / actor regions
         const uint32_t obs_bytes = (uint32_t)(TILE * D * sizeof(float)), row_bytes = (uint32_t)(TILE * A * sizeof(float));
-        const bool sample = !value_only && noise != nullptr;
+        const bool rng = !value_only && noise == nullptr && rng_step != nullptr;      // in-kernel Gaussian noise
+        const bool sample = !value_only && noise != nullptr;                         // caller-supplied noise rows
+        const unsigned long long step = rng ? *rng_step + rng_offset : 0ull;
         uint32_t n_phase = 0, mc_phase = 0, ma_phase = 0;
-        bool stores_pending = false;
         auto tile_full = [&](long long tile) { return aligned && tile < n_tiles && (n_envs - tile * TILE) >= TILE; };
         // copy-engine fetch of a whole tile's observation rows into stage `buf` (thread 0)
         auto fetch_obs = [&](long long tile, int buf) {
@@ -512,7 +559,6 @@ __global__ void __launch_bounds__(THREADS + 32, 1)
                 tc_fence_after();
                 TRACE();
                 tanh_epilogue(tc + src + 16 * cb, tc + C_Q + 16 * cb);
-                if (layer == 0 && threadIdx.x == 0 && stores_pending) bulk_wait_read<0>();   // before anyone restages action rows
                 tc_fence_before();
                 mbar_arrive(rbar);
                 TRACE();
@@ -550,38 +596,66 @@ __global__ void __launch_bounds__(THREADS + 32, 1)
                 tc_fence_after();
                 TRACE();
                 __syncwarp();
-                if (cb == 1) {                     // DiagGaussian sample, clip to the Box, log-probability
-                    uint32_t out[16];
-                    tmem_ld16(xb + 48, out);
+                // DiagGaussian sample, clip to the Box, log-probability: the four warps that share a row block split the
+                // action columns (4 each), so the work ahead of the tile's last barrier is a quarter of a full row
+                const int a0 = 4 * cb;
+                if (a0 < A) {                      // warp-uniform
+                    uint32_t out[4];
+                    tmem_ld4(xb + 48 + a0, out);
                     tmem_wait_ld();
                     if (sample && full) mbar_wait(nbar, n_phase);
+                    float zz[4] = {0.f, 0.f, 0.f, 0.f};
+                    if (rng) {
+                        const unsigned long long gid = rng_gid0 + (unsigned long long)(e0 + t);
+                        uint32_t x[4];
+                        philox4x32_10((uint32_t)gid, (uint32_t)(gid >> 32), (uint32_t)cb, (uint32_t)step, (uint32_t)rng_seed,
+                                      (uint32_t)(rng_seed >> 32) ^ (uint32_t)(step >> 32), x);
+                        box_muller(x[0], x[1], zz[0], zz[1]);
+                        box_muller(x[2], x[3], zz[2], zz[3]);
+                    }
                     float lp = 0.f;
 #pragma unroll
-                    for (int a = 0; a < NH; ++a) {
+                    for (int j = 0; j < 4; ++j) {
+                        const int a = a0 + j;
                         if (a < A) {
-                            const float sd = __ldg(img + OFF_STD + a), ls = __ldg(img + OFF_STD + 16 + a);
-                            const float z = sample ? noise_s[t * A + a] : 0.f;
-                            const float x = fmaf(z, sd, __uint_as_float(out[a]));
+                            const float sd = const_s[a], ls = const_s[NH + a];
+                            const float z = sample ? noise_s[t * A + a] : zz[j];
+                            if (rng && noise_out && t < nv) noise_out[(e0 + t) * A + a] = z;
+                            const float x = fmaf(z, sd, __uint_as_float(out[j]));
                             raw_s[t * A + a] = x;
-                            act_s[t * A + a] = fminf(fmaxf(x, __ldg(low + a)), __ldg(high + a));   // SB3 clips Box actions before env.step
-                            lp += -0.5f * z * z - ls - 0.91893853320467274f;                        // log N(x; mean, std)
+                            act_s[t * A + a] = fminf(fmaxf(x, const_s[2 * NH + a]), const_s[3 * NH + a]);   // SB3 clips Box actions before env.step
+                            lp += -0.5f * z * z - ls - 0.91893853320467274f;                              // log N(x; mean, std)
                         }
                     }
-                    if (t < nv) log_probs[e0 + t] = lp;
+                    lp_s[cb * TILE + t] = lp;
                 }
                 if (sample && full) n_phase ^= 1u;
+                const int n_parts = (A + 3) / 4;
                 if (full) {
-                    fence_proxy_async();
+                    // the two row slabs leave as coalesced 16-byte stores by all compute threads (a copy-engine store
+                    // issued by one thread held that thread -- and with it the next tile's first barrier -- for ~0.9 us)
                     compute_barrier();
                     TRACE();
-                    if (threadIdx.x == 0) {
-                        bulk_s2g(raw_actions + e0 * A, raw_s, row_bytes);
-                        bulk_s2g(actions + e0 * A, act_s, row_bytes);
-                        bulk_commit();
+                    if (cb == 0) {
+                        float lp = lp_s[t];
+                        for (int q = 1; q < n_parts; ++q) lp += lp_s[q * TILE + t];
+                        log_probs[e0 + t] = lp;
                     }
-                    stores_pending = true;
+                    const int nvec = (int)(row_bytes / 16);
+                    const float4 *rs = reinterpret_cast<const float4 *>(raw_s), *as = reinterpret_cast<const float4 *>(act_s);
+                    float4 *rg = reinterpret_cast<float4 *>(raw_actions + e0 * A), *ag = reinterpret_cast<float4 *>(actions + e0 * A);
+                    for (int k = threadIdx.x; k < 2 * nvec; k += THREADS) {
+                        if (k < nvec) rg[k] = rs[k];
+                        else ag[k - nvec] = as[k - nvec];
+                    }
+                    TRACE();
                 } else {
                     compute_barrier();
+                    if (cb == 0 && t < nv) {
+                        float lp = lp_s[t];
+                        for (int q = 1; q < n_parts; ++q) lp += lp_s[q * TILE + t];
+                        log_probs[e0 + t] = lp;
+                    }
                     for (int k = threadIdx.x; k < nv * A; k += THREADS) {
                         raw_actions[e0 * A + k] = raw_s[k];
                         actions[e0 * A + k] = act_s[k];
@@ -590,7 +664,6 @@ __global__ void __launch_bounds__(THREADS + 32, 1)
             }
             tc_fence_before();
         }
-        if (threadIdx.x == 0 && stores_pending) bulk_wait_read<0>();
     }
     tc_fence_before();
     __syncthreads();
@@ -644,9 +717,11 @@ extern "C" int sng_policy_pack(const sng_mlp *mlp, void *packed, void *stream)
     return cudaGetLastError() == cudaSuccess ? SNG_OK : SNG_ERR_CUDA;
 }
 
-extern "C" int sng_policy_forward_packed(const void *packed, int obs_dim, int act_dim, const float *obs, const float *noise,
-                                         const float *low, const float *high, float *raw_actions, float *actions,
-                                         float *values, float *log_probs, int64_t n_envs, void *stream)
+namespace {
+int launch_policy_tc(const void *packed, int obs_dim, int act_dim, const float *obs, const float *noise, const float *low,
+                     const float *high, float *raw_actions, float *actions, float *values, float *log_probs, int64_t n_envs,
+                     const unsigned long long *rng_step, unsigned long long rng_offset, unsigned long long rng_seed,
+                     unsigned long long rng_gid0, float *noise_out, void *stream)
 {
     if (!packed || !obs || !values || n_envs < 1) return SNG_ERR_ARG;
     if (actions && (!raw_actions || !log_probs || !low || !high)) return SNG_ERR_ARG;
@@ -665,6 +740,26 @@ extern "C" int sng_policy_forward_packed(const void *packed, int obs_dim, int ac
     if (!aligned16(packed)) return SNG_ERR_ARG;
     policy_tc_kernel<<<(unsigned)grid, THREADS + 32, smem, (cudaStream_t)stream>>>(reinterpret_cast<const float *>(packed), obs, noise, low, high,
                                                                              raw_actions, actions, values, log_probs,
-                                                                             (long long)n_envs, obs_dim, act_dim, aligned, g_trace);
+                                                                             (long long)n_envs, obs_dim, act_dim, aligned, g_trace,
+                                                                             rng_step, rng_offset, rng_seed, rng_gid0, noise_out);
     return cudaGetLastError() == cudaSuccess ? SNG_OK : SNG_ERR_CUDA;
+}
+}  // namespace
+
+extern "C" int sng_policy_forward_packed(const void *packed, int obs_dim, int act_dim, const float *obs, const float *noise,
+                                         const float *low, const float *high, float *raw_actions, float *actions,
+                                         float *values, float *log_probs, int64_t n_envs, void *stream)
+{
+    return launch_policy_tc(packed, obs_dim, act_dim, obs, noise, low, high, raw_actions, actions, values, log_probs, n_envs,
+                            nullptr, 0ull, 0ull, 0ull, nullptr, stream);
+}
+
+extern "C" int sng_policy_forward_sampled(const void *packed, int obs_dim, int act_dim, const float *obs, uint64_t seed,
+                                          const uint64_t *step_counter, uint64_t step_offset, uint64_t env_gid0,
+                                          const float *low, const float *high, float *raw_actions, float *actions,
+                                          float *values, float *log_probs, float *noise_out, int64_t n_envs, void *stream)
+{
+    if (!step_counter || !actions) return SNG_ERR_ARG;
+    return launch_policy_tc(packed, obs_dim, act_dim, obs, nullptr, low, high, raw_actions, actions, values, log_probs, n_envs,
+                            reinterpret_cast<const unsigned long long *>(step_counter), step_offset, seed, env_gid0, noise_out, stream);
 }

@@ -127,11 +127,14 @@ class MlpPolicy(nn.Module):
 
     @torch.no_grad()
     def fused_forward(self, obs, noise, low, high, raw_actions, actions, values, log_probs, repack: bool = True,
-                      cuda_cores: bool = False):
+                      cuda_cores: bool = False, rng=None, noise_out=None):
         """One launch: values, sampled + clipped actions and log-probs written into the given [E, ...] buffers
         (noise None = deterministic; actions None = values only).  Inference only (no autograd graph).
         repack=False reuses the weight image of the last pack_weights() (weights unchanged since);
-        cuda_cores=True runs the FP32 CUDA-core kernel instead of the tensor-core one."""
+        cuda_cores=True runs the FP32 CUDA-core kernel instead of the tensor-core one.
+        rng=(seed, step_counter, step_offset, env_gid0) draws the noise inside the kernel (sng_policy_forward_sampled:
+        Philox keyed by seed and step = step_counter[0] + step_offset, step_counter a one-element int64 CUDA tensor);
+        noise_out [E, A] then optionally receives the standard normals that were used."""
         p = lambda t: None if t is None else C.c_void_p(t.data_ptr())  # noqa: E731
         stream = C.c_void_p(torch.cuda.current_stream(obs.device).cuda_stream)
         if cuda_cores:
@@ -141,6 +144,14 @@ class MlpPolicy(nn.Module):
             return
         if repack or getattr(self, "_packed", None) is None:
             self.pack_weights()
+        if rng is not None:
+            seed, counter, offset, gid0 = rng
+            assert noise is None and counter.dtype == torch.int64 and counter.is_cuda and counter.numel() == 1
+            nat.check(nat.lib().sng_policy_forward_sampled(p(self._packed), self.pi[0].in_features, self.action_net.out_features,
+                                                           p(obs), int(seed) & (2 ** 64 - 1), p(counter), int(offset), int(gid0),
+                                                           p(low), p(high), p(raw_actions), p(actions), p(values), p(log_probs),
+                                                           p(noise_out), obs.shape[0], stream))
+            return
         nat.check(nat.lib().sng_policy_forward_packed(p(self._packed), self.pi[0].in_features, self.action_net.out_features,
                                                       p(obs), p(noise), p(low), p(high), p(raw_actions), p(actions),
                                                       p(values), p(log_probs), obs.shape[0], stream))
@@ -158,8 +169,11 @@ class RolloutBuffer:
         self.actions = z(n_steps, n_envs, act_dim)            # what the env executed (clipped to the Box)
         self.raw_actions = z(n_steps, n_envs, act_dim)        # what the policy sampled (SB3 stores these)
         self.rewards = z(n_steps, n_envs)
-        self.dones = z(n_steps, n_envs, dtype=torch.uint8)
-        self.episode_starts = z(n_steps, n_envs, dtype=torch.uint8)
+        # episode_starts[s + 1] IS dones[s] (SB3 carries `_last_episode_starts = dones`): two views of one
+        # [n_steps + 1, E] array, so the step kernel's done flags land in both without a copy per step
+        self._flags = z(n_steps + 1, n_envs, dtype=torch.uint8)
+        self.episode_starts = self._flags[:n_steps]
+        self.dones = self._flags[1:]
         self.values = z(n_steps, n_envs)
         self.log_probs = z(n_steps, n_envs)
         self.advantages = z(n_steps, n_envs)
@@ -180,31 +194,42 @@ class RolloutBuffer:
 
 @torch.no_grad()
 def collect_rollout(env, policy: MlpPolicy, buf: RolloutBuffer, obs: torch.Tensor, episode_starts: torch.Tensor,
-                    generator: torch.Generator | None = None, deterministic: bool = False, fused: bool = True):
+                    generator: torch.Generator | None = None, deterministic: bool = False, fused: bool = True,
+                    rng_seed: int | None = None):
     """SB3 OnPolicyAlgorithm.collect_rollouts for a BatchedSmartNanogridEnv: n_steps policy + env steps,
     then GAE.  `obs` [E, D] is the current observation (from reset() or the previous rollout),
-    `episode_starts` [E] u8.  Returns (last_obs, last_dones) to carry into the next call."""
+    `episode_starts` [E] u8.  Returns (last_obs, last_dones) to carry into the next call.
+    Exploration noise: torch.randn (with `generator`) per step, or -- `rng_seed` given, fused kernel -- drawn inside
+    the policy kernel (Philox keyed by rng_seed and the policy's step counter: no noise tensor, no RNG launch)."""
     low, high = env.action_low.float(), env.action_high.float()
     buf.observations[0].copy_(obs)
-    starts = episode_starts.to(torch.uint8)
+    buf.episode_starts[0].copy_(episode_starts.to(torch.uint8))    # episode_starts[s + 1] aliases dones[s]
     fused = fused and policy.fused_supported()
+    in_kernel_noise = fused and not deterministic and rng_seed is not None
     if fused:
         policy.pack_weights()          # once per rollout: the weights do not change while it is collected
+    if in_kernel_noise and (getattr(policy, "rng_counter", None) is None or policy.rng_counter.device != obs.device):
+        policy.rng_counter = torch.zeros(1, dtype=torch.int64, device=obs.device)   # rollout steps drawn so far
     for s in range(buf.n_steps):
         o = buf.observations[s]
-        noise = None if deterministic else torch.randn(buf.n_envs, buf.actions.shape[2], device=o.device, generator=generator)
-        if fused:      # one kernel: both networks, heads, sampling, clipping, log-probs, straight into the buffer slabs
-            policy.fused_forward(o, noise, low, high, buf.raw_actions[s], buf.actions[s], buf.values[s], buf.log_probs[s], repack=False)
+        if in_kernel_noise:
+            policy.fused_forward(o, None, low, high, buf.raw_actions[s], buf.actions[s], buf.values[s], buf.log_probs[s],
+                                 repack=False, rng=(rng_seed, policy.rng_counter, s, env.env_gid0))
         else:
-            a, v, lp = policy(o, noise)
-            buf.raw_actions[s].copy_(a)
-            torch.clamp(a, low, high, out=buf.actions[s])      # SB3 clips Box actions before env.step
-            buf.values[s].copy_(v)
-            buf.log_probs[s].copy_(lp)
-        buf.episode_starts[s].copy_(starts)
-        # the kernel writes the next observation, the reward and the done flag into the buffer slabs
+            noise = None if deterministic else torch.randn(buf.n_envs, buf.actions.shape[2], device=o.device, generator=generator)
+            if fused:      # one kernel: both networks, heads, sampling, clipping, log-probs, straight into the buffer slabs
+                policy.fused_forward(o, noise, low, high, buf.raw_actions[s], buf.actions[s], buf.values[s], buf.log_probs[s], repack=False)
+            else:
+                a, v, lp = policy(o, noise)
+                buf.raw_actions[s].copy_(a)
+                torch.clamp(a, low, high, out=buf.actions[s])      # SB3 clips Box actions before env.step
+                buf.values[s].copy_(v)
+                buf.log_probs[s].copy_(lp)
+        # the kernel writes the next observation, the reward and the done flag (= the next step's episode start)
+        # into the buffer slabs
         env.step(buf.actions[s], out=(buf.observations[s + 1], buf.rewards[s], buf.dones[s]))
-        starts = buf.dones[s]
+    if in_kernel_noise:
+        policy.rng_counter += buf.n_steps
     last_obs = buf.observations[buf.n_steps]
     if fused:
         policy.fused_forward(last_obs, None, None, None, None, None, buf.last_values, None, repack=False)
@@ -217,9 +242,11 @@ def collect_rollout(env, policy: MlpPolicy, buf: RolloutBuffer, obs: torch.Tenso
 class GraphedRollout:
     """collect_rollout captured ONCE in a CUDA graph (n_steps x [policy MLP, clip, step kernel] + GAE) and
     replayed: at 65,536 envs the eager loop is bound by ~20 small launches per step, the graph is not.
-    Sampling noise comes from torch's default CUDA generator (graph-safe); `deterministic=True` uses the mean."""
+    Sampling noise is drawn inside the policy kernel (rng_seed; the step counter is a device word the graph advances),
+    or -- rng_seed=None -- by torch's default CUDA generator (graph-safe); `deterministic=True` uses the mean."""
 
-    def __init__(self, env, policy: MlpPolicy, buf: RolloutBuffer, deterministic: bool = False, fused: bool = True):
+    def __init__(self, env, policy: MlpPolicy, buf: RolloutBuffer, deterministic: bool = False, fused: bool = True,
+                 rng_seed: int | None = 0):
         dev = buf.rewards.device
         self.env, self.policy, self.buf = env, policy, buf
         self.obs_in = torch.zeros(buf.n_envs, buf.observations.shape[2], device=dev)
@@ -228,12 +255,12 @@ class GraphedRollout:
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):                     # warm-up outside capture (lazy inits, cuBLAS workspaces)
             self.obs_in.copy_(env.obs)
-            collect_rollout(env, policy, buf, self.obs_in, self.starts_in, deterministic=deterministic, fused=fused)
+            collect_rollout(env, policy, buf, self.obs_in, self.starts_in, deterministic=deterministic, fused=fused, rng_seed=rng_seed)
         torch.cuda.current_stream(dev).wait_stream(side)
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.last_obs, self.last_dones = collect_rollout(env, policy, buf, self.obs_in, self.starts_in,
-                                                             deterministic=deterministic, fused=fused)
+                                                             deterministic=deterministic, fused=fused, rng_seed=rng_seed)
 
     def __call__(self, obs: torch.Tensor, episode_starts: torch.Tensor):
         self.obs_in.copy_(obs)

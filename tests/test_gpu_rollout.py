@@ -169,6 +169,80 @@ def test_fused_policy_kernel_matches_torch_modules(n_spots, obs_dim, act_dim):
     assert torch.allclose(raw_d, mean_ref, rtol=1e-4, atol=2e-5) and torch.allclose(lp_d, lp0_ref, rtol=1e-5, atol=1e-4)
 
 
+def test_in_kernel_exploration_noise():
+    """sng_policy_forward_sampled: the noise drawn inside the policy kernel is Philox4x32-10 (key = seed, step; counter =
+    global env, action / 4) through Box-Muller -- checked value for value against a float64 restatement; the sampled
+    actions / log-probs are the torch modules' given that noise; the draw depends on (seed, step, global env) only."""
+    from oracle.oracle import philox4x32_10
+    from smart_nanogrid_gym_b200.rollout import MlpPolicy
+    E, D, A = 4096 + 37, 29, 11
+    torch.manual_seed(3)
+    policy = MlpPolicy(D, A).to("cuda:0")
+    g = torch.Generator(device="cuda:0").manual_seed(2)
+    obs = torch.rand(E, D, device="cuda:0", generator=g)
+    low, high = torch.zeros(A, device="cuda:0"), torch.ones(A, device="cuda:0")
+    low[-1] = -1.0
+    new = lambda *shape: torch.empty(*shape, device="cuda:0")  # noqa: E731
+    raw, act, val, lp, z = new(E, A), new(E, A), new(E), new(E), new(E, A)
+    counter = torch.tensor([7], dtype=torch.int64, device="cuda:0")
+    seed, offset, gid0 = 0x1234567890ABCDEF, 3, 1000
+    policy.fused_forward(obs, None, low, high, raw, act, val, lp, rng=(seed, counter, offset, gid0), noise_out=z)
+    step = 7 + offset
+    zc = z.cpu().numpy().astype(np.float64)
+    for e in list(range(0, 64)) + [E - 1, E - 37, 2048]:
+        for cb in range(3):
+            x = philox4x32_10([(gid0 + e) & 0xFFFFFFFF, (gid0 + e) >> 32, cb, step & 0xFFFFFFFF],
+                              [seed & 0xFFFFFFFF, (seed >> 32) ^ (step >> 32)])
+            u = ((x >> 8).astype(np.float64) + 0.5) * 2.0 ** -24
+            want = []
+            for k in (0, 2):
+                r = np.sqrt(-2.0 * np.log(u[k]))
+                want += [r * np.cos(2 * np.pi * u[k + 1]), r * np.sin(2 * np.pi * u[k + 1])]
+            got = zc[e, 4 * cb:4 * cb + 4]
+            assert np.allclose(got, want[:len(got)], rtol=0, atol=5e-5), (e, cb, got, want)
+    with torch.no_grad():
+        a_ref, v_ref, lp_ref = policy(obs, z)
+    assert torch.allclose(raw, a_ref, rtol=1e-4, atol=2e-5) and torch.allclose(val, v_ref, rtol=1e-4, atol=2e-5)
+    assert torch.allclose(act, torch.minimum(torch.maximum(a_ref, low), high), rtol=1e-4, atol=2e-5)
+    assert torch.allclose(lp, lp_ref, rtol=1e-5, atol=1e-4)
+    # moments of 45k standard normals
+    assert abs(float(z.mean())) < 0.02 and abs(float(z.var()) - 1.0) < 0.03 and float(z.abs().max()) < 6.5
+    # a shard [h, E) with env_gid0 advanced by h draws what the whole batch drew; another step draws something else
+    h = 2048
+    raw2, act2, val2, lp2, z2 = new(E - h, A), new(E - h, A), new(E - h), new(E - h), new(E - h, A)
+    policy.fused_forward(obs[h:], None, low, high, raw2, act2, val2, lp2, repack=False, rng=(seed, counter, offset, gid0 + h), noise_out=z2)
+    assert torch.equal(z2, z[h:]) and torch.equal(raw2, raw[h:])
+    counter += 1
+    policy.fused_forward(obs[h:], None, low, high, raw2, act2, val2, lp2, repack=False, rng=(seed, counter, offset, gid0 + h), noise_out=z2)
+    assert not torch.equal(z2, z[h:]) and abs(float((z2 * z[h:]).mean())) < 0.02
+
+
+def test_graphed_rollout_with_in_kernel_noise_advances_between_replays():
+    from smart_nanogrid_gym_b200 import BatchedSmartNanogridEnv
+    from smart_nanogrid_gym_b200.rollout import GraphedRollout, MlpPolicy, RolloutBuffer
+    E, n = 1024, 6
+    env = BatchedSmartNanogridEnv(E, device="cuda:0", seed=1, number_of_chargers=10, charging_mode="bounded",
+                                  vehicle_uncharged_penalty_mode="sparse", time_interval="1h")
+    torch.manual_seed(0)
+    policy = MlpPolicy(env.cfg.obs_dim, env.cfg.act_dim).to("cuda:0")
+    buf = RolloutBuffer(n, E, env.cfg.obs_dim, env.cfg.act_dim, "cuda:0")
+    obs = env.reset()
+    collect = GraphedRollout(env, policy, buf, rng_seed=11)
+    c0 = int(policy.rng_counter.item())
+    starts = torch.ones(E, dtype=torch.uint8, device="cuda:0")
+    obs, starts = collect(obs, starts)
+    first = buf.raw_actions.clone()
+    assert int(policy.rng_counter.item()) == c0 + n
+    obs, starts = collect(obs, starts)
+    assert int(policy.rng_counter.item()) == c0 + 2 * n and not torch.equal(first, buf.raw_actions)
+    # episode_starts[s + 1] is dones[s] (one array), and the GAE consumed them
+    assert torch.equal(buf.episode_starts[1:], buf.dones[:-1]) and bool(torch.isfinite(buf.advantages).all())
+    # noise of different steps of one rollout is different
+    zs = (buf.raw_actions[1] - buf.raw_actions[0]).abs().mean()
+    assert float(zs) > 1e-3
+    env.close()
+
+
 def test_shipped_sb3_policy_on_the_recorded_episode():
     """the reference's shipped PPO checkpoint (tests/golden/sb3_ppo_4ch_policy.npz) drives the
     N = 4 station: on the observations of the reference's recorded episode G1 the fused kernel's deterministic
