@@ -712,7 +712,7 @@ def main():
     ap.add_argument("--generic", action="store_true", help="tuning: use the generic runtime-N kernel")
     ap.add_argument("--bulk", type=int, default=1, help="tuning: row staging: -1 scalar, 0 vector loads/stores, 1 copy-engine loads + vector stores, 3 copy engine both ways")
     ap.add_argument("--host-chunks", type=int, default=0, help="tuning: env chunks of the pipelined host path")
-    ap.add_argument("--variant", type=int, default=0, help="tuning: 0 default, 1 persistent pipelined kernel, 2 one lane per env even for large stations")
+    ap.add_argument("--variant", type=int, default=0, help="tuning: 0 default, 1 persistent pipelined kernel, 2 one lane per env even for large stations, 3 two lanes per env")
     ap.add_argument("--ctas", type=int, default=0, help="tuning: cap on resident CTAs per SM (pipelined kernel)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs")
     ap.add_argument("--legs", default="all", help="'all', 'none' or a comma list of c4_strong,c5,c3,c3_sb3,c2,rollout_kernel,generic")

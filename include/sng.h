@@ -243,6 +243,10 @@ int sng_policy_forward_sampled(const void *packed, int obs_dim, int act_dim, con
  * floor under one sng_step per step for batches that live in L2; bench.py reports it beside those numbers). */
 int sng_null_launch(void *stream);
 
+/* Test hook: evaluates the step kernels' arrival-gap function (the number of failed Bernoulli(0.4) arrival trials a
+ * 32-bit Philox word encodes: charging_station.py:213-214 sampled per vehicle) on n device words. */
+int sng_debug_arrival_gap(sng_env *env, const uint32_t *x, uint32_t *gap, int64_t n, void *stream);
+
 /* Kernels launched by this handle so far (bench.py's gpu_launches claim). */
 int64_t sng_launch_count(const sng_env *env);
 
@@ -253,10 +257,10 @@ int64_t sng_launch_count(const sng_env *env);
  * both ways (unaligned buffers and a partial last block always take the scalar path); number of env
  * chunks sng_step_host pipelines over PCIe (0 = auto). */
 int sng_set_tuning(sng_env *env, int warps_per_cta, int use_generic_kernel, int use_bulk_copy, int host_chunks);
-/* Tuning knob: which step kernel runs: 0 (default) one 32-env block per warp, with two lanes per env for
+/* Tuning knob: which step kernel runs: 0 (default) one 32-env block per warp, with four lanes per env for
  * specialised stations of more than 32 spots; 1 the persistent software-pipelined kernel (measured slower,
- * see DESIGN.md); 2 one block per warp and always one lane per env.  ctas_per_sm caps the resident CTAs
- * per SM of the pipelined kernel (0 = as many as fit). */
+ * see DESIGN.md); 2 one block per warp and always one lane per env; 3 like 0 with two lanes per env.
+ * ctas_per_sm caps the resident CTAs per SM of the pipelined kernel (0 = as many as fit). */
 int sng_set_pipeline(sng_env *env, int kernel_variant, int ctas_per_sm);
 
 #ifdef __cplusplus

@@ -180,6 +180,12 @@ int sng_null_launch(void *stream)
     return cudaGetLastError() == cudaSuccess ? SNG_OK : fail(SNG_ERR_CUDA, "sng_null_launch failed");
 }
 
+int sng_debug_arrival_gap(sng_env *env, const uint32_t *x, uint32_t *gap, int64_t n, void *stream)
+{
+    SNG_ENV_CHECK(env);
+    return done(env, env->eng->probe_arrival_gap(x, gap, (long long)n, (cudaStream_t)stream));
+}
+
 int64_t sng_launch_count(const sng_env *env) { return (env && env->eng) ? env->eng->launches : 0; }
 
 int sng_set_tuning(sng_env *env, int warps_per_cta, int use_generic_kernel, int use_bulk_copy, int host_chunks)

@@ -37,7 +37,9 @@ __device__ __forceinline__ uint32_t real_to_word(float x) { return __float_as_ui
 __device__ __forceinline__ unsigned long long real_to_word(double x) { return (unsigned long long)__double_as_longlong(x); }
 constexpr uint32_t kNoVehicle = 0xFFu;
 constexpr int kMaxVehicles = 8;
-constexpr int kDepTab = 256;
+constexpr int kDepTab = 208;          // departure-normalisation entries (dep - t <= 10 h / dt <= 93 steps)
+constexpr int kGapTab = 48;           // thresholds of the geometric arrival gap (43 used)
+constexpr int kSmemTab = kDepTab + kGapTab;   // words of the per-CTA shared-memory copy: [dep | gap]
 
 // Per-spot header word: arr | dep << 8 | cap << 16 | next << 24
 //   arr   arrival step of the current / last vehicle (0xFF: none yet this episode)
@@ -80,7 +82,7 @@ template <typename real> struct Params {
     real dt, ev_pmax, ev_eff, b_cap, b_pmax, b_eff, b_dod, b_soc0, sell, cost_w, batt_w, margin;
     // shared read-only tables in global memory (L1-resident; every env of a lock-stepped batch reads the same entry)
     const real *pv_power, *irr_norm, *price, *price_norm;  // [table_len]
-    const float *dep_norm;                                 // [kDepTab]: float(k / 24.0)
+    const float *dep_norm;                                 // [kSmemTab]: float(k / 24.0), k < kDepTab | gap thresholds (uint32 bits)
     // caller-owned buffers
     const real *actions;   // [E][A]
     float *obs;            // [E][D]
@@ -137,9 +139,33 @@ __host__ __device__ __forceinline__ uint32_t geometric_gap(uint32_t x)
 
 template <typename real> struct Vehicle { uint32_t hdr; real soc0, req; };
 
-template <typename real>
+// The same count without the data-dependent loop (whose trip count diverges across the lanes of a warp: ~9 iterations
+// per warp for a mean of 1.5 per lane): estimate k from log2(x), then settle it against the exact thresholds
+// th_1 > th_2 > ... > th_43 = 0 (the CTA's shared-memory copy, staged next to the departure table).  The estimate is
+// within one of the answer, so each fix-up loop runs at most once; the result is exact by construction.
+__device__ __forceinline__ uint32_t geometric_gap_tab(uint32_t x, uint32_t tab_base)
+{
+    float lg;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"((float)x));                  // x = 0: -inf -> clamped below
+    int c = (int)fminf(fmaxf((32.0f - lg) * 1.35692f, 0.0f), 42.0f);              // 1 / log2(1 / 0.6)
+    const uint32_t gap_base = tab_base + 4u * (uint32_t)kDepTab;
+    auto th = [&](int k) {
+        uint32_t v;
+        asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(gap_base + 4u * (uint32_t)k));
+        return v;
+    };
+    while (c < 42 && x < th(c + 1)) ++c;
+    while (c > 0 && x >= th(c)) --c;
+    return (uint32_t)c;
+}
+template <bool SMEM> __device__ __forceinline__ uint32_t arrival_gap(uint32_t x, uint32_t tab_base)
+{
+    return SMEM ? geometric_gap_tab(x, tab_base) : geometric_gap(x);
+}
+
+template <typename real, bool SMEM = false>
 __device__ __forceinline__ Vehicle<real> sample_vehicle(const Params<real> &p, unsigned long long stream,
-                                                        uint32_t episode, int tn)
+                                                        uint32_t episode, int tn, uint32_t tab_base = 0u)
 {
     uint32_t x[4];
     philox4x32_10((uint32_t)stream, (uint32_t)(stream >> 32), episode, (uint32_t)tn, p.seed_lo, p.seed_hi, x);
@@ -155,7 +181,7 @@ __device__ __forceinline__ Vehicle<real> sample_vehicle(const Params<real> &p, u
     const int low = tn + p.i4;                                           // :271-279
     const int up = min(tn + p.i10, p.T + p.i1);
     const int dep = (low >= up) ? low : low + (int)(((x[3] & 0xFFFFu) * (uint32_t)(up - low)) >> 16);
-    const uint32_t next = (uint32_t)dep + 1u + geometric_gap(x[0]);
+    const uint32_t next = (uint32_t)dep + 1u + arrival_gap<SMEM>(x[0], tab_base);
     Vehicle<real> v;
     v.hdr = make_hdr((uint32_t)tn, (uint32_t)dep, cap, next < (uint32_t)p.T ? next : kNoVehicle);
     v.soc0 = (real)soc0;
@@ -175,14 +201,14 @@ __device__ __forceinline__ real sample_pv_shift(const Params<real> &p, int N, un
 }
 
 // Step at which the first vehicle of the day arrives at spot i (0xFF: none).
-template <typename real>
-__device__ __forceinline__ uint32_t first_arrival(const Params<real> &p, int N, long long e, int i, uint32_t episode)
+template <typename real, bool SMEM = false>
+__device__ __forceinline__ uint32_t first_arrival(const Params<real> &p, int N, long long e, int i, uint32_t episode, uint32_t tab_base = 0u)
 {
     if (p.mode == MODE_SAMPLE) {
         const unsigned long long stream = (p.gid0 + (unsigned long long)e) * (unsigned long long)N + (unsigned)i;
         uint32_t x[4];
         philox4x32_10((uint32_t)stream, (uint32_t)(stream >> 32), episode, kCtrFirstArrival, p.seed_lo, p.seed_hi, x);
-        const uint32_t g = geometric_gap(x[0]);
+        const uint32_t g = arrival_gap<SMEM>(x[0], tab_base);
         return g < (uint32_t)p.T ? g : kNoVehicle;
     }
     if (p.plan == nullptr) return kNoVehicle;
@@ -190,13 +216,13 @@ __device__ __forceinline__ uint32_t first_arrival(const Params<real> &p, int N, 
 }
 
 // The vehicle that arrives at spot i at step tn: sampled, or looked up in the replayed plan.
-template <typename real>
+template <typename real, bool SMEM = false>
 __device__ __forceinline__ Vehicle<real> fetch_vehicle(const Params<real> &p, int N, long long e, int i,
-                                                       uint32_t episode, int tn)
+                                                       uint32_t episode, int tn, uint32_t tab_base = 0u)
 {
     if (p.mode == MODE_SAMPLE) {
         const unsigned long long stream = (p.gid0 + (unsigned long long)e) * (unsigned long long)N + (unsigned)i;
-        return sample_vehicle(p, stream, episode, tn);
+        return sample_vehicle<real, SMEM>(p, stream, episode, tn, tab_base);
     }
     Vehicle<real> v;
     v.hdr = make_hdr(kNoVehicle, 0, 0, kNoVehicle);
@@ -221,6 +247,9 @@ __device__ __forceinline__ void store_vehicle(typename WordOf<real>::type *sp, c
     if (has_req) sp[PL_REQ * kBlock] = real_to_word(v.req);
     sp[PL_SOC * kBlock] = real_to_word(v.soc0);   // the step at `arr` starts from the arrival SoC (charger.py:62-67)
 }
+
+__device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
 
 // numpy's pairwise float64 sum (n <= 128 branch) for the bit-faithful double build:
 // charger_power_values[mask].sum(), utils/charging_station.py:293-294.
@@ -256,7 +285,7 @@ __device__ __forceinline__ double div_cap(double x, double cap) { return x / cap
 // the CTA's shared-memory copy in the step kernels (SMEM) or from global memory elsewhere.
 __device__ __forceinline__ float *dep_table_smem()
 {
-    __shared__ float tab[kDepTab];
+    __shared__ float tab[kSmemTab];
     return tab;
 }
 // 32-bit shared-space address of the table, made opaque so that it stays in one register instead of
@@ -335,12 +364,12 @@ __device__ __forceinline__ void begin_episode(const Params<real> &p, int N, long
     const uint32_t dep_base = SMEM ? dep_table_base() : 0u;
 #pragma unroll 1
     for (int i = sub; i < N; i += L) {
-        const uint32_t next = first_arrival(p, N, e, i, episode);
+        const uint32_t next = first_arrival<real, SMEM>(p, N, e, i, episode, dep_base);
         Vehicle<real> v;
         v.hdr = make_hdr(kNoVehicle, 0, 0, next);
         v.soc0 = 0;
         v.req = 0;
-        if (next == 0u) v = fetch_vehicle(p, N, e, i, episode, 0);
+        if (next == 0u) v = fetch_vehicle<real, SMEM>(p, N, e, i, episode, 0, dep_base);
         // the dense SoC array holds the arrival SoC at slot `arr` (charging_station.py:257-259),
         // so the reset observation shows it for vehicles arriving at t = 0
         store_vehicle<real>(spot + (size_t)(i / L) * (L * kPlanes * kBlock), v, p.has_req != 0);
@@ -458,7 +487,7 @@ __device__ __forceinline__ Arrivals env_step(const Params<real> &p, long long e,
 {
     float *const obs = io.row();   // env-level entries, reset observation
     static_assert(!COOP || (NCT > 0 && NCT <= 32 && L == 1), "cooperative admission needs a 32-bit arrival mask");
-    static_assert(L == 1 || (L == 2 && NCT > 0 && NCT % 2 == 0 && !EXACT), "two lanes per env: even compile-time N, float32");
+    static_assert(L == 1 || ((L == 2 || L == 4) && NCT > 0 && NCT % L == 0 && !EXACT), "several lanes per env: compile-time N divisible by L, float32");
     typedef typename WordOf<real>::type word;
     constexpr int MCT = NCT / L;                               // spots per lane at compile time
     const int N = NCT ? NCT : p.N;
@@ -473,9 +502,27 @@ __device__ __forceinline__ Arrivals env_step(const Params<real> &p, long long e,
     const int tn = t + 1;
     const bool is_done = (tn == p.T);
     const uint32_t tn_key = is_done ? 0x100u : (uint32_t)tn;   // never equals a header's `next` byte when done
-    // Station sums are kept per spot PARITY (even spots, odd spots) and combined at the end: a fixed
-    // association order that a two-lanes-per-env mapping (lane = parity) reproduces bit for bit.
-    real pos_e = 0, pos_o = 0, neg_e = 0, neg_o = 0, pen_e = 0, pen_o = 0;
+    // Station sums are kept per spot CLASS (spot index mod 2; mod 4 for stations of more than 32 spots) and the class
+    // sums are combined at the end as (c0 + c2) + (c1 + c3): a fixed association order that a mapping with several
+    // lanes per env (a lane owns the spots of one or two classes) reproduces bit for bit.
+    constexpr int NCLS = NCT > 32 ? 4 : 2;                     // specialised kernels; the generic kernel decides at run time
+    constexpr int NLC = NCT ? NCLS / L : 4;                    // classes this lane accumulates (its k-th spot: class k % NLC)
+    static_assert(NLC >= 1 && (NCT == 0 || NLC * L == NCLS), "lanes per env must divide the number of spot classes");
+    const int cls_mask = NCT ? NCLS - 1 : (p.N > 32 ? 3 : 1);
+    real pos_l[NLC], neg_l[NLC], pen_l[NLC];
+#pragma unroll
+    for (int k = 0; k < NLC; ++k) { pos_l[k] = 0; neg_l[k] = 0; pen_l[k] = 0; }
+    // a[class of the lane's i-th spot] += v  (lc: that class when known at compile time; adding +0 changes nothing)
+    auto accumulate = [&](real (&a)[NLC], int lc, int i, real v) {
+        if (NCT) {
+#pragma unroll
+            for (int k = 0; k < NLC; ++k)
+                if (k == lc) a[k] += v;
+        } else {
+#pragma unroll
+            for (int k = 0; k < NLC; ++k) a[k] += ((i & cls_mask) == k) ? v : (real)0;
+        }
+    };
     uint32_t err = 0;
     // spots whose next vehicle arrives at tn (specialised kernels only: N <= 64)
     typename std::conditional<(MCT > 32), unsigned long long, uint32_t>::type arrivals = 0, discharging = 0;   // bit k: the lane's k-th spot
@@ -506,8 +553,8 @@ __device__ __forceinline__ Arrivals env_step(const Params<real> &p, long long e,
 #pragma unroll
         for (int j = 0; j < CH; ++j) {
             const int i = c + j;                               // the lane's i-th spot = real spot i * L + sub
-            const int par = (L == 1) ? ((NCT ? j : i) & 1) : 0;   // spot parity (chunks of the specialised kernels are even;
-                                                               // with two lanes per env the lane IS the parity)
+            const int lc = NCT ? j % NLC : 0;                  // class of this spot among the lane's own (chunk sizes are
+                                                               // multiples of NLC, so j decides); generic kernel: see accumulate
             const uint32_t hd = (uint32_t)wh[j];
             const real rq = word_to_real(wr[j], (real)0);
             const real s_prev = word_to_real(ws[j], (real)0);  // SoC column t-1 (the arrival SoC when arr == t, charger.py:62-67)
@@ -524,8 +571,10 @@ __device__ __forceinline__ Arrivals env_step(const Params<real> &p, long long e,
             const real lower = p.margin * rq;                  // penaliser.py:72
             if (checked && s_prev < rq - lower) {              // :78
                 const real d = (rq - s_prev) * (real)10;
-                real &pen = (par && !EXACT) ? pen_o : pen_e;   // the float64 build sums in spot order like the reference
-                pen = pen + d * d;                             // :79 (Python `** 2`)
+                const real dd = mul_rn(d, d);                  // :79 (Python `** 2`); never contracted into the sum, so that every
+                                                               // kernel variant rounds the square the same way
+                if (EXACT) pen_l[0] = pen_l[0] + dd;           // the float64 build sums in spot order like the reference
+                else accumulate(pen_l, lc, i, dd);
             }
 
             const bool present = arr <= t && t < dep;          // charger.occupancy[t] == 1
@@ -550,7 +599,7 @@ __device__ __forceinline__ Arrivals env_step(const Params<real> &p, long long e,
                 if (EXACT) {
                     if (P > 0) cpos[npos++] = (double)P;
                 } else {
-                    (par ? pos_o : pos_e) += P;                // P >= 0 here
+                    accumulate(pos_l, lc, i, P);               // P >= 0 here
                 }
             } else if (present) {                              // a < 0 (or NaN): V2X discharge
                 const PowerSoc<real> r = discharge_vehicle(a * p.ev_pmax * p.ev_eff, p.dt, s_prev, (real)((hd >> 16) & 0xFFu));
@@ -561,8 +610,8 @@ __device__ __forceinline__ Arrivals env_step(const Params<real> &p, long long e,
                     if (P < 0) cneg[nneg++] = (double)P;
                     if (P > 0) cpos[npos++] = (double)P;
                 } else {
-                    if (P < 0) (par ? neg_o : neg_e) += P;
-                    if (P > 0) (par ? pos_o : pos_e) += P;
+                    if (P < 0) accumulate(neg_l, lc, i, P);
+                    if (P > 0) accumulate(pos_l, lc, i, P);
                 }
             }
             word *sp = spot + (size_t)i * SP;
@@ -573,7 +622,7 @@ __device__ __forceinline__ Arrivals env_step(const Params<real> &p, long long e,
                 if (NCT) {
                     arrivals |= (decltype(arrivals))1 << i;
                 } else {                                   // generic kernel: admit the arriving vehicle in place
-                    store_vehicle<real>(sp, fetch_vehicle(p, N, e, i * L + sub, episode, tn), p.has_req != 0);
+                    store_vehicle<real>(sp, fetch_vehicle<real, SMEM>(p, N, e, i * L + sub, episode, tn, dep_base), p.has_req != 0);
                 }
             }
         }
@@ -591,12 +640,12 @@ __device__ __forceinline__ Arrivals env_step(const Params<real> &p, long long e,
         const uint32_t hd = (uint32_t)sp[PL_HDR * kBlock];
         const real s_prev = word_to_real(sp[PL_SOC * kBlock], (real)0);   // the hot loop left it unchanged
         const PowerSoc<real> r = discharge_vehicle(io.action(i, 0) * p.ev_pmax * p.ev_eff, p.dt, s_prev, (real)((hd >> 16) & 0xFFu));
-        if ((L == 1) && (i & 1)) {
-            if (r.P < 0) neg_o += r.P;
-            if (r.P > 0) pos_o += r.P;
-        } else {
-            if (r.P < 0) neg_e += r.P;
-            if (r.P > 0) pos_e += r.P;
+#pragma unroll
+        for (int k = 0; k < NLC; ++k) {                   // DEFER implies NCT > 0: the class is i % NLC
+            if (k == i % NLC) {
+                if (r.P < 0) neg_l[k] += r.P;
+                if (r.P > 0) pos_l[k] += r.P;
+            }
         }
         sp[PL_SOC * kBlock] = real_to_word(r.soc);
         io.fix_soc(i, (float)r.soc);
@@ -604,18 +653,37 @@ __device__ __forceinline__ Arrivals env_step(const Params<real> &p, long long e,
     }
 
     // ---- env-level phase: CentralManagementSystem.manage_nanogrid (central_management_system.py:99-113) ----
-    if (L > 1) {   // this lane's spots all have parity `sub`: fetch the other parity's sums from the partner lane
+    // the four class sums in canonical order (class of a spot = its index mod 4, or mod 2 with classes 2 and 3 empty)
+    real pos4[4] = {0, 0, 0, 0}, neg4[4] = {0, 0, 0, 0}, pen4[4] = {0, 0, 0, 0};
+    if (L == 1) {
+#pragma unroll
+        for (int k = 0; k < NLC; ++k) { pos4[k] = pos_l[k]; neg4[k] = neg_l[k]; pen4[k] = pen_l[k]; }
+    } else {
+        // lane `sub` of the env holds the classes k * L + sub: every lane fetches every class from the lane that owns it
         constexpr uint32_t FULL = 0xffffffffu;
-        pos_o = __shfl_xor_sync(FULL, pos_e, 32 / L);
-        neg_o = __shfl_xor_sync(FULL, neg_e, 32 / L);
-        pen_o = __shfl_xor_sync(FULL, pen_e, 32 / L);
-        nan_probe += __shfl_xor_sync(FULL, nan_probe, 32 / L);
+        constexpr int EPW = kBlock / L;
+        const int el = (int)(threadIdx.x & 31) % EPW;
+#pragma unroll
+        for (int k = 0; k < NLC; ++k) {
+#pragma unroll
+            for (int q = 0; q < L; ++q) {
+                pos4[k * L + q] = __shfl_sync(FULL, pos_l[k], el + q * EPW);
+                neg4[k * L + q] = __shfl_sync(FULL, neg_l[k], el + q * EPW);
+                pen4[k * L + q] = __shfl_sync(FULL, pen_l[k], el + q * EPW);
+            }
+        }
+        real probe = nan_probe;
+#pragma unroll
+        for (int q = 1; q < L; ++q) probe += __shfl_xor_sync(FULL, nan_probe, q * EPW);
+        nan_probe = probe;
     }
+    // (two classes: classes 2 and 3 are +0 and none of these sums can be -0, so c0 + c1 is the same number)
+    constexpr bool TWO = NCT > 0 && NCLS == 2;
     if (!EXACT) {
-        pos = pos_e + pos_o;
-        neg = neg_e + neg_o;
+        pos = TWO ? pos4[0] + pos4[1] : (pos4[0] + pos4[2]) + (pos4[1] + pos4[3]);
+        neg = TWO ? neg4[0] + neg4[1] : (neg4[0] + neg4[2]) + (neg4[1] + neg4[3]);
     }
-    const real pen_veh = pen_e + pen_o;
+    const real pen_veh = TWO ? pen4[0] + pen4[1] : (pen4[0] + pen4[2]) + (pen4[1] + pen4[3]);
     const real total_power = pos + neg;                                   // :105
     if (total_power < (real)0 && !p.v2x) err |= FLAG_NEG_DEMAND;          // reference raises, :158-159
     const int pvo = pv_day_offset<ND>(p, episode);
@@ -690,7 +758,7 @@ __device__ __forceinline__ Arrivals env_step(const Params<real> &p, long long e,
         while (!COOP && arrivals) {
             const int i = (MCT > 32) ? __ffsll((long long)arrivals) - 1 : __ffs((int)arrivals) - 1;
             arrivals &= arrivals - 1;
-            store_vehicle<real>(spot + (size_t)i * SP, fetch_vehicle(p, N, e, i * L + sub, episode, tn), p.has_req != 0);
+            store_vehicle<real>(spot + (size_t)i * SP, fetch_vehicle<real, SMEM>(p, N, e, i * L + sub, episode, tn, dep_base), p.has_req != 0);
         }
         es.t_ep = (episode << 8) | (uint32_t)tn;
     } else {
@@ -699,7 +767,11 @@ __device__ __forceinline__ Arrivals env_step(const Params<real> &p, long long e,
         if (p.auto_reset) {
             // lanes sharing an env take this branch together: pair barriers keep the partner's row entries
             // complete before they are copied and untouched until they have been
-            const uint32_t pair = (L == 1) ? 0u : ((1u << (threadIdx.x & 31)) | (1u << ((threadIdx.x & 31) ^ (32 / L))));
+            uint32_t pair = 0u;                                           // the L lanes of this env
+            if (L > 1) {
+#pragma unroll
+                for (int q = 0; q < L; ++q) pair |= 1u << ((int)(threadIdx.x & 31) % (kBlock / L) + q * (kBlock / L));
+            }
             if (p.tobs) {
                 if (L > 1) __syncwarp(pair);
                 float *tobs = p.tobs + (size_t)e * p.D;
@@ -738,6 +810,7 @@ __device__ __forceinline__ void admit_arrivals_warp(const Params<real> &p, long 
                                                     uint16_t *queue)
 {
     constexpr uint32_t FULL = 0xffffffffu;
+    const uint32_t tab_base = dep_table_base();
     const int cnt = __popc(a.mask);
     int incl = cnt;
 #pragma unroll
@@ -759,7 +832,7 @@ __device__ __forceinline__ void admit_arrivals_warp(const Params<real> &p, long 
         const int tn = __shfl_sync(FULL, a.tn, src);
         if (mine)
             store_vehicle<real>(block_spot + (size_t)i * (kPlanes * kBlock) + src,
-                                fetch_vehicle(p, NCT, e0 + src, i, episode, tn), p.has_req != 0);
+                                fetch_vehicle<real, true>(p, NCT, e0 + src, i, episode, tn, tab_base), p.has_req != 0);
     }
     __syncwarp();                                 // the queue may be refilled by the next step
 }

@@ -28,6 +28,7 @@ struct EngineBase {
     virtual int step_host(const void *a, float *obs, void *rew, uint8_t *done, cudaStream_t st) = 0;
     virtual int sample_plan(cudaStream_t st) = 0;
     virtual int error_flags(uint32_t *out, cudaStream_t st) = 0;
+    virtual int probe_arrival_gap(const uint32_t *x, uint32_t *g, long long n, cudaStream_t st) = 0;
     virtual int set_tuning(int warps_per_cta, int use_generic, int use_bulk, int host_chunks) = 0;
     virtual int set_pipeline(int kernel_variant, int ctas_per_sm) = 0;
     int64_t launches = 0;
@@ -83,7 +84,7 @@ template <typename real> __device__ __forceinline__ void publish_dep_table(const
 {
     float4 *tab = reinterpret_cast<float4 *>(dep_table_smem());
 #pragma unroll 1
-    for (int k = threadIdx.x; k < kDepTab / 4; k += blockDim.x) tab[k] = __ldg(reinterpret_cast<const float4 *>(p.dep_norm) + k);
+    for (int k = threadIdx.x; k < kSmemTab / 4; k += blockDim.x) tab[k] = __ldg(reinterpret_cast<const float4 *>(p.dep_norm) + k);
     __syncthreads();
 }
 
@@ -161,6 +162,9 @@ __global__ void __launch_bounds__(SNG_PIPE_THREADS, SNG_PIPE_MINB)
 #ifndef SNG_STEP_MINB
 #define SNG_STEP_MINB 8
 #endif
+#ifndef SNG_STEP_MINB_LANES
+#define SNG_STEP_MINB_LANES 5     // several lanes per env, <= 16 spots per lane: 96 registers without spills, 20 warps per SM (measured: 6 -> 80 registers + spills 0.106 ms, 5 -> 0.093 ms, 4 -> 0.098 ms, 8 -> 0.143 ms per C5 step)
+#endif
 // Row staging modes (kernel argument `mode`): how the 32 action rows reach shared memory and the 32
 // observation rows leave it.
 enum : int {
@@ -171,12 +175,12 @@ enum : int {
 };
 
 // MULTI: n_steps > 1 (rollout); the single-step instantiation carries no slab arithmetic.
-// L: lanes per env (1; 2 for large specialised stations: a warp then covers 16 envs, needs half the shared
-// memory per warp and half the work per thread, so twice as many warps stay resident.  L = 2 handles whole
+// L: lanes per env (1; 4 or 2 for large specialised stations: a warp then covers 8 or 16 envs, needs a quarter / half
+// the shared memory per warp and of the work per thread, so more warps stay resident.  L > 1 handles whole
 // 32-env state blocks only -- the host sends a ragged last block to the L = 1 instantiation, whose sums
 // associate identically).
 template <typename real, int NCT, int ND, bool EXACT, bool MULTI, int L>
-__global__ void __launch_bounds__(SNG_STEP_MAXT, (EXACT || NCT / L > 32) ? 2 : (NCT / L > 16 ? 4 : SNG_STEP_MINB))   // large rows: shared memory bounds occupancy, not registers
+__global__ void __launch_bounds__(SNG_STEP_MAXT, (EXACT || NCT / L > 32) ? 2 : (NCT / L > 16 ? 4 : (L > 1 ? SNG_STEP_MINB_LANES : SNG_STEP_MINB)))   // large rows: shared memory bounds occupancy, not registers
     step_simple_kernel(const Params<real> p, const real *actions, float *obs_out, real *reward, uint8_t *done, int n_steps,
                        int mode)
 {
@@ -319,6 +323,17 @@ __global__ void __launch_bounds__(SNG_STEP_MAXT, (EXACT || NCT / L > 32) ? 2 : (
     if (tma_store && lane == 0) bulk_wait_read<0>();   // shared memory must stay valid until the store has read it
 }
 
+// Test hook (sng_debug_arrival_gap): the table-based geometric gap of the step kernels, evaluated on given words with
+// this handle's own threshold table.
+template <typename real>
+__global__ void __launch_bounds__(128) gap_probe_kernel(const Params<real> p, const uint32_t *x, uint32_t *g, long long n)
+{
+    publish_dep_table(p);
+    const uint32_t base = dep_table_base();
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        g[i] = geometric_gap_tab(x[i], base);
+}
+
 template <typename real>
 __global__ void __launch_bounds__(256) reset_kernel(const Params<real> p, const uint8_t *mask, int init,
                                                    int new_episode, int reset_battery)
@@ -398,7 +413,7 @@ public:
     int warps_per_cta = 0;   // 0 = auto
     int use_generic = 0, use_bulk = 1, host_chunks = 0, ctas_per_sm = 0;
     int kernel_variant = 0;   // 0 / 2 one block per warp, 1 persistent pipelined
-    int lanes_per_env = 0;    // 0 auto (2 for specialised stations of more than 32 spots), 1 always one lane per env
+    int lanes_per_env = 0;    // 0 auto (4 for specialised stations of more than 32 spots), 1 / 2: that many lanes per env
     int num_sms = 148;
     size_t smem_optin = 0;
     void *d_tables = nullptr;
@@ -462,8 +477,17 @@ public:
             h[2 * n + k] = (real)c.price[k];
             h[3 * n + k] = (real)c.price_norm[k];
         }
-        std::vector<float> dn(kDepTab);
+        std::vector<float> dn(kSmemTab, 0.0f);
         for (int k = 0; k < kDepTab; ++k) dn[k] = (float)((double)k / c.dep_norm);  // ...environment.py:208,228
+        {   // thresholds of the geometric arrival gap (geometric_gap's recurrence), th_0 unused
+            uint32_t th = 0x99999999u;
+            uint32_t bits = 0xFFFFFFFFu;
+            memcpy(&dn[kDepTab], &bits, 4);
+            for (int k = 1; k < kGapTab; ++k) {
+                memcpy(&dn[kDepTab + k], &th, 4);
+                th = (uint32_t)(((unsigned long long)th * 0x9999999Aull) >> 32);
+            }
+        }
         const size_t tb = h.size() * sizeof(real), db = dn.size() * sizeof(float);
         SNG_CUDA(cudaMalloc(&d_tables, tb + db));
         SNG_CUDA(cudaMemcpy(d_tables, h.data(), tb, cudaMemcpyHostToDevice));
@@ -573,7 +597,7 @@ public:
                         const size_t q = sp * V + k;
                         const int a = v->arr[q], d = v->dep[q], c = v->cap[q];
                         // invariants of generated schedules the step kernel relies on (schedule.py validate())
-                        if (a < 0 || a >= p.T || d <= a || d > 250 || c < 1 || c > 255 || a <= prev_dep) {
+                        if (a < 0 || a >= p.T || d <= a || d > 250 || d - a >= kDepTab || c < 1 || c > 255 || a <= prev_dep) {   // dep - t indexes the departure table
                             error = "sng_load_schedule: invalid vehicle record (arrival/departure/capacity)";
                             return SNG_ERR_ARG;
                         }
@@ -632,7 +656,7 @@ public:
     {
         return (size_t)stages * align128((uint32_t)(kBlock * p.A * sizeof(real))) + align128((uint32_t)(kBlock * p.D * sizeof(float)));
     }
-    static constexpr size_t kStaticSmem = kDepTab * sizeof(float);
+    static constexpr size_t kStaticSmem = kSmemTab * sizeof(float);
 
     // L lanes per env (see step_simple_kernel); L = 2 requires q.n_envs to be a multiple of 32.
     template <int NCT, int ND, int L = 1>
@@ -699,14 +723,18 @@ public:
             if (rc != SNG_ERR_UNSUPPORTED) return rc;
         }
         if constexpr (!EXACT && NCT > 32 && NCT % 2 == 0) {
-            // large stations (64 spots): two lanes per env over the whole 32-env blocks, the ragged last block one lane
+            // large stations (64 spots): four (or two) lanes per env over the whole 32-env blocks, the ragged last block one lane
             // per env (a 32-spot station already reaches 85 % of the HBM roofline with one lane per env)
             if (lanes_per_env != 1 && q.n_envs >= kBlock) {
                 const long long full = q.n_envs / kBlock * kBlock;
-                if (full == q.n_envs) return launch_simple<NCT, ND, 2>(q, actions, obs, reward, done, n_steps, bulk, st);
+                const bool four = lanes_per_env != 2 && NCT % 4 == 0;      // default: four lanes per env (a warp covers 8 envs)
+                if (full == q.n_envs)
+                    return four ? launch_simple<NCT, ND, 4>(q, actions, obs, reward, done, n_steps, bulk, st)
+                                : launch_simple<NCT, ND, 2>(q, actions, obs, reward, done, n_steps, bulk, st);
                 if (n_steps == 1 && actions == q.actions && obs == q.obs && reward == q.reward && done == q.done) {
                     const Params<real> head = slice_of(q, 0, full), tail = slice_of(q, full, q.n_envs - full);
-                    const int rc = launch_simple<NCT, ND, 2>(head, head.actions, head.obs, head.reward, head.done, 1, bulk, st);
+                    const int rc = four ? launch_simple<NCT, ND, 4>(head, head.actions, head.obs, head.reward, head.done, 1, bulk, st)
+                                        : launch_simple<NCT, ND, 2>(head, head.actions, head.obs, head.reward, head.done, 1, bulk, st);
                     if (rc) return rc;
                     return launch_simple<NCT, ND, 1>(tail, tail.actions, tail.obs, tail.reward, tail.done, 1, STAGE_SCALAR, st);
                 }
@@ -867,6 +895,16 @@ public:
         return SNG_OK;
     }
 
+    int probe_arrival_gap(const uint32_t *x, uint32_t *g, long long n, cudaStream_t st) override
+    {
+        if (!x || !g || n < 1) { error = "sng_debug_arrival_gap: bad arguments"; return SNG_ERR_ARG; }
+        DeviceGuard guard(device);
+        gap_probe_kernel<real><<<148, 128, 0, st>>>(p, x, g, n);
+        ++launches;
+        SNG_CUDA(cudaGetLastError());
+        return SNG_OK;
+    }
+
     int error_flags(uint32_t *out, cudaStream_t st) override
     {
         int rc = check_ready(false);
@@ -896,9 +934,9 @@ public:
 
     int set_pipeline(int up, int cps) override
     {
-        if (cps < 0 || up < 0 || up > 2) { error = "sng_set_pipeline: bad arguments"; return SNG_ERR_ARG; }
-        kernel_variant = up == 2 ? 0 : up;
-        lanes_per_env = up == 2 ? 1 : 0;
+        if (cps < 0 || up < 0 || up > 3) { error = "sng_set_pipeline: bad arguments"; return SNG_ERR_ARG; }
+        kernel_variant = up >= 2 ? 0 : up;
+        lanes_per_env = up == 2 ? 1 : (up == 3 ? 2 : 0);
         ctas_per_sm = cps;
         return SNG_OK;
     }

@@ -223,6 +223,36 @@ def test_multiday_pv_vs_oracle(cycle, precision):
     env.close()
 
 
+def test_arrival_gap_table_form_equals_the_recurrence():
+    """The step kernels count the failed arrival trials a Philox word encodes with a log2 estimate settled against a
+    threshold table; it must equal the integer recurrence (geometric_gap / the oracle's mirror) for EVERY word: all
+    43 thresholds and their neighbours, the ends of the range, and a million random words of every magnitude."""
+    import ctypes as C
+    from smart_nanogrid_gym_b200 import _native as nat
+    env = _env(32, "float32", number_of_chargers=10)
+    ths, th = [], 0x99999999
+    while th > 0:
+        ths.append(th)
+        th = (th * 0x9999999A) >> 32
+    ths.append(0)
+    assert len(ths) == 43
+    rng = np.random.default_rng(3)
+    xs = [0, 1, 2, 3, 0xFFFFFFFF, 0xFFFFFFFE, 0x80000000, 0x7FFFFFFF]
+    for t in ths:
+        xs += [max(t - 2, 0), max(t - 1, 0), t, min(t + 1, 0xFFFFFFFF), min(t + 2, 0xFFFFFFFF)]
+    rand = rng.integers(0, 2 ** 32, size=1 << 20, dtype=np.uint64)
+    rand >>= rng.integers(0, 32, size=rand.shape, dtype=np.uint64)         # every magnitude
+    x = np.concatenate([np.array(xs, np.uint64), rand]).astype(np.uint32)
+    want = (x[:, None].astype(np.uint64) < np.array(ths, np.uint64)[None, :]).sum(axis=1).astype(np.uint32)
+    xd = torch.from_numpy(x.view(np.int32)).to("cuda:0")
+    gd = torch.empty_like(xd)
+    nat.check(nat.lib().sng_debug_arrival_gap(env._h, C.c_void_p(xd.data_ptr()), C.c_void_p(gd.data_ptr()), x.shape[0], None))
+    got = gd.cpu().numpy().view(np.uint32)
+    assert np.array_equal(got, want), np.flatnonzero(got != want)[:10]
+    assert want.max() == 42 and want.min() == 0
+    env.close()
+
+
 def test_sampler_matches_cpu_mirror_bit_exact():
     """sng_sample_plan (GPU, Philox4x32-10) == oracle mirror, record for record; and the in-step lazy
     sampler follows the same plan (covered by the lockstep tests)."""
@@ -252,6 +282,8 @@ def test_sampler_matches_cpu_mirror_bit_exact():
     dict(number_of_chargers=64, time_interval="15min", enable_requested_state_of_charge=True),
     dict(number_of_chargers=8, battery_system_available_in_model=False, pv_system_available_in_model=False),
     dict(number_of_chargers=7),
+    dict(number_of_chargers=64, time_interval="30min", vehicle_to_everything=True, vehicle_uncharged_penalty_mode="dense"),
+    dict(number_of_chargers=32, hours_ahead=2),
 ])
 def test_kernel_variants_are_bit_identical(kw):
     """The persistent pipelined and the one-block-per-warp kernel, the specialised (compile-time N) and the
@@ -262,7 +294,8 @@ def test_kernel_variants_are_bit_identical(kw):
     variants = [(dict(), dict()), (dict(use_generic_kernel=1), dict()), (dict(use_bulk_copy=0), dict()),
                 (dict(use_bulk_copy=-1), dict()), (dict(use_bulk_copy=3), dict()), (dict(use_bulk_copy=1, use_generic_kernel=1), dict()),
                 (dict(warps_per_cta=1), dict(kernel_variant=1, ctas_per_sm=1)), (dict(), dict(kernel_variant=1)),
-                (dict(warps_per_cta=4, use_generic_kernel=1), dict(kernel_variant=1)), (dict(), dict(kernel_variant=2))]
+                (dict(warps_per_cta=4, use_generic_kernel=1), dict(kernel_variant=1)), (dict(), dict(kernel_variant=2)),
+                (dict(), dict(kernel_variant=3))]      # 2: one lane per env, 3: two lanes per env (default for 64 spots: four)
     envs = []
     for tune, pipe in variants:
         env = _env(E, "float32", seed=21, **kw)
