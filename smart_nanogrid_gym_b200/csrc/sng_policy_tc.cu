@@ -347,6 +347,13 @@ __host__ __device__ inline Smem smem_plan(int D, int A)
     return s;
 }
 
+// One arrival per WARP (512 per-thread arrivals on one shared-memory word serialise: ~0.25 us per barrier round).  Every
+// lane has completed its TMEM stores (tcgen05.wait::st) and fenced them; __syncwarp orders the lanes before lane 0 arrives.
+__device__ __forceinline__ void mbar_arrive_warp(uint64_t *bar)
+{
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -409,7 +416,7 @@ __global__ void __launch_bounds__(THREADS + 32, 1)
     uint64_t *wbar = bars;                                  // [3] weight image: critic layer 0 | rest of the critic | actor
     uint64_t *obar = bars + 3;                              // [2] observation rows of the even / odd tiles have landed
     uint64_t *nbar = bars + 5;                              // noise rows have landed
-    // compute -> issuer, 512 arrivals each: X of a tile is in TMEM | tanh(critic layer) is | tanh(actor layer) is.
+    // compute -> issuer, 16 arrivals (one per warp) each: X of a tile is in TMEM | tanh(critic layer) is | tanh(actor layer) is.
     // (One barrier per chain: a thread's next wait after arriving on a chain's barrier depends on that very phase, so a fast
     //  warp can never arrive twice in one phase and complete it on behalf of a slow one.)
     uint64_t *xbar = bars + 6, *rbar = bars + 7;            // rbar[2]: critic, actor
@@ -419,7 +426,7 @@ __global__ void __launch_bounds__(THREADS + 32, 1)
     const int n_nets = value_only ? 1 : 2;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < 11; ++i) mbar_init(bars + i, (i >= 6 && i <= 8) ? THREADS : 1);
+        for (int i = 0; i < 11; ++i) mbar_init(bars + i, (i >= 6 && i <= 8) ? THREADS / 32 : 1);   // compute -> issuer: one arrival per warp
         fence_mbar_init();
         // the weight image: one copy per CTA, in three pieces in the order they are needed (the first tile's critic
         // layer 0 starts as soon as its 16 KB have landed)
@@ -524,7 +531,7 @@ __global__ void __launch_bounds__(THREADS + 32, 1)
             tmem_st8(tlane + x_cols(buf) + 32 + 8 * cb, xl);
             tmem_wait_st();
             tc_fence_before();
-            mbar_arrive(xbar);
+            mbar_arrive_warp(xbar);
         };
 
         if (threadIdx.x == 0) {
@@ -560,7 +567,7 @@ __global__ void __launch_bounds__(THREADS + 32, 1)
                 TRACE();
                 tanh_epilogue(tc + src + 16 * cb, tc + C_Q + 16 * cb);
                 tc_fence_before();
-                mbar_arrive(rbar);
+                mbar_arrive_warp(rbar);
                 TRACE();
                 if (n_nets == 2) {
                     mbar_wait(mbar + 1, ma_phase); ma_phase ^= 1u;
@@ -568,7 +575,7 @@ __global__ void __launch_bounds__(THREADS + 32, 1)
                     TRACE();
                     tanh_epilogue(ta + src + 16 * cb, ta + C_Q + 16 * cb);
                     tc_fence_before();
-                    mbar_arrive(rbar + 1);
+                    mbar_arrive_warp(rbar + 1);
                     TRACE();
                 }
             }
