@@ -616,9 +616,11 @@ def rollout_leg(ctx, wl_key, E, n_steps, shipped=False):
         noise = torch.randn(E, env.cfg.act_dim, device=ctx.dev)
         low, high = env.action_low.float(), env.action_high.float()
 
+        policy.pack_weights()
+
         def pol():
             for _ in range(50):
-                policy.fused_forward(o, noise, low, high, buf.raw_actions[0], buf.actions[0], buf.values[0], buf.log_probs[0])
+                policy.fused_forward(o, noise, low, high, buf.raw_actions[0], buf.actions[0], buf.values[0], buf.log_probs[0], repack=False)
         pol()
         t_pol = timed_ms(ctx, pol) / 50
     flops = 2.0 * 2 * (env.cfg.obs_dim * 64 + 64 * 64) + 2.0 * 64 * (env.cfg.act_dim + 1)    # per env: actor + critic + heads
@@ -634,6 +636,49 @@ def rollout_leg(ctx, wl_key, E, n_steps, shipped=False):
         out["policy_forward_ms"] = t_pol
         out["policy_forward_tflops"] = flops * E / (t_pol * 1e-3) / 1e12
     env.close()
+    return out
+
+
+def rollout_sharded_leg(ctx, wl_key, E, n_steps, shards=2):
+    """BASELINE config 3 with the batch cut into `shards` env shards collected side by side (ShardedGraphedRollout):
+    the policy kernel of one shard overlaps the step kernel of the other."""
+    torch = ctx.torch
+    from smart_nanogrid_gym_b200 import BatchedSmartNanogridEnv
+    from smart_nanogrid_gym_b200.rollout import MlpPolicy, RolloutBuffer, ShardedGraphedRollout
+    per = E // shards
+    envs = [BatchedSmartNanogridEnv(per, device=ctx.dev, seed=0, env_gid0=ctx.rank * E + k * per, precision="float32",
+                                    auto_reset=True, **WORKLOADS[wl_key]["kw"]) for k in range(shards)]
+    cfg = envs[0].cfg
+    torch.manual_seed(0)
+    policy = MlpPolicy(cfg.obs_dim, cfg.act_dim).to(ctx.dev)
+    bufs = [RolloutBuffer(n_steps, per, cfg.obs_dim, cfg.act_dim, ctx.dev) for _ in range(shards)]
+    obs = [e.reset() for e in envs]
+    starts = [torch.ones(per, dtype=torch.uint8, device=ctx.dev) for _ in range(shards)]
+    collect = ShardedGraphedRollout(envs, policy, bufs)
+    state = [obs, starts]
+
+    def run(reps):
+        for _ in range(reps):
+            state[0], state[1] = collect(state[0], state[1])
+
+    run(2)
+    ms_probe = ctx.max_over_ranks(timed_ms(ctx, lambda: run(2))) / 2
+    reps = int(min(max(250.0 / max(ms_probe, 1e-3), 5), 2000))
+    sampler = ClockSampler(ctx.local_rank)
+    sampler.start()
+    ms = timed_ms(ctx, lambda: run(reps))
+    clocks = sampler.stop()
+    ms_max = ctx.max_over_ranks(ms)
+    steps = reps * n_steps
+    out = {"value": per * shards * ctx.n_gpus * steps / (ms_max * 1e-3), "unit": UNIT, "ms_per_step": ms_max / steps, "steps": steps,
+           "n_steps_per_rollout": n_steps, "envs_per_gpu": per * shards, "total_envs": per * shards * ctx.n_gpus, "shards_per_gpu": shards,
+           "launch": "one CUDA graph per rollout with %d parallel branches (one per env shard): n_steps x [policy kernel, step kernel] "
+                     "+ bootstrap value + GAE each" % shards,
+           "policy": "fresh-init (torch seed 0) tanh MLP %d-64-64-%d actor + critic (%s), exploration noise drawn in the kernel, "
+                     "GAE by sng_gae" % (cfg.obs_dim, cfg.act_dim, policy.fused_kind()),
+           "mean_step_reward": float(torch.stack([b.rewards.mean() for b in bufs]).mean()), "clocks": clocks}
+    for e in envs:
+        e.close()
     return out
 
 
@@ -715,7 +760,7 @@ def main():
     ap.add_argument("--variant", type=int, default=0, help="tuning: 0 default, 1 persistent pipelined kernel, 2 one lane per env even for large stations, 3 two lanes per env")
     ap.add_argument("--ctas", type=int, default=0, help="tuning: cap on resident CTAs per SM (pipelined kernel)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs")
-    ap.add_argument("--legs", default="all", help="'all', 'none' or a comma list of c4_strong,c5,c3,c3_sb3,c2,rollout_kernel,generic")
+    ap.add_argument("--legs", default="all", help="'all', 'none' or a comma list of c4_strong,c5,c3,c3_sharded,c3_sb3,c2,rollout_kernel,generic")
     ap.add_argument("--rollout", type=int, default=0, help="legacy: same as --legs c3 with this many steps per rollout")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -786,7 +831,7 @@ def main():
     want = args.legs
     if args.rollout > 0 and want in ("none", ""):
         want = "c3"
-    names = ["c4_strong", "c5", "c3", "c3_sb3", "c2", "rollout_kernel", "generic"] if want == "all" else [x for x in want.split(",") if x and x != "none"]
+    names = ["c4_strong", "c5", "c3", "c3_sharded", "c3_sb3", "c2", "rollout_kernel", "generic"] if want == "all" else [x for x in want.split(",") if x and x != "none"]
     legs = {}
     if names:
         floor_us = launch_floor_us(ctx)
@@ -804,6 +849,9 @@ def main():
                 elif name == "c3":
                     legs[name] = rollout_leg(ctx, "c4", 65536, args.rollout or 24)
                     legs[name]["what"] = "BASELINE config 3: PPO rollout collection over 65,536 envs per GPU, N=10 station"
+                elif name == "c3_sharded":
+                    legs[name] = rollout_sharded_leg(ctx, "c4", 65536, args.rollout or 24, shards=2)
+                    legs[name]["what"] = "BASELINE config 3, 65,536 envs per GPU as two 32,768-env shards collected side by side"
                 elif name == "c3_sb3":
                     legs[name] = rollout_leg(ctx, "n4", 65536, 24, shipped=True)
                     legs[name]["what"] = "BASELINE config 3 with the reference's shipped policy (N=4 station)"

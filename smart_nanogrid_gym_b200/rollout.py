@@ -195,18 +195,20 @@ class RolloutBuffer:
 @torch.no_grad()
 def collect_rollout(env, policy: MlpPolicy, buf: RolloutBuffer, obs: torch.Tensor, episode_starts: torch.Tensor,
                     generator: torch.Generator | None = None, deterministic: bool = False, fused: bool = True,
-                    rng_seed: int | None = None):
+                    rng_seed: int | None = None, pack: bool = True, advance_counter: bool = True):
     """SB3 OnPolicyAlgorithm.collect_rollouts for a BatchedSmartNanogridEnv: n_steps policy + env steps,
     then GAE.  `obs` [E, D] is the current observation (from reset() or the previous rollout),
     `episode_starts` [E] u8.  Returns (last_obs, last_dones) to carry into the next call.
     Exploration noise: torch.randn (with `generator`) per step, or -- `rng_seed` given, fused kernel -- drawn inside
-    the policy kernel (Philox keyed by rng_seed and the policy's step counter: no noise tensor, no RNG launch)."""
+    the policy kernel (Philox keyed by rng_seed and the policy's step counter: no noise tensor, no RNG launch).
+    pack=False / advance_counter=False: the caller packs the weights / advances the step counter itself (several
+    shards collected side by side share both, see ShardedGraphedRollout)."""
     low, high = env.action_low.float(), env.action_high.float()
     buf.observations[0].copy_(obs)
     buf.episode_starts[0].copy_(episode_starts.to(torch.uint8))    # episode_starts[s + 1] aliases dones[s]
     fused = fused and policy.fused_supported()
     in_kernel_noise = fused and not deterministic and rng_seed is not None
-    if fused:
+    if fused and pack:
         policy.pack_weights()          # once per rollout: the weights do not change while it is collected
     if in_kernel_noise and (getattr(policy, "rng_counter", None) is None or policy.rng_counter.device != obs.device):
         policy.rng_counter = torch.zeros(1, dtype=torch.int64, device=obs.device)   # rollout steps drawn so far
@@ -228,7 +230,7 @@ def collect_rollout(env, policy: MlpPolicy, buf: RolloutBuffer, obs: torch.Tenso
         # the kernel writes the next observation, the reward and the done flag (= the next step's episode start)
         # into the buffer slabs
         env.step(buf.actions[s], out=(buf.observations[s + 1], buf.rewards[s], buf.dones[s]))
-    if in_kernel_noise:
+    if in_kernel_noise and advance_counter:
         policy.rng_counter += buf.n_steps
     last_obs = buf.observations[buf.n_steps]
     if fused:
@@ -267,6 +269,63 @@ class GraphedRollout:
         self.starts_in.copy_(episode_starts)
         self.graph.replay()
         return self.last_obs, self.last_dones
+
+
+class ShardedGraphedRollout:
+    """One rollout over K env shards of ONE GPU, collected side by side: shard k's policy kernel (tensor cores, one CTA
+    per SM) runs while shard k'ish step kernel (a few small CTAs per SM, HBM / L2 traffic) runs -- the two kernels bound by
+    different resources overlap instead of alternating with a launch gap in between.  Captured once as a CUDA graph with
+    K parallel branches.  The shards are ordinary BatchedSmartNanogridEnv objects with consecutive env_gid0 (RNG streams
+    and exploration noise are keyed by global env id, so K shards produce exactly what one env of the summed size does:
+    tests/test_gpu_rollout.py)."""
+
+    def __init__(self, envs, policy: MlpPolicy, bufs, deterministic: bool = False, rng_seed: int | None = 0):
+        assert len(envs) == len(bufs) and len(envs) >= 1
+        dev = bufs[0].rewards.device
+        self.envs, self.policy, self.bufs = list(envs), policy, list(bufs)
+        self.n_steps = bufs[0].n_steps
+        self.obs_in = [torch.zeros(b.n_envs, b.observations.shape[2], device=dev) for b in bufs]
+        self.starts_in = [torch.zeros(b.n_envs, dtype=torch.uint8, device=dev) for b in bufs]
+        self.streams = [torch.cuda.Stream(device=dev) for _ in envs]
+        in_kernel = (not deterministic) and rng_seed is not None and policy.fused_supported()
+        if in_kernel and (getattr(policy, "rng_counter", None) is None or policy.rng_counter.device != dev):
+            policy.rng_counter = torch.zeros(1, dtype=torch.int64, device=dev)
+
+        def body():
+            main = torch.cuda.current_stream(dev)
+            policy.pack_weights()
+            fork = torch.cuda.Event()
+            fork.record(main)
+            outs = []
+            for k, st in enumerate(self.streams):
+                st.wait_event(fork)
+                with torch.cuda.stream(st):
+                    outs.append(collect_rollout(self.envs[k], policy, self.bufs[k], self.obs_in[k], self.starts_in[k],
+                                                deterministic=deterministic, rng_seed=rng_seed, pack=False, advance_counter=False))
+                    join = torch.cuda.Event()
+                    join.record(st)
+                main.wait_event(join)
+            if in_kernel:
+                policy.rng_counter += self.n_steps
+            return outs
+
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):                     # warm-up outside capture
+            for k, e in enumerate(self.envs):
+                self.obs_in[k].copy_(e.obs)
+            body()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.outs = body()
+
+    def __call__(self, obs_list, starts_list):
+        for k in range(len(self.envs)):
+            self.obs_in[k].copy_(obs_list[k])
+            self.starts_in[k].copy_(starts_list[k])
+        self.graph.replay()
+        return [o[0] for o in self.outs], [o[1] for o in self.outs]
 
 
 def gae_reference(rewards, values, episode_starts, last_values, last_dones, gamma, gae_lambda):

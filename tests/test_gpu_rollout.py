@@ -243,6 +243,44 @@ def test_graphed_rollout_with_in_kernel_noise_advances_between_replays():
     env.close()
 
 
+def test_sharded_rollout_equals_the_unsharded_one():
+    """Two env shards collected side by side (ShardedGraphedRollout: parallel graph branches, in-kernel noise keyed by
+    global env id) produce bit for bit what one env of the summed size does."""
+    from smart_nanogrid_gym_b200 import BatchedSmartNanogridEnv
+    from smart_nanogrid_gym_b200.rollout import GraphedRollout, MlpPolicy, RolloutBuffer, ShardedGraphedRollout
+    E, n, seed = 1024, 5, 9
+    torch.manual_seed(4)
+    policy = MlpPolicy(29, 11).to("cuda:0")
+    one = BatchedSmartNanogridEnv(E, device="cuda:0", seed=seed, **KW)
+    buf1 = RolloutBuffer(n, E, 29, 11, "cuda:0")
+    one.reset()
+    whole = GraphedRollout(one, policy, buf1, rng_seed=5)              # steps `one` 2 x n times (warm-up, capture)
+    halves = [BatchedSmartNanogridEnv(E // 2, device="cuda:0", seed=seed, env_gid0=k * (E // 2), **KW) for k in range(2)]
+    bufs = [RolloutBuffer(n, E // 2, 29, 11, "cuda:0") for _ in range(2)]
+    for h in halves:
+        h.reset()
+    sharded = ShardedGraphedRollout(halves, policy, bufs, rng_seed=5)
+    # both sides: second reset -> episode 1, battery back to its initial SoC (it survives plain resets, quirk Q8)
+    obs1 = one.reset(reset_battery=True)
+    obs2 = [h.reset(reset_battery=True) for h in halves]
+    assert torch.equal(torch.cat(obs2), obs1)
+    ones = torch.ones(E, dtype=torch.uint8, device="cuda:0")
+    for rep in range(2):
+        policy.rng_counter.fill_(100 * rep)
+        o1, s1 = whole(obs1 if rep == 0 else o1, ones if rep == 0 else s1)
+        a1, r1, v1, adv1 = buf1.raw_actions.clone(), buf1.rewards.clone(), buf1.values.clone(), buf1.advantages.clone()
+        policy.rng_counter.fill_(100 * rep)
+        o2, s2 = sharded(obs2 if rep == 0 else o2, [ones[:E // 2], ones[E // 2:]] if rep == 0 else s2)
+        assert torch.equal(torch.cat([b.raw_actions for b in bufs], dim=1), a1)
+        assert torch.equal(torch.cat([b.rewards for b in bufs], dim=1), r1)
+        assert torch.equal(torch.cat([b.values for b in bufs], dim=1), v1)
+        assert torch.equal(torch.cat([b.advantages for b in bufs], dim=1), adv1)
+        assert torch.equal(torch.cat(o2), o1) and torch.equal(torch.cat(s2), s1)
+    one.close()
+    for h in halves:
+        h.close()
+
+
 def test_shipped_sb3_policy_on_the_recorded_episode():
     """the reference's shipped PPO checkpoint (tests/golden/sb3_ppo_4ch_policy.npz) drives the
     N = 4 station: on the observations of the reference's recorded episode G1 the fused kernel's deterministic
