@@ -831,7 +831,7 @@ def main():
     want = args.legs
     if args.rollout > 0 and want in ("none", ""):
         want = "c3"
-    names = ["c4_strong", "c5", "c3", "c3_sharded", "c3_sb3", "c2", "rollout_kernel", "generic"] if want == "all" else [x for x in want.split(",") if x and x != "none"]
+    names = ["c4_strong", "c5", "c3", "c3_sb3", "c2", "rollout_kernel", "generic"] if want == "all" else [x for x in want.split(",") if x and x != "none"]
     legs = {}
     if names:
         floor_us = launch_floor_us(ctx)

@@ -388,7 +388,7 @@ __device__ __forceinline__ void issue_phase(int phase, uint32_t tn, uint32_t x, 
 //     compute             | E(c0)   | E(a0)   | E(c1)   | E(a1)  X'   | value, actions | E(c0') ...
 // (c0 = critic layer 0, ch = critic head, ' = next tile).  The next tile's X is converted into the other X buffer while
 // the heads run, so the pipeline never drains between tiles.  Synchronisation: `rbar` (512 arrivals: "operands of the
-// next layer are in TMEM") compute -> issuer, `mbar[net]` (tcgen05.commit) issuer -> compute.
+// next layer are in TMEM") compute -> issuer, `mbar[net]` / `hbar[net]` (tcgen05.commit: hidden layers / heads) issuer -> compute.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(THREADS + 32, 1)
     policy_tc_kernel(const float *__restrict__ img, const float *__restrict__ obs, const float *__restrict__ noise,
@@ -420,13 +420,18 @@ __global__ void __launch_bounds__(THREADS + 32, 1)
     // (One barrier per chain: a thread's next wait after arriving on a chain's barrier depends on that very phase, so a fast
     //  warp can never arrive twice in one phase and complete it on behalf of a slow one.)
     uint64_t *xbar = bars + 6, *rbar = bars + 7;            // rbar[2]: critic, actor
-    uint64_t *mbar = bars + 9;                              // [2] issuer -> compute: the critic's / the actor's layer is complete
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 11);
+    uint64_t *mbar = bars + 9;                              // [2] issuer -> compute: the critic's / the actor's hidden layer is complete
+    // [2] issuer -> compute: the critic's / the actor's HEAD is complete.  Separate from mbar: the next tile's layer 0 can
+    // complete before a delayed compute warp has observed this tile's head (both are issued back to back once the next
+    // tile's X is staged), and a parity wait cannot be two completions behind -- with one barrier per chain such a
+    // warp waits forever (seen when step-kernel CTAs of another stream shared the SM).
+    uint64_t *hbar = bars + 11;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 13);
     const bool value_only = actions == nullptr;
     const int n_nets = value_only ? 1 : 2;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < 11; ++i) mbar_init(bars + i, (i >= 6 && i <= 8) ? THREADS / 32 : 1);   // compute -> issuer: one arrival per warp
+        for (int i = 0; i < 13; ++i) mbar_init(bars + i, (i >= 6 && i <= 8) ? THREADS / 32 : 1);   // compute -> issuer: one arrival per warp
         fence_mbar_init();
         // the weight image: one copy per CTA, in three pieces in the order they are needed (the first tile's critic
         // layer 0 starts as soon as its 16 KB have landed)
@@ -459,7 +464,7 @@ __global__ void __launch_bounds__(THREADS + 32, 1)
         const uint32_t tm = *tmem_slot;
         const uint32_t w_base = smem_u32(smem);
         const uint32_t w_net1 = w_base + (uint32_t)(NET_FLOATS * sizeof(float));
-        const uint32_t mb0 = smem_u32(mbar), mb1 = mb0 + 8u;
+        const uint32_t mb0 = smem_u32(mbar), mb1 = mb0 + 8u, hb0 = smem_u32(hbar), hb1 = hb0 + 8u;
         const uint32_t tn0 = tm + C_NET0, tn1 = tn0 + C_NETSTRIDE;
         uint32_t xp = 0u, cp = 0u, ap = 0u;
 #pragma unroll 1
@@ -483,10 +488,10 @@ __global__ void __launch_bounds__(THREADS + 32, 1)
                 issue_phase(1, tn1, x, 0, w_net1, mb1);
             }
             mbar_wait(rbar, cp); cp ^= 1u;                             // tanh(critic layer 1)
-            issue_phase(2, tn0, x, head0, w_base, mb0);
+            issue_phase(2, tn0, x, head0, w_base, hb0);
             if (n_nets == 2) {
                 mbar_wait(rbar + 1, ap); ap ^= 1u;                     // tanh(actor layer 1)
-                issue_phase(2, tn1, x, head1, w_net1, mb1);
+                issue_phase(2, tn1, x, head1, w_net1, hb1);
             }
         }
     } else if (my_tiles > 0) {
@@ -497,7 +502,7 @@ __global__ void __launch_bounds__(THREADS + 32, 1)
         const bool rng = !value_only && noise == nullptr && rng_step != nullptr;      // in-kernel Gaussian noise
         const bool sample = !value_only && noise != nullptr;                         // caller-supplied noise rows
         const unsigned long long step = rng ? *rng_step + rng_offset : 0ull;
-        uint32_t n_phase = 0, mc_phase = 0, ma_phase = 0;
+        uint32_t n_phase = 0, mc_phase = 0, ma_phase = 0, h_phase = 0;   // h_phase: one head of each network per tile
         auto tile_full = [&](long long tile) { return aligned && tile < n_tiles && (n_envs - tile * TILE) >= TILE; };
         // copy-engine fetch of a whole tile's observation rows into stage `buf` (thread 0)
         auto fetch_obs = [&](long long tile, int buf) {
@@ -589,7 +594,7 @@ __global__ void __launch_bounds__(THREADS + 32, 1)
             TRACE();
             // ---- heads: value (column 32 of the tile's X buffer), action means (columns 48..63) ----
             const uint32_t xb = tlane + x_cols(it & 1);
-            mbar_wait(mbar, mc_phase); mc_phase ^= 1u;
+            mbar_wait(hbar, h_phase);
             tc_fence_after();
             TRACE();
             __syncwarp();
@@ -599,7 +604,7 @@ __global__ void __launch_bounds__(THREADS + 32, 1)
                 if (t < nv) values[e0 + t] = __uint_as_float(v);
             }
             if (n_nets == 2) {
-                mbar_wait(mbar + 1, ma_phase); ma_phase ^= 1u;
+                mbar_wait(hbar + 1, h_phase);
                 tc_fence_after();
                 TRACE();
                 __syncwarp();
@@ -669,6 +674,7 @@ __global__ void __launch_bounds__(THREADS + 32, 1)
                     }
                 }
             }
+            h_phase ^= 1u;
             tc_fence_before();
         }
     }
@@ -737,7 +743,7 @@ int launch_policy_tc(const void *packed, int obs_dim, int act_dim, const float *
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     const Smem sp = smem_plan(obs_dim, act_dim);
-    const size_t smem = sp.bars + 128;   // 11 mbarriers + the TMEM address slot
+    const size_t smem = sp.bars + 128;   // 13 mbarriers + the TMEM address slot
     if (ensure_smem(dev, (const void *)policy_tc_kernel, smem) != SNG_OK) return SNG_ERR_CUDA;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const long long n_tiles = (n_envs + TILE - 1) / TILE;

@@ -281,6 +281,30 @@ def test_sharded_rollout_equals_the_unsharded_one():
         h.close()
 
 
+@pytest.mark.timeout(240)
+def test_concurrent_policy_and_step_kernels_do_not_stall():
+    """Regression: with step-kernel CTAs of another stream sharing its SMs, a delayed compute warp of the policy kernel
+    could fall two completions behind the issuer on the mbarrier that signalled both the heads and the next tile's
+    layer 0, and wait forever (r2: 50 back-to-back replays of a two-branch rollout graph at 65,536 envs hung every
+    time).  Heads now complete on their own barrier; 60 replays must finish."""
+    from smart_nanogrid_gym_b200 import BatchedSmartNanogridEnv
+    from smart_nanogrid_gym_b200.rollout import MlpPolicy, RolloutBuffer, ShardedGraphedRollout
+    per, n = 32768, 24
+    envs = [BatchedSmartNanogridEnv(per, device="cuda:0", seed=0, env_gid0=k * per, **KW) for k in range(2)]
+    torch.manual_seed(0)
+    policy = MlpPolicy(29, 11).to("cuda:0")
+    bufs = [RolloutBuffer(n, per, 29, 11, "cuda:0") for _ in range(2)]
+    obs = [e.reset() for e in envs]
+    starts = [torch.ones(per, dtype=torch.uint8, device="cuda:0") for _ in range(2)]
+    collect = ShardedGraphedRollout(envs, policy, bufs)
+    for _ in range(60):
+        obs, starts = collect(obs, starts)
+    torch.cuda.synchronize()
+    assert all(bool(torch.isfinite(b.advantages).all()) for b in bufs) and all(e.error_flags() == 0 for e in envs)
+    for e in envs:
+        e.close()
+
+
 def test_shipped_sb3_policy_on_the_recorded_episode():
     """the reference's shipped PPO checkpoint (tests/golden/sb3_ppo_4ch_policy.npz) drives the
     N = 4 station: on the observations of the reference's recorded episode G1 the fused kernel's deterministic
