@@ -4,6 +4,7 @@
 #pragma once
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -412,6 +413,7 @@ public:
     int device = 0;
     int warps_per_cta = 0;   // 0 = auto
     int use_generic = 0, use_bulk = 1, host_chunks = 0, ctas_per_sm = 0;
+    int host_ramp = getenv("SNG_HOST_RAMP") ? atoi(getenv("SNG_HOST_RAMP")) : 1;   // step_host: small first chunks (experiment switch)
     int kernel_variant = 0;   // 0 / 2 one block per warp, 1 persistent pipelined
     int lanes_per_env = 0;    // 0 auto (4 for specialised stations of more than 32 spots), 1 / 2: that many lanes per env
     int num_sms = 148;
@@ -861,8 +863,24 @@ public:
         SNG_CUDA(cudaEventRecord(ev0, st));
         SNG_CUDA(cudaStreamWaitEvent(copy_in, ev0, 0));
         SNG_CUDA(cudaStreamWaitEvent(copy_out, ev0, 0));
+        // chunk boundaries: equal chunks, except that the first one is cut into 1/4 + 1/4 + 1/2 -- the D2H engine (the
+        // bottleneck) idles until the first chunk's actions have arrived and its step has run, so that chunk is small
+        std::vector<long long> cut;
+        for (long long e0 = 0; e0 < E; e0 += per) {
+            if (e0 == 0 && host_ramp && per % 4096 == 0) { cut.push_back(0); cut.push_back(per / 4); cut.push_back(per / 2); }
+            else cut.push_back(e0);
+        }
+        cut.push_back(E);
+        chunks = (int)cut.size() - 1;
+        while ((int)ev_in.size() < chunks) {
+            cudaEvent_t e1, e2;
+            SNG_CUDA(cudaEventCreateWithFlags(&e1, cudaEventDisableTiming));
+            SNG_CUDA(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming));
+            ev_in.push_back(e1);
+            ev_step.push_back(e2);
+        }
         for (int c = 0; c < chunks; ++c) {
-            const long long e0 = (long long)c * per, n = (e0 + per <= E) ? per : E - e0;
+            const long long e0 = cut[c], n = cut[c + 1] - cut[c];
             SNG_CUDA(cudaMemcpyAsync((char *)buf.actions + (size_t)e0 * p.A * sizeof(real), (const char *)a + (size_t)e0 * p.A * sizeof(real),
                                      (size_t)n * p.A * sizeof(real), cudaMemcpyHostToDevice, copy_in));
             SNG_CUDA(cudaEventRecord(ev_in[c], copy_in));
@@ -873,10 +891,11 @@ public:
             SNG_CUDA(cudaEventRecord(ev_step[c], st));
             SNG_CUDA(cudaStreamWaitEvent(copy_out, ev_step[c], 0));
             SNG_CUDA(cudaMemcpyAsync(obs + (size_t)e0 * p.D, buf.obs + (size_t)e0 * p.D, (size_t)n * p.D * sizeof(float), cudaMemcpyDeviceToHost, copy_out));
-            SNG_CUDA(cudaMemcpyAsync((char *)rew + (size_t)e0 * sizeof(real), (char *)buf.reward + (size_t)e0 * sizeof(real), (size_t)n * sizeof(real),
-                                     cudaMemcpyDeviceToHost, copy_out));
-            SNG_CUDA(cudaMemcpyAsync(done + e0, buf.done + e0, (size_t)n, cudaMemcpyDeviceToHost, copy_out));
         }
+        // rewards and done flags are 4 % of the bytes: one copy each behind the last chunk's rows instead of two small
+        // copies per chunk (every copy costs ~10 us of fixed time on the D2H engine, which is the bottleneck)
+        SNG_CUDA(cudaMemcpyAsync(rew, buf.reward, (size_t)E * sizeof(real), cudaMemcpyDeviceToHost, copy_out));
+        SNG_CUDA(cudaMemcpyAsync(done, buf.done, (size_t)E, cudaMemcpyDeviceToHost, copy_out));
         SNG_CUDA(cudaStreamSynchronize(copy_out));
         SNG_CUDA(cudaStreamSynchronize(st));
         return SNG_OK;
