@@ -47,7 +47,7 @@ def main():
         rd = sum(x["dram__bytes_read.sum"] for x in launches) / n
         wr = sum(x["dram__bytes_write.sum"] for x in launches) / n
         cfg = NanogridConfig(**bench.WORKLOADS[wl]["kw"])
-        alg = bench.algorithmic_bytes_per_env_step(cfg.n_spots, int(cfg.batt), int(cfg.pv)) * envs
+        alg = bench.algorithmic_bytes_per_env_step(cfg.n_spots, int(cfg.batt), int(cfg.pv), cfg.hours_ahead) * envs
         e = {"kernel": launches[0]["kernel"], "dram_bytes_read": rd, "dram_bytes_write": wr, "dram_bytes_per_launch": rd + wr,
              "algorithmic_bytes_per_launch": alg, "launches_profiled": n,
              "ncu_duration_us": sum(x.get("gpu__time_duration.sum", 0.0) for x in launches) / n / 1e3,
