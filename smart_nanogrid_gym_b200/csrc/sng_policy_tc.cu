@@ -377,20 +377,30 @@ __device__ __forceinline__ void issue_phase(int phase, uint32_t tn, uint32_t x, 
 }
 
 // ------------------------------------------------------------------------------------------
-// The forward kernel.  One CTA per SM, persistent over tiles of 128 envs.
-//   warps 0..15  compute: warp w owns TMEM lanes 32 (w % 4) .. + 31 (the envs of those rows) and column block w / 4
-//                (16 of a layer's 64 columns) in the epilogues -- four warps per scheduler partition, which is what the
-//                tanh epilogue needs to hide its dependent FMA chains;
-//   warp 16      issues every tcgen05.mma (one elected lane), in the order the operands become ready.
+// The forward kernel.  One CTA per SM, persistent over tiles of 128 envs, three warp roles:
+//   warps 0..15  compute: the tanh epilogues.  Warp w owns TMEM lanes 32 (w % 4) .. + 31 (the envs of those rows) and column
+//                block w / 4 (16 of a layer's 64 columns) -- four warps per scheduler partition, which is what the epilogue
+//                needs to hide its dependent FMA chains;
+//   warp 16      issues every tcgen05.mma (one elected lane), in the order the operands become ready;
+//   warps 17..20 io (thread = row of the tile): convert the NEXT tile's observation rows into the tf32 hi / lo A operand
+//                in TMEM, and finish the PREVIOUS heads: value, DiagGaussian sample (noise drawn here), clip, log-prob,
+//                coalesced stores.  Both are latency-bound, short phases; on the compute warps they were 35 % of a tile.
 // Critic and actor are two independent chains of  MMA -> tanh epilogue -> MMA -> ...; the compute warps alternate
 // between them, so while they run the epilogue of one network the tensor pipe runs the layer of the other:
-//     tensor pipe   c0 a0 | c1      | a1      | ch      | ah  c0' a0' | ...
-//     compute             | E(c0)   | E(a0)   | E(c1)   | E(a1)  X'   | value, actions | E(c0') ...
-// (c0 = critic layer 0, ch = critic head, ' = next tile).  The next tile's X is converted into the other X buffer while
-// the heads run, so the pipeline never drains between tiles.  Synchronisation: `rbar` (512 arrivals: "operands of the
-// next layer are in TMEM") compute -> issuer, `mbar[net]` / `hbar[net]` (tcgen05.commit: hidden layers / heads) issuer -> compute.
+//     tensor pipe   c0 a0 | c1      | a1 c0' a0' | ch      | ah      | c1'     | ...
+//     compute             | E(c0)   | E(a0)      | E(c1)   | E(a1)   | E(c0')  | E(a0') ...
+//     io            X'                                     |  value, actions (this tile)  X'' ...
+// (c0 = critic layer 0, ch = critic head, ' = next tile).  Synchronisation, all mbarriers: io -> issuer `xbar[buf]` (X of a
+// tile is in TMEM), compute -> issuer `rbar[net]` (tanh of a layer is in TMEM), issuer -> compute `mbar[net][layer]`
+// (tcgen05.commit of a hidden layer), issuer -> io, compute `hbar[net][buf]` (commit of a head).  Every barrier that can be
+// signalled again before a slow waiter has looked is doubled by tile parity: a parity wait cannot be two completions
+// behind (r2: a single issuer -> compute barrier per chain stalled forever when another kernel shared the SM).
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(THREADS + 32, 1)
+constexpr int IO_THREADS = TILE;
+constexpr int ALL_THREADS = THREADS + 32 + IO_THREADS;
+__device__ __forceinline__ void io_barrier() { asm volatile("bar.sync 2, %0;" ::"n"(IO_THREADS) : "memory"); }
+
+__global__ void __launch_bounds__(ALL_THREADS, 1)
     policy_tc_kernel(const float *__restrict__ img, const float *__restrict__ obs, const float *__restrict__ noise,
                      const float *__restrict__ low, const float *__restrict__ high, float *raw_actions, float *actions,
                      float *values, float *log_probs, long long n_envs, int D, int A, int aligned, long long *trace,
@@ -403,171 +413,129 @@ __global__ void __launch_bounds__(THREADS + 32, 1)
     extern __shared__ __align__(128) unsigned char smem[];
     const Smem sp = smem_plan(D, A);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const bool issuer = warp == THREADS / 32;
-    const int cb = warp >> 2;                               // column block of this warp in the epilogues
-    const int t = (warp & 3) * 32 + lane;                   // row of the tile = TMEM lane = env
+    const bool issuer = warp == THREADS / 32, io = warp > THREADS / 32;
+    const int cb = warp >> 2;                               // column block of a compute warp in the epilogues
+    const int t = (warp & 3) * 32 + lane;                   // row of the tile = TMEM lane = env (compute and io warps)
     float *obs_s0 = reinterpret_cast<float *>(smem + sp.stages);
     float *noise_s = reinterpret_cast<float *>(smem + sp.stages + 2 * sp.obs_stage);
     float *raw_s = reinterpret_cast<float *>(smem + sp.stages + 2 * sp.obs_stage + sp.row_stage);
     float *act_s = reinterpret_cast<float *>(smem + sp.stages + 2 * sp.obs_stage + 2 * sp.row_stage);
     float *const_s = reinterpret_cast<float *>(smem + sp.consts);
-    float *lp_s = reinterpret_cast<float *>(smem + sp.lp);
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + sp.bars);
-    uint64_t *wbar = bars;                                  // [3] weight image: critic layer 0 | rest of the critic | actor
-    uint64_t *obar = bars + 3;                              // [2] observation rows of the even / odd tiles have landed
-    uint64_t *nbar = bars + 5;                              // noise rows have landed
-    // compute -> issuer, 16 arrivals (one per warp) each: X of a tile is in TMEM | tanh(critic layer) is | tanh(actor layer) is.
-    // (One barrier per chain: a thread's next wait after arriving on a chain's barrier depends on that very phase, so a fast
-    //  warp can never arrive twice in one phase and complete it on behalf of a slow one.)
-    uint64_t *xbar = bars + 6, *rbar = bars + 7;            // rbar[2]: critic, actor
-    uint64_t *mbar = bars + 9;                              // [2] issuer -> compute: the critic's / the actor's hidden layer is complete
-    // [2] issuer -> compute: the critic's / the actor's HEAD is complete.  Separate from mbar: the next tile's layer 0 can
-    // complete before a delayed compute warp has observed this tile's head (both are issued back to back once the next
-    // tile's X is staged), and a parity wait cannot be two completions behind -- with one barrier per chain such a
-    // warp waits forever (seen when step-kernel CTAs of another stream shared the SM).
-    uint64_t *hbar = bars + 11;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 13);
+    uint64_t *wbar = bars;                                  // [4] weight image: critic layer 0 | actor layer 0 | rest of the critic | rest of the actor
+    uint64_t *obar = bars + 4;                              // [2] observation rows of the even / odd tiles have landed
+    uint64_t *nbar = bars + 6;                              // noise rows have landed
+    uint64_t *xbar = bars + 7;                              // [2] io -> issuer (4 warp arrivals): X of an even / odd tile is in TMEM
+    uint64_t *rbar = bars + 9;                              // [2] compute -> issuer (16 warp arrivals): tanh(critic / actor layer) is in TMEM
+    uint64_t *mbar = bars + 11;                             // [2][2] issuer -> compute: layer 0 / layer 1 of the critic / the actor is complete
+    uint64_t *hbar = bars + 15;                             // [2][2] issuer -> io, compute: the critic's / the actor's head of an even / odd tile
+    constexpr int N_BARS = 19;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + N_BARS);
     const bool value_only = actions == nullptr;
     const int n_nets = value_only ? 1 : 2;
-
-    if (threadIdx.x == 0) {
-        for (int i = 0; i < 13; ++i) mbar_init(bars + i, (i >= 6 && i <= 8) ? THREADS / 32 : 1);   // compute -> issuer: one arrival per warp
-        fence_mbar_init();
-        // the weight image: one copy per CTA, in three pieces in the order they are needed (the first tile's critic
-        // layer 0 starts as soon as its 16 KB have landed)
-        const uint32_t cut[4] = {0u, (uint32_t)(OFF_W1HI * sizeof(float)), (uint32_t)(NET_FLOATS * sizeof(float)), IMG_SMEM_BYTES};
-        for (int piece = 0; piece < 3; ++piece) {
-            mbar_expect_tx(wbar + piece, cut[piece + 1] - cut[piece]);
-            for (uint32_t off = cut[piece]; off < cut[piece + 1]; off += 16384u) {
-                const uint32_t n = cut[piece + 1] - off < 16384u ? cut[piece + 1] - off : 16384u;
-                bulk_g2s(smem + off, reinterpret_cast<const unsigned char *>(img) + off, n, wbar + piece);
-            }
-        }
-    }
-    if (threadIdx.x >= 64 && threadIdx.x < 64 + 4 * NH && actions != nullptr) {   // per-action constants of the sampling epilogue
-        const int q = (threadIdx.x - 64) / NH, a = (threadIdx.x - 64) % NH;
-        float v = 0.f;
-        if (a < A) v = q == 0 ? img[OFF_STD + a] : (q == 1 ? img[OFF_STD + 16 + a] : (q == 2 ? low[a] : high[a]));
-        const_s[q * NH + a] = v;
-    }
-    if (warp == 0) tmem_alloc(tmem_slot, 512);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
     const long long n_tiles = (n_envs + TILE - 1) / TILE;
     const long long stride = gridDim.x;
     const long long first_tile = blockIdx.x;
     const int my_tiles = first_tile < n_tiles ? (int)((n_tiles - 1 - first_tile) / stride + 1) : 0;
+    const uint32_t obs_bytes = (uint32_t)(TILE * D * sizeof(float));
+    auto tile_full = [&](long long tile) { return aligned && tile < n_tiles && (n_envs - tile * TILE) >= TILE; };
+    // copy-engine fetch of a whole tile's observation rows into stage `buf` (one thread)
+    auto fetch_obs = [&](long long tile, int buf) {
+        mbar_expect_tx(obar + buf, obs_bytes);
+        bulk_g2s(reinterpret_cast<unsigned char *>(obs_s0) + (size_t)buf * sp.obs_stage, obs + tile * TILE * D, obs_bytes, obar + buf);
+    };
+
+    // the weight image, one copy per CTA, in four pieces in the order they are needed
+    constexpr uint32_t L0_BYTES = (uint32_t)(OFF_W1HI * sizeof(float)), NET_BYTES = (uint32_t)(NET_FLOATS * sizeof(float));
+    auto fetch_weights = [&](int piece) {       // 0: critic layer 0, 1: actor layer 0, 2: rest of the critic, 3: rest of the actor
+        const uint32_t lo = (piece & 1) * NET_BYTES + (piece >= 2 ? L0_BYTES : 0u), hi = (piece & 1) * NET_BYTES + (piece >= 2 ? NET_BYTES : L0_BYTES);
+        mbar_expect_tx(wbar + piece, hi - lo);
+        for (uint32_t off = lo; off < hi; off += 16384u) {
+            const uint32_t n = hi - off < 16384u ? hi - off : 16384u;
+            bulk_g2s(smem + off, reinterpret_cast<const unsigned char *>(img) + off, n, wbar + piece);
+        }
+    };
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < N_BARS; ++i)
+            mbar_init(bars + i, (i == 7 || i == 8) ? IO_THREADS / 32 : ((i == 9 || i == 10) ? THREADS / 32 : 1));
+        fence_mbar_init();
+        // head of the dependency chain first: the first tile's observation rows and the critic's layer 0 (the rest of the
+        // image is requested after the CTA barrier by a thread that would otherwise wait: issuing a bulk copy costs the
+        // issuing thread ~100 cycles, and everybody waits for this thread at the barrier)
+        if (tile_full(first_tile)) fetch_obs(first_tile, 0);
+        fetch_weights(0);
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (threadIdx.x == 0) {                     // compute warp 0, about to wait for the first layer anyway
+        if (!value_only) fetch_weights(1);
+        fetch_weights(2);
+        if (!value_only) fetch_weights(3);
+        if (tile_full(first_tile + stride)) fetch_obs(first_tile + stride, 1);
+    }
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16);   // TMEM as seen by this warp's 32 lanes
 
     if (issuer) {
         // ---- the MMA issuer ----
-        const uint32_t tm = *tmem_slot;
         const uint32_t w_base = smem_u32(smem);
         const uint32_t w_net1 = w_base + (uint32_t)(NET_FLOATS * sizeof(float));
-        const uint32_t mb0 = smem_u32(mbar), mb1 = mb0 + 8u, hb0 = smem_u32(hbar), hb1 = hb0 + 8u;
-        const uint32_t tn0 = tm + C_NET0, tn1 = tn0 + C_NETSTRIDE;
-        uint32_t xp = 0u, cp = 0u, ap = 0u;
+        const uint32_t mb = smem_u32(mbar), hb = smem_u32(hbar);        // mbar[net][layer] at mb + 8 (2 net + layer), hbar[net][buf] likewise
+        const uint32_t tn0 = tmem + C_NET0, tn1 = tn0 + C_NETSTRIDE;
+        uint32_t cp = 0u, ap = 0u;
+        // layer 0 of both networks for this CTA's tile number `it`: needs only X of that tile
+        auto layer0 = [&](int it) {
+            const int buf = it & 1;
+            const uint32_t x = tmem + x_cols(buf);
+            mbar_wait(xbar + buf, (uint32_t)((it >> 1) & 1));
+            if (it == 0) mbar_wait(wbar, 0);
+            issue_phase(0, tn0, x, 0, w_base, mb);
+            if (n_nets == 2) {
+                if (it == 0) mbar_wait(wbar + 1, 0);
+                issue_phase(0, tn1, x, 0, w_net1, mb + 16u);
+            }
+        };
+        if (my_tiles > 0) layer0(0);
 #pragma unroll 1
         for (int it = 0; it < my_tiles; ++it) {
-            const uint32_t x = tm + x_cols(it & 1);
-            // the heads write into the (by then unused) lo half of the tile's own X buffer: P is overwritten by the next
-            // tile's layer 0 before the compute warps get to read the heads
+            const int buf = it & 1;
+            const uint32_t x = tmem + x_cols(buf);
+            // the heads write into the (by then unused) lo half of the tile's own X buffer
             const uint32_t head0 = x + 32u, head1 = x + 48u;
-            mbar_wait(xbar, xp); xp ^= 1u;                             // X of this tile
-            if (it == 0) mbar_wait(wbar, 0);
-            issue_phase(0, tn0, x, 0, w_base, mb0);
-            if (n_nets == 2) {
-                if (it == 0) mbar_wait(wbar + 2, 0);
-                issue_phase(0, tn1, x, 0, w_net1, mb1);
-            }
             mbar_wait(rbar, cp); cp ^= 1u;                             // tanh(critic layer 0)
-            if (it == 0) mbar_wait(wbar + 1, 0);
-            issue_phase(1, tn0, x, 0, w_base, mb0);
+            if (it == 0) mbar_wait(wbar + 2, 0);
+            issue_phase(1, tn0, x, 0, w_base, mb + 8u);
             if (n_nets == 2) {
                 mbar_wait(rbar + 1, ap); ap ^= 1u;                     // tanh(actor layer 0)
-                issue_phase(1, tn1, x, 0, w_net1, mb1);
+                if (it == 0) mbar_wait(wbar + 3, 0);
+                issue_phase(1, tn1, x, 0, w_net1, mb + 24u);
             }
+            // the NEXT tile's layer 0 goes in ahead of this tile's heads: the compute warps then find it complete when
+            // they finish this tile's last epilogue (the heads -- 50 small MMAs -- would otherwise sit in front of it)
+            if (it + 1 < my_tiles) layer0(it + 1);
             mbar_wait(rbar, cp); cp ^= 1u;                             // tanh(critic layer 1)
-            issue_phase(2, tn0, x, head0, w_base, hb0);
+            issue_phase(2, tn0, x, head0, w_base, hb + 8u * (uint32_t)buf);
             if (n_nets == 2) {
                 mbar_wait(rbar + 1, ap); ap ^= 1u;                     // tanh(actor layer 1)
-                issue_phase(2, tn1, x, head1, w_net1, hb1);
+                issue_phase(2, tn1, x, head1, w_net1, hb + 8u * (uint32_t)(2 + buf));
             }
         }
-    } else if (my_tiles > 0) {
-        const uint32_t tmem = *tmem_slot;
-        const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16);   // ... as seen by this warp's 32 lanes
+    } else if (!io) {
+        // ---- compute warps: the tanh epilogues; the epilogue of one network overlaps the MMAs of the other ----
         const uint32_t tc = tlane + C_NET0, ta = tc + C_NETSTRIDE;           // critic / actor regions
-        const uint32_t obs_bytes = (uint32_t)(TILE * D * sizeof(float)), row_bytes = (uint32_t)(TILE * A * sizeof(float));
-        const bool rng = !value_only && noise == nullptr && rng_step != nullptr;      // in-kernel Gaussian noise
-        const bool sample = !value_only && noise != nullptr;                         // caller-supplied noise rows
-        const unsigned long long step = rng ? *rng_step + rng_offset : 0ull;
-        uint32_t n_phase = 0, mc_phase = 0, ma_phase = 0, h_phase = 0;   // h_phase: one head of each network per tile
-        auto tile_full = [&](long long tile) { return aligned && tile < n_tiles && (n_envs - tile * TILE) >= TILE; };
-        // copy-engine fetch of a whole tile's observation rows into stage `buf` (thread 0)
-        auto fetch_obs = [&](long long tile, int buf) {
-            mbar_expect_tx(obar + buf, obs_bytes);
-            bulk_g2s(reinterpret_cast<unsigned char *>(obs_s0) + (size_t)buf * sp.obs_stage, obs + tile * TILE * D, obs_bytes, obar + buf);
-        };
-        // X = [obs | 0 | 1 1] of tile `tile` -> tf32 hi / lo -> X buffer `it & 1` in TMEM (the A operand of layer 0), then
-        // tell the issuer.  Each warp converts 8 of the 32 columns of its 32 rows.
-        auto stage_x = [&](long long tile, int it) {
-            const int buf = it & 1;
-            float *obs_s = reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(obs_s0) + (size_t)buf * sp.obs_stage);
-            const long long e0 = tile * TILE;
-            const int nv = (int)((n_envs - e0) < TILE ? (n_envs - e0) : TILE);
-            if (tile_full(tile)) {
-                mbar_wait(obar + buf, (uint32_t)((it >> 1) & 1));
-                TRACE();
-            } else {                                                     // ragged last tile / unaligned rows: plain loads
-                for (int k = threadIdx.x; k < nv * D; k += THREADS) obs_s[k] = obs[e0 * D + k];
-                compute_barrier();
-            }
-            uint32_t xh[8], xl[8];
-            const float *row = obs_s + t * D;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int k = 8 * cb + j;
-                const float x = k < D ? (t < nv ? row[k] : 0.f) : (k >= KP - 2 ? 1.0f : 0.f);
-                split_tf32(x, xh[j], xl[j]);
-            }
-            __syncwarp();
-            tmem_st8(tlane + x_cols(buf) + 8 * cb, xh);
-            tmem_st8(tlane + x_cols(buf) + 32 + 8 * cb, xl);
-            tmem_wait_st();
-            tc_fence_before();
-            mbar_arrive_warp(xbar);
-        };
-
-        if (threadIdx.x == 0) {
-            if (tile_full(first_tile)) fetch_obs(first_tile, 0);
-            if (tile_full(first_tile + stride)) fetch_obs(first_tile + stride, 1);
-        }
-        stage_x(first_tile, 0);
-
 #pragma unroll 1
         for (int it = 0; it < my_tiles; ++it) {
-            const long long tile = first_tile + (long long)it * stride;
-            const long long e0 = tile * TILE;
-            const int nv = (int)((n_envs - e0) < TILE ? (n_envs - e0) : TILE);
-            const bool full = tile_full(tile);
+            const uint32_t ph = (uint32_t)(it & 1);                      // every mbar[net][layer] completes once per tile
             TRACE();
-            if (sample) {
-                if (full) {
-                    if (threadIdx.x == 0) {                              // the previous tile's samples were taken before its barrier
-                        mbar_expect_tx(nbar, row_bytes);
-                        bulk_g2s(noise_s, noise + e0 * A, row_bytes, nbar);
-                    }
-                } else {
-                    for (int k = threadIdx.x; k < nv * A; k += THREADS) noise_s[k] = noise[e0 * A + k];
-                    compute_barrier();
-                }
-            }
-            // ---- hidden layers: the epilogue of one network overlaps the MMAs of the other ----
 #pragma unroll
             for (int layer = 0; layer < 2; ++layer) {
                 const uint32_t src = layer == 0 ? C_P : C_S;
-                mbar_wait(mbar, mc_phase); mc_phase ^= 1u;
+                mbar_wait(mbar + layer, ph);
+                // layer 0 of this tile was issued ahead of the previous tile's heads, and its epilogue overwrites Q, which
+                // those heads read: wait for them (normally long complete)
+                if (layer == 0 && it > 0) mbar_wait(hbar + ((it - 1) & 1), (uint32_t)(((it - 1) >> 1) & 1));
                 tc_fence_after();
                 TRACE();
                 tanh_epilogue(tc + src + 16 * cb, tc + C_Q + 16 * cb);
@@ -575,7 +543,8 @@ __global__ void __launch_bounds__(THREADS + 32, 1)
                 mbar_arrive_warp(rbar);
                 TRACE();
                 if (n_nets == 2) {
-                    mbar_wait(mbar + 1, ma_phase); ma_phase ^= 1u;
+                    mbar_wait(mbar + 2 + layer, ph);
+                    if (layer == 0 && it > 0) mbar_wait(hbar + 2 + ((it - 1) & 1), (uint32_t)(((it - 1) >> 1) & 1));
                     tc_fence_after();
                     TRACE();
                     tanh_epilogue(ta + src + 16 * cb, ta + C_Q + 16 * cb);
@@ -584,103 +553,157 @@ __global__ void __launch_bounds__(THREADS + 32, 1)
                     TRACE();
                 }
             }
-            // ---- while the heads run: the next tile's X into the other buffer, then prefetch the tile after it ----
-            if (it + 1 < my_tiles) {
-                stage_x(tile + stride, it + 1);
-                // stage `it & 1` held this tile's rows: every warp read them before it arrived for X(it), and this tile's
-                // layers (observed complete above) were issued after all of those arrivals -- the stage is free
-                if (threadIdx.x == 0 && tile_full(tile + 2 * stride)) fetch_obs(tile + 2 * stride, it & 1);
+        }
+    } else if (my_tiles > 0) {
+        // ---- io warps ----
+        const int tio = (int)threadIdx.x - (THREADS + 32);                    // 0 .. 127
+        const uint32_t row_bytes = (uint32_t)(TILE * A * sizeof(float));
+        const bool rng = !value_only && noise == nullptr && rng_step != nullptr;      // in-kernel Gaussian noise
+        const bool sample = !value_only && noise != nullptr;                         // caller-supplied noise rows
+        const unsigned long long step = rng ? *rng_step + rng_offset : 0ull;
+        uint32_t n_phase = 0;
+        if (!value_only && tio < 4 * NH) {          // per-action constants of the sampling epilogue (first read behind the io barriers below)
+            const int q = tio / NH, a = tio % NH;
+            float v = 0.f;
+            if (a < A) v = q == 0 ? img[OFF_STD + a] : (q == 1 ? img[OFF_STD + 16 + a] : (q == 2 ? low[a] : high[a]));
+            const_s[q * NH + a] = v;
+        }
+        // X = [obs | 0 | 1 1] of this CTA's tile number `it` -> tf32 hi / lo -> X buffer `it & 1` in TMEM (the A operand of
+        // layer 0), then tell the issuer; the observation stage is refilled with the tile two further on.
+        // (The X buffer is free: its previous tile's heads -- which live in its lo half -- were consumed by this warp's own
+        //  tail two calls ago, after the commit that covers all of that tile's MMAs.)
+        auto stage_x = [&](long long tile, int it) {
+            const int buf = it & 1;
+            float *obs_s = reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(obs_s0) + (size_t)buf * sp.obs_stage);
+            const long long e0 = tile * TILE;
+            const int nv = (int)((n_envs - e0) < TILE ? (n_envs - e0) : TILE);
+            const bool full = tile_full(tile);
+            if (full) {
+                mbar_wait(obar + buf, (uint32_t)((it >> 1) & 1));
+            } else {                                                     // ragged last tile / unaligned rows: plain loads
+                for (int k = tio; k < nv * D; k += IO_THREADS) obs_s[k] = obs[e0 * D + k];
+                io_barrier();
             }
-            TRACE();
-            // ---- heads: value (column 32 of the tile's X buffer), action means (columns 48..63) ----
-            const uint32_t xb = tlane + x_cols(it & 1);
-            mbar_wait(hbar, h_phase);
-            tc_fence_after();
-            TRACE();
+            const float *row = obs_s + t * D;
             __syncwarp();
-            if (cb == 0) {                         // warp-uniform
-                const uint32_t v = tmem_ld1(xb + 32);
-                tmem_wait_ld();
-                if (t < nv) values[e0 + t] = __uint_as_float(v);
-            }
-            if (n_nets == 2) {
-                mbar_wait(hbar + 1, h_phase);
-                tc_fence_after();
-                TRACE();
-                __syncwarp();
-                // DiagGaussian sample, clip to the Box, log-probability: the four warps that share a row block split the
-                // action columns (4 each), so the work ahead of the tile's last barrier is a quarter of a full row
-                const int a0 = 4 * cb;
-                if (a0 < A) {                      // warp-uniform
-                    uint32_t out[4];
-                    tmem_ld4(xb + 48 + a0, out);
-                    tmem_wait_ld();
-                    if (sample && full) mbar_wait(nbar, n_phase);
-                    float zz[4] = {0.f, 0.f, 0.f, 0.f};
-                    if (rng) {
-                        const unsigned long long gid = rng_gid0 + (unsigned long long)(e0 + t);
-                        uint32_t x[4];
-                        philox4x32_10((uint32_t)gid, (uint32_t)(gid >> 32), (uint32_t)cb, (uint32_t)step, (uint32_t)rng_seed,
-                                      (uint32_t)(rng_seed >> 32) ^ (uint32_t)(step >> 32), x);
-                        box_muller(x[0], x[1], zz[0], zz[1]);
-                        box_muller(x[2], x[3], zz[2], zz[3]);
-                    }
-                    float lp = 0.f;
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int a = a0 + j;
-                        if (a < A) {
-                            const float sd = const_s[a], ls = const_s[NH + a];
-                            const float z = sample ? noise_s[t * A + a] : zz[j];
-                            if (rng && noise_out && t < nv) noise_out[(e0 + t) * A + a] = z;
-                            const float x = fmaf(z, sd, __uint_as_float(out[j]));
-                            raw_s[t * A + a] = x;
-                            act_s[t * A + a] = fminf(fmaxf(x, const_s[2 * NH + a]), const_s[3 * NH + a]);   // SB3 clips Box actions before env.step
-                            lp += -0.5f * z * z - ls - 0.91893853320467274f;                              // log N(x; mean, std)
-                        }
-                    }
-                    lp_s[cb * TILE + t] = lp;
+            for (int half = 0; half < 2; ++half) {
+                uint32_t xh[16], xl[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int k = 16 * half + j;
+                    const float x = k < D ? (t < nv ? row[k] : 0.f) : (k >= KP - 2 ? 1.0f : 0.f);
+                    split_tf32(x, xh[j], xl[j]);
                 }
-                if (sample && full) n_phase ^= 1u;
-                const int n_parts = (A + 3) / 4;
+                tmem_st16(tlane + x_cols(buf) + 16 * half, xh);
+                tmem_st16(tlane + x_cols(buf) + 32 + 16 * half, xl);
+            }
+            tmem_wait_st();
+            tc_fence_before();
+            mbar_arrive_warp(xbar + buf);
+            io_barrier();                                                // every io thread is done with this observation stage
+            if (tio == 0 && tile_full(tile + 2 * stride)) fetch_obs(tile + 2 * stride, buf);
+        };
+
+        stage_x(first_tile, 0);
+        if (my_tiles > 1) stage_x(first_tile + stride, 1);
+
+#pragma unroll 1
+        for (int it = 0; it < my_tiles; ++it) {
+            const long long tile = first_tile + (long long)it * stride;
+            const long long e0 = tile * TILE;
+            const int nv = (int)((n_envs - e0) < TILE ? (n_envs - e0) : TILE);
+            const bool full = tile_full(tile);
+            const int buf = it & 1;
+            const uint32_t hph = (uint32_t)((it >> 1) & 1);
+            if (sample) {                                                // noise_s: the previous tail ended with a barrier
                 if (full) {
-                    // the two row slabs leave as coalesced 16-byte stores by all compute threads (a copy-engine store
-                    // issued by one thread held that thread -- and with it the next tile's first barrier -- for ~0.9 us)
-                    compute_barrier();
-                    TRACE();
-                    if (cb == 0) {
-                        float lp = lp_s[t];
-                        for (int q = 1; q < n_parts; ++q) lp += lp_s[q * TILE + t];
-                        log_probs[e0 + t] = lp;
+                    if (tio == 0) {
+                        mbar_expect_tx(nbar, row_bytes);
+                        bulk_g2s(noise_s, noise + e0 * A, row_bytes, nbar);
                     }
+                } else {
+                    for (int k = tio; k < nv * A; k += IO_THREADS) noise_s[k] = noise[e0 * A + k];
+                    io_barrier();
+                }
+            }
+            // ---- this tile's heads: value (column 32 of its X buffer), action means (columns 48..63), into registers ----
+            const uint32_t xb = tlane + x_cols(buf);
+            uint32_t out[16];
+            mbar_wait(hbar + buf, hph);
+            tc_fence_after();
+            __syncwarp();
+            const uint32_t value_bits = tmem_ld1(xb + 32);
+            if (n_nets == 2) {
+                mbar_wait(hbar + 2 + buf, hph);
+                tc_fence_after();
+                __syncwarp();
+                tmem_ld16(xb + 48, out);
+            }
+            tmem_wait_ld();
+            // The X buffer is free now (the heads' commits cover every MMA that read it, and their outputs are in
+            // registers): stage the tile that uses it next -- two tiles on -- BEFORE the sampling work, so that the
+            // issuer finds X of the next tile ready a whole tile early and can run its layer 0 ahead of the heads.
+            if (it + 2 < my_tiles) stage_x(tile + 2 * stride, it + 2);
+            if (t < nv) values[e0 + t] = __uint_as_float(value_bits);
+            if (n_nets == 2) {
+                if (sample && full) { mbar_wait(nbar, n_phase); n_phase ^= 1u; }
+                // DiagGaussian sample, clip to the Box, log-probability.  In-kernel noise: one Philox block per four
+                // action columns, keyed by (seed, step), counter = (global env, column block)
+                float lp = 0.f;
+#pragma unroll
+                for (int q = 0; q < NH / 4; ++q) {
+                    if (4 * q < A) {                                     // warp-uniform
+                        float zz[4] = {0.f, 0.f, 0.f, 0.f};
+                        if (rng) {
+                            const unsigned long long gid = rng_gid0 + (unsigned long long)(e0 + t);
+                            uint32_t x[4];
+                            philox4x32_10((uint32_t)gid, (uint32_t)(gid >> 32), (uint32_t)q, (uint32_t)step, (uint32_t)rng_seed,
+                                          (uint32_t)(rng_seed >> 32) ^ (uint32_t)(step >> 32), x);
+                            box_muller(x[0], x[1], zz[0], zz[1]);
+                            box_muller(x[2], x[3], zz[2], zz[3]);
+                        }
+                        float part = 0.f;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const int a = 4 * q + j;
+                            if (a < A) {
+                                const float sd = const_s[a], ls = const_s[NH + a];
+                                const float z = sample ? noise_s[t * A + a] : zz[j];
+                                if (rng && noise_out && t < nv) noise_out[(e0 + t) * A + a] = z;
+                                const float x = fmaf(z, sd, __uint_as_float(out[a]));
+                                raw_s[t * A + a] = x;
+                                act_s[t * A + a] = fminf(fmaxf(x, const_s[2 * NH + a]), const_s[3 * NH + a]);   // SB3 clips Box actions before env.step
+                                part += -0.5f * z * z - ls - 0.91893853320467274f;                            // log N(x; mean, std)
+                            }
+                        }
+                        lp += part;
+                    }
+                }
+                if (t < nv) log_probs[e0 + t] = lp;
+                io_barrier();                                            // all rows of the two slabs are in shared memory
+                if (full) {                                              // coalesced 16-byte stores
                     const int nvec = (int)(row_bytes / 16);
                     const float4 *rs = reinterpret_cast<const float4 *>(raw_s), *as = reinterpret_cast<const float4 *>(act_s);
                     float4 *rg = reinterpret_cast<float4 *>(raw_actions + e0 * A), *ag = reinterpret_cast<float4 *>(actions + e0 * A);
-                    for (int k = threadIdx.x; k < 2 * nvec; k += THREADS) {
+                    for (int k = tio; k < 2 * nvec; k += IO_THREADS) {
                         if (k < nvec) rg[k] = rs[k];
                         else ag[k - nvec] = as[k - nvec];
                     }
-                    TRACE();
                 } else {
-                    compute_barrier();
-                    if (cb == 0 && t < nv) {
-                        float lp = lp_s[t];
-                        for (int q = 1; q < n_parts; ++q) lp += lp_s[q * TILE + t];
-                        log_probs[e0 + t] = lp;
-                    }
-                    for (int k = threadIdx.x; k < nv * A; k += THREADS) {
+                    for (int k = tio; k < nv * A; k += IO_THREADS) {
                         raw_actions[e0 * A + k] = raw_s[k];
                         actions[e0 * A + k] = act_s[k];
                     }
                 }
+                io_barrier();                                            // the slabs may be overwritten by the next tile
             }
-            h_phase ^= 1u;
             tc_fence_before();
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(*tmem_slot, 512);
+    if (warp == 1) tmem_dealloc(*tmem_slot, 512);
     if (trace && blockIdx.x == 0 && threadIdx.x == 0) trace[254] = clock64();
 }
 
@@ -743,7 +766,7 @@ int launch_policy_tc(const void *packed, int obs_dim, int act_dim, const float *
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     const Smem sp = smem_plan(obs_dim, act_dim);
-    const size_t smem = sp.bars + 128;   // 13 mbarriers + the TMEM address slot
+    const size_t smem = sp.bars + 160;   // 19 mbarriers + the TMEM address slot
     if (ensure_smem(dev, (const void *)policy_tc_kernel, smem) != SNG_OK) return SNG_ERR_CUDA;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const long long n_tiles = (n_envs + TILE - 1) / TILE;
@@ -751,7 +774,7 @@ int launch_policy_tc(const void *packed, int obs_dim, int act_dim, const float *
     if (grid > sms) grid = sms;
     const int aligned = aligned16(obs) && aligned16(noise) && aligned16(raw_actions) && aligned16(actions) && aligned16(packed);
     if (!aligned16(packed)) return SNG_ERR_ARG;
-    policy_tc_kernel<<<(unsigned)grid, THREADS + 32, smem, (cudaStream_t)stream>>>(reinterpret_cast<const float *>(packed), obs, noise, low, high,
+    policy_tc_kernel<<<(unsigned)grid, ALL_THREADS, smem, (cudaStream_t)stream>>>(reinterpret_cast<const float *>(packed), obs, noise, low, high,
                                                                              raw_actions, actions, values, log_probs,
                                                                              (long long)n_envs, obs_dim, act_dim, aligned, g_trace,
                                                                              rng_step, rng_offset, rng_seed, rng_gid0, noise_out);
