@@ -257,6 +257,15 @@ int64_t sng_launch_count(const sng_env *env);
  * both ways (unaligned buffers and a partial last block always take the scalar path); number of env
  * chunks sng_step_host pipelines over PCIe (0 = auto). */
 int sng_set_tuning(sng_env *env, int warps_per_cta, int use_generic_kernel, int use_bulk_copy, int host_chunks);
+/* How sng_step launches its kernel.  0 (default): an ordinary launch.  1: programmatic dependent launch -- the kernel may
+ * start (block scheduling, parameter and index set-up) while its predecessor in the stream is still running and waits for
+ * it (griddepcontrol.wait) before it touches memory; hides the kernel-to-kernel launch latency of small batches.
+ * 2: the same, and the per-env state is loaded BEFORE the wait: only valid when the predecessor in the stream does not
+ * write this handle's state (e.g. the policy kernel of a rollout loop; NOT another sng_step of the same handle). */
+int sng_set_launch_mode(sng_env *env, int mode);
+/* The same switch for sng_policy_forward_packed / _sampled (process-wide): 1 = programmatic dependent launch. */
+int sng_policy_set_launch_mode(int mode);
+
 /* Tuning knob: which step kernel runs: 0 (default) one 32-env block per warp, with four lanes per env for
  * specialised stations of more than 32 spots; 1 the persistent software-pipelined kernel (measured slower,
  * see DESIGN.md); 2 one block per warp and always one lane per env; 3 like 0 with two lanes per env.

@@ -137,6 +137,12 @@ class BatchedSmartNanogridEnv:
         one lane per env, 3 two lanes per env for large stations (include/sng.h)."""
         nat.check(self._lib.sng_set_pipeline(self._h, kernel_variant, ctas_per_sm))
 
+    def set_launch_mode(self, mode=0):
+        """0 ordinary launches; 1 programmatic dependent launch of the step kernel (hides the kernel-to-kernel latency of
+        small batches); 2 the same with the state loads ahead of the wait -- only when the previous kernel in the stream
+        does not write this env's state (a policy kernel, not another step of this env).  include/sng.h."""
+        nat.check(self._lib.sng_set_launch_mode(self._h, int(mode)))
+
     def _plane(self, f):
         """Plane f of the blocked per-spot state -> a de-blocked [E, N] copy (words)."""
         return self._spot[:, :, f, :].permute(0, 2, 1).reshape(-1, self.cfg.n_spots)[:self.num_envs].contiguous()

@@ -214,6 +214,12 @@ int sng_gae(const float *rewards, const float *values, const uint8_t *episode_st
     return SNG_OK;
 }
 
+int sng_set_launch_mode(sng_env *env, int mode)
+{
+    SNG_ENV_CHECK(env);
+    return done(env, env->eng->set_launch_mode(mode));
+}
+
 int sng_set_pipeline(sng_env *env, int kernel_variant, int ctas_per_sm)
 {
     SNG_ENV_CHECK(env);

@@ -32,6 +32,7 @@ struct EngineBase {
     virtual int probe_arrival_gap(const uint32_t *x, uint32_t *g, long long n, cudaStream_t st) = 0;
     virtual int set_tuning(int warps_per_cta, int use_generic, int use_bulk, int host_chunks) = 0;
     virtual int set_pipeline(int kernel_variant, int ctas_per_sm) = 0;
+    virtual int set_launch_mode(int mode) = 0;
     int64_t launches = 0;
     std::string error;
 };
@@ -157,6 +158,13 @@ __global__ void __launch_bounds__(SNG_PIPE_THREADS, SNG_PIPE_MINB)
     }
 }
 
+// Programmatic dependent launch (sm_90+): a kernel launched with the programmatic-stream-serialization attribute may start
+// while its predecessor in the stream is still running; griddepcontrol.wait blocks until the predecessor has completed
+// and its writes are visible (a no-op for ordinary launches), griddepcontrol.launch_dependents lets the successor start.
+// A kernel releases its dependents only AFTER its own wait, so completion is transitive along the stream.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 #ifndef SNG_STEP_MAXT
 #define SNG_STEP_MAXT 128
 #endif
@@ -172,7 +180,9 @@ enum : int {
     STAGE_SCALAR = 0,     // plain 4-byte loads / stores: unaligned buffers; always used for a partial last block
     STAGE_TMA_LOAD = 1,   // actions: one cp.async.bulk per warp (mbarrier complete_tx)
     STAGE_TMA_STORE = 2,  // observations: one cp.async.bulk per warp (bulk_group)
-    STAGE_ALIGNED = 4     // buffers are 16-byte aligned: 16-byte coalesced vector loads / stores where no TMA bit is set
+    STAGE_ALIGNED = 4,    // buffers are 16-byte aligned: 16-byte coalesced vector loads / stores where no TMA bit is set
+    STAGE_PDL_EARLY = 8   // programmatic dependent launch whose predecessor does not touch this handle's state: the state
+                          // loads are issued BEFORE waiting for the predecessor (sng_set_launch_mode(env, 2))
 };
 
 // MULTI: n_steps > 1 (rollout); the single-step instantiation carries no slab arithmetic.
@@ -237,7 +247,10 @@ __global__ void __launch_bounds__(SNG_STEP_MAXT, (EXACT || NCT / L > 32) ? 2 : (
         }
         // the state loads go first: they have the longest way (DRAM), and every instruction ahead of them is time
         // the warp holds its slot with nothing in flight
+        const bool early = !MULTI && (mode & STAGE_PDL_EARLY);
+        if (!MULTI && !early) { pdl_wait(); pdl_launch_dependents(); }     // ordinary launch: no-ops
         if (valid) load_state<real, NCT / L, L>(p, e, spot, st);
+        if (early) { pdl_wait(); pdl_launch_dependents(); }                // actions (and everything written below) after the predecessor
         if (tma_load) {
             if (lane == 0) {
                 if (s == 0) {
@@ -413,6 +426,7 @@ public:
     int device = 0;
     int warps_per_cta = 0;   // 0 = auto
     int use_generic = 0, use_bulk = 1, host_chunks = 0, ctas_per_sm = 0;
+    int launch_mode = 0;      // 0 ordinary launches, 1 programmatic dependent launch, 2 the same with the state loads ahead of the wait
     int host_ramp = getenv("SNG_HOST_RAMP") ? atoi(getenv("SNG_HOST_RAMP")) : 1;   // step_host: small first chunks (experiment switch)
     int kernel_variant = 0;   // 0 / 2 one block per warp, 1 persistent pipelined
     int lanes_per_env = 0;    // 0 auto (4 for specialised stations of more than 32 spots), 1 / 2: that many lanes per env
@@ -677,7 +691,18 @@ public:
         if (rc) return rc;
         const long long groups = (q.n_envs + EPW - 1) / EPW;       // one warp each
         const unsigned grid = (unsigned)((groups + wpb - 1) / wpb);
-        kern<<<grid, wpb * 32, smem, st>>>(q, actions, obs, reward, done, n_steps, bulk);
+        if (launch_mode > 0 && n_steps == 1) {
+            cudaLaunchConfig_t lc = {};
+            lc.gridDim = dim3(grid); lc.blockDim = dim3(wpb * 32); lc.dynamicSmemBytes = smem; lc.stream = st;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            at[0].val.programmaticStreamSerializationAllowed = 1;
+            lc.attrs = at; lc.numAttrs = 1;
+            const int mode = bulk | (launch_mode == 2 ? STAGE_PDL_EARLY : 0);
+            SNG_CUDA(cudaLaunchKernelEx(&lc, kern, q, actions, obs, reward, done, n_steps, mode));
+        } else {
+            kern<<<grid, wpb * 32, smem, st>>>(q, actions, obs, reward, done, n_steps, bulk);
+        }
         ++launches;
         SNG_CUDA(cudaGetLastError());
         return SNG_OK;
@@ -832,6 +857,11 @@ public:
         if (rc) return rc;
         if (!a || !obs || !rew || !done) { error = "sng_step_host: null host buffer"; return SNG_ERR_ARG; }
         DeviceGuard guard(device);
+        struct ModeGuard {      // the chunk kernels follow each other and copies: ordinary launches
+            int &m; int saved;
+            explicit ModeGuard(int &r) : m(r), saved(r) { m = 0; }
+            ~ModeGuard() { m = saved; }
+        } mode_guard(launch_mode);
         const long long E = p.n_envs;
         int chunks = host_chunks > 0 ? host_chunks : (E >= (1 << 16) ? 8 : 1);
         long long per = ((E + chunks - 1) / chunks + 1023) / 1024 * 1024;      // multiple of 32 (and of the TMA slab alignment)
@@ -948,6 +978,13 @@ public:
         }
         if (hc < 0 || hc > 64) { error = "sng_set_tuning: host_chunks must be in 0..64"; return SNG_ERR_ARG; }
         warps_per_cta = w; use_generic = g; use_bulk = b; host_chunks = hc;
+        return SNG_OK;
+    }
+
+    int set_launch_mode(int mode) override
+    {
+        if (mode < 0 || mode > 2) { error = "sng_set_launch_mode: mode must be 0, 1 or 2"; return SNG_ERR_ARG; }
+        launch_mode = mode;
         return SNG_OK;
     }
 

@@ -34,6 +34,7 @@
 namespace {
 using namespace sng;
 long long *g_trace = nullptr;      // debugging aid: sng_policy_debug_trace
+int g_policy_pdl = 0;              // sng_policy_set_launch_mode
 
 constexpr int H = 64;        // hidden width of SB3's default MlpPolicy
 constexpr int KP = 32;       // observation width padded to the K of layer 0 (obs_dim <= 30; columns 30, 31 = 1.0)
@@ -459,13 +460,19 @@ __global__ void __launch_bounds__(ALL_THREADS, 1)
         for (int i = 0; i < N_BARS; ++i)
             mbar_init(bars + i, (i == 7 || i == 8) ? IO_THREADS / 32 : ((i == 9 || i == 10) ? THREADS / 32 : 1));
         fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    // programmatic dependent launch: everything above ran while the predecessor (the step kernel that writes `obs`) was
+    // still running; nothing below may start before it has completed.  No-ops for an ordinary launch.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (threadIdx.x == 0) {
         // head of the dependency chain first: the first tile's observation rows and the critic's layer 0 (the rest of the
         // image is requested after the CTA barrier by a thread that would otherwise wait: issuing a bulk copy costs the
         // issuing thread ~100 cycles, and everybody waits for this thread at the barrier)
         if (tile_full(first_tile)) fetch_obs(first_tile, 0);
         fetch_weights(0);
     }
-    if (warp == 1) tmem_alloc(tmem_slot, 512);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -741,6 +748,13 @@ bool aligned16(const void *p) { return p == nullptr || (reinterpret_cast<uintptr
 
 extern "C" void sng_policy_debug_trace(long long *device_buf) { g_trace = device_buf; }
 
+extern "C" int sng_policy_set_launch_mode(int mode)
+{
+    if (mode < 0 || mode > 1) return SNG_ERR_ARG;
+    g_policy_pdl = mode;
+    return SNG_OK;
+}
+
 extern "C" size_t sng_policy_packed_bytes(void) { return (size_t)IMG_FLOATS * sizeof(float); }
 
 extern "C" int sng_policy_pack(const sng_mlp *mlp, void *packed, void *stream)
@@ -774,6 +788,19 @@ int launch_policy_tc(const void *packed, int obs_dim, int act_dim, const float *
     if (grid > sms) grid = sms;
     const int aligned = aligned16(obs) && aligned16(noise) && aligned16(raw_actions) && aligned16(actions) && aligned16(packed);
     if (!aligned16(packed)) return SNG_ERR_ARG;
+    if (g_policy_pdl) {
+        cudaLaunchConfig_t lc = {};
+        lc.gridDim = dim3((unsigned)grid); lc.blockDim = dim3(ALL_THREADS); lc.dynamicSmemBytes = smem; lc.stream = (cudaStream_t)stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        lc.attrs = at; lc.numAttrs = 1;
+        const cudaError_t e = cudaLaunchKernelEx(&lc, policy_tc_kernel, reinterpret_cast<const float *>(packed), obs, noise, low, high, raw_actions,
+                                                 actions, values, log_probs, (long long)n_envs, obs_dim, act_dim, aligned, g_trace,
+                                                 rng_step, (unsigned long long)rng_offset, (unsigned long long)rng_seed,
+                                                 (unsigned long long)rng_gid0, noise_out);
+        return e == cudaSuccess ? SNG_OK : SNG_ERR_CUDA;
+    }
     policy_tc_kernel<<<(unsigned)grid, ALL_THREADS, smem, (cudaStream_t)stream>>>(reinterpret_cast<const float *>(packed), obs, noise, low, high,
                                                                              raw_actions, actions, values, log_probs,
                                                                              (long long)n_envs, obs_dim, act_dim, aligned, g_trace,

@@ -195,14 +195,19 @@ class RolloutBuffer:
 @torch.no_grad()
 def collect_rollout(env, policy: MlpPolicy, buf: RolloutBuffer, obs: torch.Tensor, episode_starts: torch.Tensor,
                     generator: torch.Generator | None = None, deterministic: bool = False, fused: bool = True,
-                    rng_seed: int | None = None, pack: bool = True, advance_counter: bool = True):
+                    rng_seed: int | None = None, pack: bool = True, advance_counter: bool = True, pdl: bool = False):
     """SB3 OnPolicyAlgorithm.collect_rollouts for a BatchedSmartNanogridEnv: n_steps policy + env steps,
     then GAE.  `obs` [E, D] is the current observation (from reset() or the previous rollout),
     `episode_starts` [E] u8.  Returns (last_obs, last_dones) to carry into the next call.
     Exploration noise: torch.randn (with `generator`) per step, or -- `rng_seed` given, fused kernel -- drawn inside
     the policy kernel (Philox keyed by rng_seed and the policy's step counter: no noise tensor, no RNG launch).
     pack=False / advance_counter=False: the caller packs the weights / advances the step counter itself (several
-    shards collected side by side share both, see ShardedGraphedRollout)."""
+    shards collected side by side share both, see ShardedGraphedRollout).
+    pdl=True (fused kernel only): policy and step kernels are launched with programmatic dependent launch -- each starts
+    while the other is draining (block scheduling, barrier / TMEM set-up, and the step's state loads, which the policy
+    kernel does not touch) and waits for it before reading what it wrote.  Measured on a B200 at 65,536 envs: SLOWER
+    (33.6 vs 30.4 us per rollout step: early step CTAs spin next to the policy CTAs that are still running), so it is
+    off by default; for step-after-step launches of small batches it gains 4-6 % (bench.py --pdl)."""
     low, high = env.action_low.float(), env.action_high.float()
     buf.observations[0].copy_(obs)
     buf.episode_starts[0].copy_(episode_starts.to(torch.uint8))    # episode_starts[s + 1] aliases dones[s]
@@ -212,6 +217,28 @@ def collect_rollout(env, policy: MlpPolicy, buf: RolloutBuffer, obs: torch.Tenso
         policy.pack_weights()          # once per rollout: the weights do not change while it is collected
     if in_kernel_noise and (getattr(policy, "rng_counter", None) is None or policy.rng_counter.device != obs.device):
         policy.rng_counter = torch.zeros(1, dtype=torch.int64, device=obs.device)   # rollout steps drawn so far
+    pdl = pdl and fused
+    if pdl:
+        env.set_launch_mode(2)         # the step's predecessor is the policy kernel: state loads ahead of the wait
+        nat.check(nat.lib().sng_policy_set_launch_mode(1))
+    try:
+        _rollout_steps(env, policy, buf, low, high, fused, in_kernel_noise, rng_seed, deterministic, generator)
+    finally:
+        if pdl:
+            env.set_launch_mode(0)
+            nat.check(nat.lib().sng_policy_set_launch_mode(0))
+    if in_kernel_noise and advance_counter:
+        policy.rng_counter += buf.n_steps
+    last_obs = buf.observations[buf.n_steps]
+    if fused:
+        policy.fused_forward(last_obs, None, None, None, None, None, buf.last_values, None, repack=False)
+    else:
+        buf.last_values.copy_(policy.predict_values(last_obs))
+    buf.compute_returns_and_advantage(buf.last_values, buf.dones[buf.n_steps - 1])
+    return last_obs, buf.dones[buf.n_steps - 1]
+
+
+def _rollout_steps(env, policy, buf, low, high, fused, in_kernel_noise, rng_seed, deterministic, generator):
     for s in range(buf.n_steps):
         o = buf.observations[s]
         if in_kernel_noise:
@@ -230,15 +257,6 @@ def collect_rollout(env, policy: MlpPolicy, buf: RolloutBuffer, obs: torch.Tenso
         # the kernel writes the next observation, the reward and the done flag (= the next step's episode start)
         # into the buffer slabs
         env.step(buf.actions[s], out=(buf.observations[s + 1], buf.rewards[s], buf.dones[s]))
-    if in_kernel_noise and advance_counter:
-        policy.rng_counter += buf.n_steps
-    last_obs = buf.observations[buf.n_steps]
-    if fused:
-        policy.fused_forward(last_obs, None, None, None, None, None, buf.last_values, None, repack=False)
-    else:
-        buf.last_values.copy_(policy.predict_values(last_obs))
-    buf.compute_returns_and_advantage(buf.last_values, buf.dones[buf.n_steps - 1])
-    return last_obs, buf.dones[buf.n_steps - 1]
 
 
 class GraphedRollout:
@@ -248,7 +266,7 @@ class GraphedRollout:
     or -- rng_seed=None -- by torch's default CUDA generator (graph-safe); `deterministic=True` uses the mean."""
 
     def __init__(self, env, policy: MlpPolicy, buf: RolloutBuffer, deterministic: bool = False, fused: bool = True,
-                 rng_seed: int | None = 0):
+                 rng_seed: int | None = 0, pdl: bool = False):
         dev = buf.rewards.device
         self.env, self.policy, self.buf = env, policy, buf
         self.obs_in = torch.zeros(buf.n_envs, buf.observations.shape[2], device=dev)
@@ -257,12 +275,12 @@ class GraphedRollout:
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):                     # warm-up outside capture (lazy inits, cuBLAS workspaces)
             self.obs_in.copy_(env.obs)
-            collect_rollout(env, policy, buf, self.obs_in, self.starts_in, deterministic=deterministic, fused=fused, rng_seed=rng_seed)
+            collect_rollout(env, policy, buf, self.obs_in, self.starts_in, deterministic=deterministic, fused=fused, rng_seed=rng_seed, pdl=pdl)
         torch.cuda.current_stream(dev).wait_stream(side)
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.last_obs, self.last_dones = collect_rollout(env, policy, buf, self.obs_in, self.starts_in,
-                                                             deterministic=deterministic, fused=fused, rng_seed=rng_seed)
+                                                             deterministic=deterministic, fused=fused, rng_seed=rng_seed, pdl=pdl)
 
     def __call__(self, obs: torch.Tensor, episode_starts: torch.Tensor):
         self.obs_in.copy_(obs)

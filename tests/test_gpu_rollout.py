@@ -243,6 +243,45 @@ def test_graphed_rollout_with_in_kernel_noise_advances_between_replays():
     env.close()
 
 
+def test_programmatic_dependent_launch_changes_nothing_but_timing():
+    """sng_set_launch_mode / sng_policy_set_launch_mode: the same rollout with and without programmatic dependent launch
+    (step kernel in mode 2: state loads ahead of the wait; policy kernel in mode 1) is bit-identical, eager and graphed;
+    step-after-step launches in mode 1 equal ordinary launches."""
+    from smart_nanogrid_gym_b200 import BatchedSmartNanogridEnv
+    from smart_nanogrid_gym_b200.rollout import GraphedRollout, MlpPolicy, RolloutBuffer
+    E, n = 4096 + 32, 30
+    torch.manual_seed(2)
+    policy = MlpPolicy(29, 11).to("cuda:0")
+    res = []
+    for pdl in (False, True):
+        env = BatchedSmartNanogridEnv(E, device="cuda:0", seed=3, **KW)
+        buf = RolloutBuffer(n, E, 29, 11, "cuda:0")
+        env.reset()
+        collect = GraphedRollout(env, policy, buf, rng_seed=4, pdl=pdl)
+        obs = env.reset(reset_battery=True)
+        policy.rng_counter.zero_()
+        starts = torch.ones(E, dtype=torch.uint8, device="cuda:0")
+        for _ in range(3):
+            obs, starts = collect(obs, starts)
+        res.append((buf.raw_actions.clone(), buf.rewards.clone(), buf.observations.clone(), buf.advantages.clone(), env._spot.clone()))
+        assert env.error_flags() == 0
+        env.close()
+    for a, b in zip(res[0], res[1]):
+        assert torch.equal(a, b)
+    envs = [BatchedSmartNanogridEnv(E, device="cuda:0", seed=5, **KW) for _ in range(2)]
+    envs[1].set_launch_mode(1)
+    for e in envs:
+        e.reset()
+    g = torch.Generator(device="cuda:0").manual_seed(1)
+    for s in range(30):
+        a = envs[0].sample_actions(g)
+        o0, o1 = envs[0].step(a), envs[1].step(a)
+        assert torch.equal(o0[0], o1[0]) and torch.equal(o0[1], o1[1]) and torch.equal(o0[2], o1[2])
+    assert torch.equal(envs[0]._spot, envs[1]._spot)
+    for e in envs:
+        e.close()
+
+
 def test_sharded_rollout_equals_the_unsharded_one():
     """Two env shards collected side by side (ShardedGraphedRollout: parallel graph branches, in-kernel noise keyed by
     global env id) produce bit for bit what one env of the summed size does."""
