@@ -1,0 +1,38 @@
+"""Small workloads for compute-sanitizer: step kernels (specialised, generic, four lanes, rollout), policy kernels, GAE."""
+import os, sys, torch
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+from smart_nanogrid_gym_b200 import BatchedSmartNanogridEnv
+from smart_nanogrid_gym_b200.rollout import MlpPolicy, RolloutBuffer, collect_rollout
+dev = "cuda:0"
+KW = dict(charging_mode="bounded", vehicle_uncharged_penalty_mode="sparse", time_interval="1h")
+g = torch.Generator(device=dev).manual_seed(0)
+for kw, E in ((dict(number_of_chargers=10), 333), (dict(number_of_chargers=10, hours_ahead=5), 97),
+              (dict(number_of_chargers=64, time_interval="15min"), 96), (dict(number_of_chargers=7, vehicle_to_everything=True), 65)):
+    k = dict(KW); k.update(kw)
+    env = BatchedSmartNanogridEnv(E, device=dev, seed=1, want_terminal_obs=True, want_diagnostics=True, **k)
+    env.reset()
+    for s in range(env.cfg.n_steps + 3):
+        env.step(env.sample_actions(g))
+    acts = torch.stack([env.sample_actions(g) for _ in range(4)]).contiguous()
+    env.rollout(acts)
+    assert env.error_flags() == 0
+    env.close()
+    print("step ok", kw, flush=True)
+env = BatchedSmartNanogridEnv(640 + 17, device=dev, seed=2, number_of_chargers=10, **KW)
+policy = MlpPolicy(29, 11).to(dev)
+buf = RolloutBuffer(6, env.num_envs, 29, 11, dev)
+obs = env.reset()
+starts = torch.ones(env.num_envs, dtype=torch.uint8, device=dev)
+for kwargs in (dict(rng_seed=3), dict(generator=g), dict(deterministic=True), dict(rng_seed=3, pdl=True)):
+    obs, starts = collect_rollout(env, policy, buf, obs, starts, **kwargs)
+    torch.cuda.synchronize()
+    print("rollout ok", kwargs.keys(), flush=True)
+E = 128 * 9          # aligned: the copy-engine paths of the policy kernel
+o = torch.rand(E, 29, device=dev); raw = torch.empty(E, 11, device=dev); act = torch.empty_like(raw)
+val = torch.empty(E, device=dev); lp = torch.empty(E, device=dev)
+low = torch.zeros(11, device=dev); high = torch.ones(11, device=dev)
+policy.fused_forward(o, torch.randn(E, 11, device=dev), low, high, raw, act, val, lp)
+policy.fused_forward(o, None, None, None, None, None, val, None, repack=False)
+policy.fused_forward(o, torch.randn(E, 11, device=dev), low, high, raw, act, val, lp, cuda_cores=True)
+torch.cuda.synchronize()
+print("policy ok", flush=True)
