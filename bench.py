@@ -15,9 +15,13 @@ over all envs of the rank (the launches of one episode are captured in a CUDA gr
 
 Beside the headline the same JSON line carries `legs`: every other BASELINE configuration measured in the same
 run (untimed for the headline) -- `c4_strong` (1,048,576 envs SPLIT over the ranks: 131,072 per GPU at 8),
-`c5` (64 spots, 96 steps, 262,144 envs per GPU), `c3` (PPO rollout collection at 65,536 envs, policy in the loop),
-`c2` (4,096 envs, per-step launches and the multi-step sng_rollout launch) and `rollout_kernel` (sng_rollout with
-pre-supplied actions at 65,536 / 131,072 envs) -- each with value, ms_per_step, roofline and clocks.
+`c5` (64 spots, 96 steps, 262,144 envs per GPU), `c3` / `c3_sb3` (PPO rollout collection at 65,536 envs, policy in the
+loop: fresh-init N = 10 network / the reference's shipped checkpoint), `c2` (4,096 envs, per-step launches and the
+multi-step sng_rollout launch), `rollout_kernel` (sng_rollout with pre-supplied actions at 65,536 / 131,072 envs) and
+`generic` (stations off the reference's observation shape: 5-step horizon, two-day PV, no PV) -- each with value,
+ms_per_step, roofline (measured DRAM traffic from profiles/roofline_traffic.json) and clocks.  `e2e` carries the box's
+concurrent pinned-memcpy ceiling for the same bytes; `cpu_baseline` (the C port) and `cpu_baseline_live` (the live
+Python reference from baseline/_ref) are timed on the host cores at N = 1.
 """
 import argparse
 import json

@@ -4,7 +4,6 @@
 #pragma once
 #include <cmath>
 #include <cstdio>
-#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -427,7 +426,6 @@ public:
     int warps_per_cta = 0;   // 0 = auto
     int use_generic = 0, use_bulk = 1, host_chunks = 0, ctas_per_sm = 0;
     int launch_mode = 0;      // 0 ordinary launches, 1 programmatic dependent launch, 2 the same with the state loads ahead of the wait
-    int host_ramp = getenv("SNG_HOST_RAMP") ? atoi(getenv("SNG_HOST_RAMP")) : 1;   // step_host: small first chunks (experiment switch)
     int kernel_variant = 0;   // 0 / 2 one block per warp, 1 persistent pipelined
     int lanes_per_env = 0;    // 0 auto (4 for specialised stations of more than 32 spots), 1 / 2: that many lanes per env
     int num_sms = 148;
@@ -897,7 +895,7 @@ public:
         // bottleneck) idles until the first chunk's actions have arrived and its step has run, so that chunk is small
         std::vector<long long> cut;
         for (long long e0 = 0; e0 < E; e0 += per) {
-            if (e0 == 0 && host_ramp && per % 4096 == 0) { cut.push_back(0); cut.push_back(per / 4); cut.push_back(per / 2); }
+            if (e0 == 0 && per % 4096 == 0) { cut.push_back(0); cut.push_back(per / 4); cut.push_back(per / 2); }
             else cut.push_back(e0);
         }
         cut.push_back(E);

@@ -150,16 +150,6 @@ __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.
 #define SNG_R8(v, o) "=r"(v[o + 0]), "=r"(v[o + 1]), "=r"(v[o + 2]), "=r"(v[o + 3]), "=r"(v[o + 4]), "=r"(v[o + 5]), "=r"(v[o + 6]), "=r"(v[o + 7])
 #define SNG_W8(v, o) "r"(v[o + 0]), "r"(v[o + 1]), "r"(v[o + 2]), "r"(v[o + 3]), "r"(v[o + 4]), "r"(v[o + 5]), "r"(v[o + 6]), "r"(v[o + 7])
 // 32 lanes x 32 columns: thread l of the warp gets columns [col, col + 32) of TMEM lane (lane base + l)
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
-{
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : SNG_R8(v, 0), SNG_R8(v, 8), SNG_R8(v, 16), SNG_R8(v, 24)
-        : "r"(taddr)
-        : "memory");
-}
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16])
 {
     asm volatile(
@@ -167,22 +157,6 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16])
         "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
         : SNG_R8(v, 0), SNG_R8(v, 8)
         : "r"(taddr)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t (&v)[4])
-{
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
-                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3])
-                 : "r"(taddr)
-                 : "memory");
-}
-__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32])
-{
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
-        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
-        SNG_W8(v, 0), SNG_W8(v, 8), SNG_W8(v, 16), SNG_W8(v, 24)
         : "memory");
 }
 
@@ -195,10 +169,6 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16
         : "memory");
 }
 
-__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8])
-{
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), SNG_W8(v, 0) : "memory");
-}
 __device__ __forceinline__ uint32_t tmem_ld1(uint32_t taddr)
 {
     uint32_t v;
@@ -315,7 +285,6 @@ __device__ __forceinline__ void box_muller(uint32_t x1, uint32_t x2, float &z0, 
     z1 = r * sn;
 }
 
-__device__ __forceinline__ void compute_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(THREADS) : "memory"); }
 
 // hidden-layer epilogue of one warp: 16 accumulator columns [src, src + 16) of its 32 lanes -> tanh -> hi part written back
 // in place (it becomes the A operand of the next layer), lo part to [dst_lo, dst_lo + 16)
@@ -334,7 +303,7 @@ __device__ __forceinline__ void tanh_epilogue(uint32_t src, uint32_t dst_lo)
 
 struct Smem {
     // byte offsets into dynamic shared memory
-    uint32_t obs_stage, row_stage, stages, consts, lp, bars;
+    uint32_t obs_stage, row_stage, stages, consts, bars;
 };
 __host__ __device__ inline Smem smem_plan(int D, int A)
 {
@@ -343,8 +312,7 @@ __host__ __device__ inline Smem smem_plan(int D, int A)
     s.row_stage = align128((uint32_t)(TILE * A * sizeof(float)));
     s.stages = align128(IMG_SMEM_BYTES);                                // obs x 2 | noise | raw actions | clipped actions
     s.consts = s.stages + 2 * s.obs_stage + 3 * s.row_stage;      // std | log_std | low | high, 16 floats each
-    s.lp = s.consts + 4 * NH * (uint32_t)sizeof(float);           // partial log-probabilities [CB][TILE]
-    s.bars = s.lp + CB * TILE * (uint32_t)sizeof(float);
+    s.bars = s.consts + 4 * NH * (uint32_t)sizeof(float);
     return s;
 }
 
@@ -354,10 +322,6 @@ __device__ __forceinline__ void mbar_arrive_warp(uint64_t *bar)
 {
     __syncwarp();
     if ((threadIdx.x & 31) == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
 // Layer `phase` (0: layer 0, X -> P;  1: layer 1, (P, Q) -> S;  2: head, (S, Q) -> `head_out`) of the network whose TMEM
