@@ -505,6 +505,7 @@ def make_env(ctx, wl_key, E, gid0, args=None):
 
 
 PDL_ARG = [-1]       # --pdl, set by main()
+ROLLOUT_PDL = [None]  # --rollout-pdl, set by main(): programmatic dependent launch inside the rollout loop (collect_rollout's pdl)
 
 
 def launch_mode_for(cfg, E):
@@ -610,7 +611,8 @@ def rollout_leg(ctx, wl_key, E, n_steps, shipped=False):
     buf = RolloutBuffer(n_steps, env.num_envs, env.cfg.obs_dim, env.cfg.act_dim, ctx.dev)
     obs = env.reset()
     starts = torch.ones(env.num_envs, dtype=torch.uint8, device=ctx.dev)
-    collect = GraphedRollout(env, policy, buf)
+    rpdl = ROLLOUT_PDL[0] if policy.fused_supported() else None
+    collect = GraphedRollout(env, policy, buf, pdl=rpdl or False)
     state = [obs, starts]
 
     def run(reps):
@@ -643,7 +645,8 @@ def rollout_leg(ctx, wl_key, E, n_steps, shipped=False):
     flops = 2.0 * 2 * (env.cfg.obs_dim * 64 + 64 * 64) + 2.0 * 64 * (env.cfg.act_dim + 1)    # per env: actor + critic + heads
     out = {"value": E * ctx.n_gpus * steps / (ms_max * 1e-3), "unit": UNIT, "ms_per_step": ms_max / steps, "steps": steps,
            "n_steps_per_rollout": n_steps, "envs_per_gpu": E, "total_envs": E * ctx.n_gpus,
-           "launch": "one CUDA graph per rollout (n_steps x [policy kernel, step kernel] + bootstrap value + GAE)",
+           "launch": "one CUDA graph per rollout (n_steps x [policy kernel, step kernel] + bootstrap value + GAE)%s" % (
+               ", programmatic dependent launch: %s" % rpdl if rpdl else ""),
            "policy": "%s tanh MLP %d-64-64-%d actor + critic%s, actions sampled and clipped to the Box, GAE by sng_gae" % (
                "the reference's shipped SB3 PPO checkpoint:" if shipped else "fresh-init (torch seed 0)",
                env.cfg.obs_dim, env.cfg.act_dim, " (fused sng_policy_forward kernel: %s)" % policy.fused_kind()
@@ -779,10 +782,13 @@ def main():
     ap.add_argument("--pdl", type=int, default=-1, help="step-kernel launch mode: 0 ordinary, 1 programmatic dependent launch; -1 = auto "
                     "(1 for small batches, where kernel-to-kernel latency is a visible share of a step)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs")
+    ap.add_argument("--rollout-pdl", default="", help="programmatic dependent launch inside the rollout loop of the c3 legs: "
+                    "policy, step, both (optionally +x: policy CTAs claim their SM's whole shared memory); default off")
     ap.add_argument("--legs", default="all", help="'all', 'none' or a comma list of c4_strong,c5,c3,c3_sharded,c3_sb3,c2,rollout_kernel,generic")
     ap.add_argument("--rollout", type=int, default=0, help="legacy: same as --legs c3 with this many steps per rollout")
     args = ap.parse_args()
     PDL_ARG[0] = args.pdl
+    ROLLOUT_PDL[0] = None if args.rollout_pdl in ("", "none", "off") else args.rollout_pdl
     args.warmup = max(args.warmup, 3)
 
     if args.impl == "reference":

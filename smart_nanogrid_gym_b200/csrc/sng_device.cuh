@@ -41,6 +41,7 @@ constexpr int kDepTab = 208;          // departure-normalisation entries (dep - 
 constexpr int kGapTab = 48;           // thresholds of the geometric arrival gap (43 used)
 constexpr int kSmemTab = kDepTab + kGapTab;   // words of the per-CTA shared-memory copy: [dep | gap]
 
+
 // Per-spot header word: arr | dep << 8 | cap << 16 | next << 24
 //   arr   arrival step of the current / last vehicle (0xFF: none yet this episode)
 //   dep   its departure step (first step the spot is free again)
@@ -80,6 +81,7 @@ template <typename real> struct Params {
     int has_req;      // 0: every vehicle requests SoC 1.0 (sampling without enable_requested_state_of_charge): the
                       //    requested-SoC plane is neither read nor written
     real dt, ev_pmax, ev_eff, b_cap, b_pmax, b_eff, b_dod, b_soc0, sell, cost_w, batt_w, margin;
+    real dt_cap, cap_dt;   // dt / b_cap and b_cap / dt (float32 build: the battery update multiplies instead of dividing)
     // shared read-only tables in global memory (L1-resident; every env of a lock-stepped batch reads the same entry)
     const real *pv_power, *irr_norm, *price, *price_norm;  // [table_len]
     const float *dep_norm;                                 // [kSmemTab]: float(k / 24.0), k < kDepTab | gap thresholds (uint32 bits)
@@ -154,8 +156,12 @@ __device__ __forceinline__ uint32_t geometric_gap_tab(uint32_t x, uint32_t tab_b
         asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(gap_base + 4u * (uint32_t)k));
         return v;
     };
-    while (c < 42 && x < th(c + 1)) ++c;
-    while (c > 0 && x >= th(c)) --c;
+    // the estimate is within one of the answer (verified on every threshold +- 2 and random words by
+    // test_arrival_gap_table_form_equals_the_recurrence): one branch-free correction either way.  th(43..47) = 0, so
+    // c + 1 needs no bound; th(0) is not a threshold
+    const uint32_t up = th(c + 1), dn = th(c);
+    c += (x < up) ? 1 : 0;
+    c -= (c > 0 && x >= dn) ? 1 : 0;          // x >= th(c) excludes x < th(c + 1): at most one of the two corrections applies
     return (uint32_t)c;
 }
 template <bool SMEM> __device__ __forceinline__ uint32_t arrival_gap(uint32_t x, uint32_t tab_base)
@@ -326,7 +332,7 @@ template <int ND, typename real> __device__ __forceinline__ int pv_day_offset(co
 // Env-level part of the observation (envs/smart_nanogrid_environment.py:197-205,
 // central_management_system.py:53-60): disturbances now and `H` steps ahead, battery SoC.
 // ND == 8 is the reference's own shape (PV on, NUMBER_OF_HOURS_AHEAD = 3).
-template <typename real, int NCT, int ND>
+template <typename real, int NCT, int ND, bool FIXED = false>
 __device__ __forceinline__ void write_obs_env(const Params<real> &p, float *obs, int t, real shift, real soc_b, int pvo = 0)
 {
     if (NCT && ND == 8) {
@@ -346,7 +352,7 @@ __device__ __forceinline__ void write_obs_env(const Params<real> &p, float *obs,
             for (int j = 1; j <= p.H; ++j) obs[k++] = (float)__ldg(p.price_norm + t + j);
         }
     }
-    if (p.batt) obs[Offsets<NCT, ND>::batt(p)] = (float)soc_b;
+    if (FIXED || p.batt) obs[Offsets<NCT, ND>::batt(p)] = (float)soc_b;
 }
 
 // Begin an episode at t = 0 (SmartNanogridEnv.reset, envs/smart_nanogrid_environment.py:311-351):
@@ -355,7 +361,7 @@ __device__ __forceinline__ void write_obs_env(const Params<real> &p, float *obs,
 // `spot` points at (this env, spot 0, plane 0).
 // With L lanes per env, lane `sub` handles the spots sub, sub + L, ... (`spot` points at its first one)
 // and lane 0 writes the env-level entries.
-template <typename real, int NCT, int ND, bool SMEM, int L = 1>
+template <typename real, int NCT, int ND, bool SMEM, int L = 1, bool FIXED = false>
 __device__ __forceinline__ void begin_episode(const Params<real> &p, int N, long long e,
                                               typename WordOf<real>::type *spot, uint32_t episode, real shift,
                                               real soc_b, float *obs, int sub = 0)
@@ -372,12 +378,12 @@ __device__ __forceinline__ void begin_episode(const Params<real> &p, int N, long
         if (next == 0u) v = fetch_vehicle<real, SMEM>(p, N, e, i, episode, 0, dep_base);
         // the dense SoC array holds the arrival SoC at slot `arr` (charging_station.py:257-259),
         // so the reset observation shows it for vehicles arriving at t = 0
-        store_vehicle<real>(spot + (size_t)(i / L) * (L * kPlanes * kBlock), v, p.has_req != 0);
+        store_vehicle<real>(spot + (size_t)(i / L) * (L * kPlanes * kBlock), v, !FIXED && p.has_req != 0);
         const bool present = (v.hdr & 0xFFu) == 0u;
         obs[off_soc + i] = present ? (float)v.soc0 : 0.0f;
         obs[off_dep + i] = present ? dep_lookup<SMEM>(p, dep_base, (int)((v.hdr >> 8) & 0xFFu)) : 0.0f;
     }
-    if (L == 1 || sub == 0) write_obs_env<real, NCT, ND>(p, obs, 0, shift, soc_b, pv_day_offset<ND>(p, episode));   // battery SoC survives resets (quirk Q8)
+    if (L == 1 || sub == 0) write_obs_env<real, NCT, ND, FIXED>(p, obs, 0, shift, soc_b, pv_day_offset<ND>(p, episode));   // battery SoC survives resets (quirk Q8)
 }
 
 // Spots whose state loads are issued together (and, in the pipelined kernel, one block ahead).
@@ -411,12 +417,12 @@ __device__ __forceinline__ void load_spots(const typename WordOf<real>::type *sp
 
 // Issue the loads of one env's scalars and first state chunk (consumed by env_step, possibly one block later).
 // (MCT = spots per lane at compile time = N / L.)
-template <typename real, int MCT, int L = 1>
+template <typename real, int MCT, int L = 1, bool FIXED = false>
 __device__ __forceinline__ void load_state(const Params<real> &p, long long e, const typename WordOf<real>::type *spot,
                                            StateRegs<real, MCT> &st)
 {
     st.es = p.envst[e];
-    load_spots<real, Chunk<MCT>::value, L>(spot, 0, p.has_req != 0, st.h, st.r, st.s);
+    load_spots<real, Chunk<MCT>::value, L>(spot, 0, !FIXED && p.has_req != 0, st.h, st.r, st.s);
 }
 
 // Discharging an EV (V2X) -- Charger.discharge_vehicle, charger.py:108-140.  Kept out of line: the
@@ -480,7 +486,9 @@ struct Arrivals {
 // (= lane / (32 / L)) owns the spots sub, sub + L, ...; `spot` and the RowIO are advanced to its first
 // spot, the partial station sums are combined with a shuffle, every lane computes the env-level phase
 // and lane 0 alone writes its results.  All 32 lanes of the warp must be in env_step together then.
-template <typename real, int NCT, int ND, bool EXACT, bool SMEM, bool COOP = false, int L = 1, typename IO = RowIO<real, L>>
+// FIXED: the reference's default station besides the observation shape -- battery on, every vehicle requests SoC 1.0
+// (no requested-SoC plane) -- known at compile time.
+template <typename real, int NCT, int ND, bool EXACT, bool SMEM, bool COOP = false, int L = 1, bool FIXED = false, typename IO = RowIO<real, L>>
 __device__ __forceinline__ Arrivals env_step(const Params<real> &p, long long e, typename WordOf<real>::type *spot,
                                              const StateRegs<real, NCT / L> &st, const IO &io, real *reward_out,
                                              uint8_t *done_out, int sub = 0)
@@ -488,6 +496,8 @@ __device__ __forceinline__ Arrivals env_step(const Params<real> &p, long long e,
     float *const obs = io.row();   // env-level entries, reset observation
     static_assert(!COOP || (NCT > 0 && NCT <= 32 && L == 1), "cooperative admission needs a 32-bit arrival mask");
     static_assert(L == 1 || ((L == 2 || L == 4) && NCT > 0 && NCT % L == 0 && !EXACT), "several lanes per env: compile-time N divisible by L, float32");
+    static_assert(!FIXED || (NCT > 0 && ND > 0 && !EXACT), "FIXED implies a compile-time observation shape");
+    const bool has_req = !FIXED && p.has_req != 0;
     typedef typename WordOf<real>::type word;
     constexpr int MCT = NCT / L;                               // spots per lane at compile time
     const int N = NCT ? NCT : p.N;
@@ -526,7 +536,8 @@ __device__ __forceinline__ Arrivals env_step(const Params<real> &p, long long e,
     uint32_t err = 0;
     // spots whose next vehicle arrives at tn (specialised kernels only: N <= 64)
     typename std::conditional<(MCT > 32), unsigned long long, uint32_t>::type arrivals = 0, discharging = 0;   // bit k: the lane's k-th spot
-    constexpr bool DEFER = NCT > 0 && !EXACT;   // V2X discharges are finished after the (branch-free) hot loop
+    bool special = false;   // some occupied spot of this lane has a negative or NaN action (finished by the cold pass)
+    constexpr bool DEFER = NCT > 0 && !EXACT;   // specialised kernels: V2X discharges are finished after the (branch-free) hot loop
     double cpos[EXACT ? 256 : 1], cneg[EXACT ? 256 : 1];
     int npos = 0, nneg = 0;
     // float32 build: fold the constant factors of the power (a * 22 * 0.95) and of the SoC change
@@ -548,7 +559,7 @@ __device__ __forceinline__ Arrivals env_step(const Params<real> &p, long long e,
 #pragma unroll
             for (int j = 0; j < CH; ++j) { wh[j] = st.h[j]; wr[j] = st.r[j]; ws[j] = st.s[j]; }
         } else {
-            load_spots<real, CH, L>(spot, c, p.has_req != 0, wh, wr, ws);
+            load_spots<real, CH, L>(spot, c, has_req, wh, wr, ws);
         }
 #pragma unroll
         for (int j = 0; j < CH; ++j) {
@@ -579,7 +590,19 @@ __device__ __forceinline__ Arrivals env_step(const Params<real> &p, long long e,
 
             const bool present = arr <= t && t < dep;          // charger.occupancy[t] == 1
             real P = 0, s_new = 0;
-            if (DEFER || a >= (real)0) {
+            if (DEFER) {
+                // branch-free hot loop: a negative (V2X) or NaN action is computed as a zero action here -- the spot
+                // keeps its SoC exactly (s + 0 * kwh / cap == s <= 1) and contributes no power -- and is finished by
+                // the cold pass below, which the env enters only when one of its occupied spots has such an action
+                const real ae = fmax(a, (real)0);              // NaN -> 0
+                const real cap = (real)((hd >> 16) & 0xFFu);
+                const real calc = s_prev + div_cap(ae * kwh, cap);
+                const real clamped = ((real)1 < calc) ? (real)1 : calc;
+                s_new = present ? clamped : (real)0;
+                P = present ? ae * kw : (real)0;
+                special = special || (present && !(a >= (real)0));
+                accumulate(pos_l, lc, i, P);
+            } else if (a >= (real)0) {
                 // a == 0: soc[t] = soc[p], power 0 (charger.py:38-45) -- the same as charging with zero power;
                 // a > 0: charge_vehicle, charger.py:58-90: min(soc + P*dt/cap, 1); power is NOT reduced when clamped
                 const real cap = (real)((hd >> 16) & 0xFFu);
@@ -588,14 +611,6 @@ __device__ __forceinline__ Arrivals env_step(const Params<real> &p, long long e,
                 const real clamped = ((real)1 < calc) ? (real)1 : calc;   // a == 0 gives calc == s_prev <= 1 exactly
                 s_new = present ? clamped : (real)0;
                 P = present ? power : (real)0;
-                if (DEFER) {
-                    // branch-free hot loop: a spot whose action is negative (V2X) or NaN keeps its SoC here
-                    // and is finished by the cold pass below
-                    const bool later = present && !(a >= (real)0);
-                    if (later) discharging |= (decltype(discharging))1 << i;
-                    s_new = later ? s_prev : s_new;
-                    P = later ? (real)0 : P;
-                }
                 if (EXACT) {
                     if (P > 0) cpos[npos++] = (double)P;
                 } else {
@@ -622,7 +637,7 @@ __device__ __forceinline__ Arrivals env_step(const Params<real> &p, long long e,
                 if (NCT) {
                     arrivals |= (decltype(arrivals))1 << i;
                 } else {                                   // generic kernel: admit the arriving vehicle in place
-                    store_vehicle<real>(sp, fetch_vehicle<real, SMEM>(p, N, e, i * L + sub, episode, tn, dep_base), p.has_req != 0);
+                    store_vehicle<real>(sp, fetch_vehicle<real, SMEM>(p, N, e, i * L + sub, episode, tn, dep_base), has_req);
                 }
             }
         }
@@ -633,12 +648,19 @@ __device__ __forceinline__ Arrivals env_step(const Params<real> &p, long long e,
         neg = (real)numpy_sum(cneg, nneg);
         pos = (real)numpy_sum(cpos, npos);
     }
-    while (DEFER && discharging) {   // cold pass: V2X discharges (and NaN actions) left out of the hot loop
+    if (DEFER && special) {   // cold: find those spots again (their headers are unchanged so far)
+        for (int i = 0; i < M; ++i) {
+            const uint32_t hd = (uint32_t)spot[(size_t)i * SP + PL_HDR * kBlock];
+            const bool present = (int)(hd & 0xFFu) <= t && t < (int)((hd >> 8) & 0xFFu);
+            if (present && !(io.action(i, 0) >= (real)0)) discharging |= (decltype(discharging))1 << i;
+        }
+    }
+    while (DEFER && discharging) {   // cold pass: the V2X discharges (and NaN actions) the hot loop computed as zero actions
         const int i = (MCT > 32) ? __ffsll((long long)discharging) - 1 : __ffs((int)discharging) - 1;
         discharging &= discharging - 1;
         word *sp = spot + (size_t)i * SP;
         const uint32_t hd = (uint32_t)sp[PL_HDR * kBlock];
-        const real s_prev = word_to_real(sp[PL_SOC * kBlock], (real)0);   // the hot loop left it unchanged
+        const real s_prev = word_to_real(sp[PL_SOC * kBlock], (real)0);   // the hot loop stored it back unchanged
         const PowerSoc<real> r = discharge_vehicle(io.action(i, 0) * p.ev_pmax * p.ev_eff, p.dt, s_prev, (real)((hd >> 16) & 0xFFu));
 #pragma unroll
         for (int k = 0; k < NLC; ++k) {                   // DEFER implies NCT > 0: the class is i % NLC
@@ -690,14 +712,25 @@ __device__ __forceinline__ Arrivals env_step(const Params<real> &p, long long e,
     const real solar = p.pv ? __ldg(p.pv_power + pvo + t) * es.pv_shift : (real)0;   // :99-103
     real rem = total_power - solar;                                       // :167
     real soc_b = es.soc_b, batt_power = 0, pen_b = 0;
-    if (p.batt) {                                                         // battery_energy_storage_system.py:30-106
+    if (FIXED || p.batt) {                                                // battery_energy_storage_system.py:30-106
         const real ab = io.action_at(N);                                  // actions[-1], :88-89
         if (EXACT) {
             if (ab != ab) err |= FLAG_NAN_ACTION;
         } else {
             nan_probe = fma(ab, (real)0, nan_probe);
         }
-        if (ab > (real)0) {                                               // charge, :46-74
+        if (!EXACT) {
+            // float32 build: one multiply-add with dt / b_cap instead of an IEEE division in each (divergent) branch
+            const real power0 = ab * p.b_pmax * p.b_eff;
+            const real calc = soc_b + power0 * p.dt_cap;
+            const bool chg = ab > (real)0, dis = ab < (real)0;
+            const real power = (dis && calc < (real)0) ? -(soc_b * p.cap_dt) : power0;   // :82-94
+            const real soc_c = ((real)1 < calc) ? (real)1 : calc;                        // :46-74
+            const real soc_d = (calc > (real)0) ? calc : (real)0;                        // :98
+            soc_b = chg ? soc_c : (dis ? soc_d : soc_b);
+            batt_power = (chg || dis) ? power : (real)0;
+            rem = rem + batt_power;                                                      // :102, -((-rem) - power)
+        } else if (ab > (real)0) {                                        // charge, :46-74
             const real power = ab * p.b_pmax * p.b_eff;
             const real calc = soc_b + (power * p.dt) / p.b_cap;
             soc_b = ((real)1 < calc) ? (real)1 : calc;
@@ -726,7 +759,7 @@ __device__ __forceinline__ Arrivals env_step(const Params<real> &p, long long e,
     const real total_cost = p.cost_w * fabs(cost) + total_pen;            // accountant.py:35
     const real reward = -total_cost;                                      // ...environment.py:183
 
-    if (lead) write_obs_env<real, NCT, ND>(p, obs, t, es.pv_shift, soc_b, pvo);   // obs at the pre-increment t, :173
+    if (lead) write_obs_env<real, NCT, ND, FIXED>(p, obs, t, es.pv_shift, soc_b, pvo);   // obs at the pre-increment t, :173
     if (p.spot_power) {
         // diagnostics only (cold): the power of the charging / idle spots is a function of the action and of the
         // header, which is unchanged until the arrivals are admitted below; discharging spots were written above
@@ -758,7 +791,7 @@ __device__ __forceinline__ Arrivals env_step(const Params<real> &p, long long e,
         while (!COOP && arrivals) {
             const int i = (MCT > 32) ? __ffsll((long long)arrivals) - 1 : __ffs((int)arrivals) - 1;
             arrivals &= arrivals - 1;
-            store_vehicle<real>(spot + (size_t)i * SP, fetch_vehicle<real, SMEM>(p, N, e, i * L + sub, episode, tn, dep_base), p.has_req != 0);
+            store_vehicle<real>(spot + (size_t)i * SP, fetch_vehicle<real, SMEM>(p, N, e, i * L + sub, episode, tn, dep_base), has_req);
         }
         es.t_ep = (episode << 8) | (uint32_t)tn;
     } else {
@@ -780,7 +813,7 @@ __device__ __forceinline__ Arrivals env_step(const Params<real> &p, long long e,
             if (L > 1) __syncwarp(pair);
             episode = (episode + 1u) & 0xFFFFFFu;
             if (p.mode == MODE_SAMPLE) shift = sample_pv_shift(p, N, p.gid0 + (unsigned long long)e, episode);
-            begin_episode<real, NCT, ND, SMEM, L>(p, N, e, spot, episode, shift, soc_b, obs, sub);
+            begin_episode<real, NCT, ND, SMEM, L, FIXED>(p, N, e, spot, episode, shift, soc_b, obs, sub);
         }
         es.t_ep = (episode << 8);                                         // t wraps to 0, :178
     }
@@ -804,7 +837,7 @@ __device__ __forceinline__ Arrivals env_step(const Params<real> &p, long long e,
 // of the block: the vehicle is a pure function of (seed, global env, spot, episode, step) and its state
 // words live at block_spot[(spot * 3 + plane) * 32 + env_lane].
 // All 32 lanes must call this (lanes without a valid env pass mask = 0); queue holds 32 * N entries.
-template <typename real, int NCT>
+template <typename real, int NCT, bool FIXED = false>
 __device__ __forceinline__ void admit_arrivals_warp(const Params<real> &p, long long e0, int lane,
                                                     typename WordOf<real>::type *block_spot, const Arrivals &a,
                                                     uint16_t *queue)
@@ -832,7 +865,7 @@ __device__ __forceinline__ void admit_arrivals_warp(const Params<real> &p, long 
         const int tn = __shfl_sync(FULL, a.tn, src);
         if (mine)
             store_vehicle<real>(block_spot + (size_t)i * (kPlanes * kBlock) + src,
-                                fetch_vehicle<real, true>(p, NCT, e0 + src, i, episode, tn, tab_base), p.has_req != 0);
+                                fetch_vehicle<real, true>(p, NCT, e0 + src, i, episode, tn, tab_base), !FIXED && p.has_req != 0);
     }
     __syncwarp();                                 // the queue may be refilled by the next step
 }

@@ -65,7 +65,7 @@ struct DeviceGuard {
 
 // ------------------------------------------------------------------------------------------
 // Step kernels.  One warp = one block of 32 consecutive envs, one thread per env; warps are
-// independent (the only CTA-wide barrier publishes the departure table).  Action rows arrive and
+// fully independent (the step kernel has no CTA-wide barrier: every warp publishes the 1 KB departure table itself).  Action rows arrive and
 // observation rows leave through shared memory, moved by the copy engine (cp.async.bulk, mbarrier
 // complete_tx / bulk_group) or by 16-byte coalesced vector accesses (STAGE_* below); the blocked state is
 // read and written with coalesced 128-byte warp accesses; env_step() is the same body everywhere.
@@ -88,6 +88,19 @@ template <typename real> __device__ __forceinline__ void publish_dep_table(const
     for (int k = threadIdx.x; k < kSmemTab / 4; k += blockDim.x) tab[k] = __ldg(reinterpret_cast<const float4 *>(p.dep_norm) + k);
     __syncthreads();
 }
+
+// The same without a CTA barrier: every warp writes the WHOLE table itself (identical values, so the warps of a CTA may
+// overwrite each other freely) and relies only on its own stores, ordered by __syncwarp.  The warps of a CTA then never
+// wait for one another.
+template <typename real> __device__ __forceinline__ void publish_dep_table_warp(const Params<real> &p)
+{
+    float4 *tab = reinterpret_cast<float4 *>(dep_table_smem());
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int k = 0; k < kSmemTab / 4 / 32; ++k) tab[lane + 32 * k] = __ldg(reinterpret_cast<const float4 *>(p.dep_norm) + lane + 32 * k);
+    __syncwarp();
+}
+static_assert(kSmemTab % 128 == 0, "publish_dep_table_warp copies whole float4 x 32 rounds");
 
 #ifndef SNG_PIPE_THREADS
 #define SNG_PIPE_THREADS 64
@@ -189,7 +202,9 @@ enum : int {
 // the shared memory per warp and of the work per thread, so more warps stay resident.  L > 1 handles whole
 // 32-env state blocks only -- the host sends a ragged last block to the L = 1 instantiation, whose sums
 // associate identically).
-template <typename real, int NCT, int ND, bool EXACT, bool MULTI, int L>
+// FIXED: battery on and no requested-SoC plane, known at compile time (the reference's default station): the row widths
+// A and D and every shared-memory offset are then constants.
+template <typename real, int NCT, int ND, bool EXACT, bool MULTI, int L, bool FIXED>
 __global__ void __launch_bounds__(SNG_STEP_MAXT, (EXACT || NCT / L > 32) ? 2 : (NCT / L > 16 ? 4 : (L > 1 ? SNG_STEP_MINB_LANES : SNG_STEP_MINB)))   // large rows: shared memory bounds occupancy, not registers
     step_simple_kernel(const Params<real> p, const real *actions, float *obs_out, real *reward, uint8_t *done, int n_steps,
                        int mode)
@@ -201,15 +216,17 @@ __global__ void __launch_bounds__(SNG_STEP_MAXT, (EXACT || NCT / L > 32) ? 2 : (
     const int n_envs = (int)p.n_envs;                            // a handle owns < 2^31 envs (sng_create)
     const int blk = blockIdx.x * wpb + warp;                     // this warp's group of EPW envs (L = 1: a state block)
     const int e0 = blk * EPW;
-    const bool active = e0 < n_envs;                             // warp-uniform; idle warps only join the CTA barrier
+    const bool active = e0 < n_envs;                             // warp-uniform; idle warps leave at once
     const int N = NCT ? NCT : p.N;
-    const int A = p.A, D = p.D;
+    const int A = FIXED ? NCT + 1 : p.A, D = FIXED ? ND + 2 * NCT + 1 : p.D;
     const uint32_t act_bytes = (uint32_t)(EPW * A * sizeof(real)), obs_bytes = (uint32_t)(EPW * D * sizeof(float));
     const uint32_t per_warp = align128(act_bytes) + align128(obs_bytes);
-    unsigned char *wbase = smem + (size_t)warp * per_warp;
+    // [one mbarrier per warp (128-byte header) | per warp: action rows, observation rows]
+    unsigned char *wbase = smem + 128 + (size_t)warp * per_warp;
     real *act_s = reinterpret_cast<real *>(wbase);
     float *obs_s = reinterpret_cast<float *>(wbase + align128(act_bytes));
-    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + (size_t)wpb * per_warp) + warp;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem) + warp;
+    static_assert(SNG_STEP_MAXT / 32 * 8 <= 128, "the mbarrier header holds one word per warp");
     constexpr bool COOP = !EXACT && NCT > 0 && NCT <= 16 && L == 1;   // warp-cooperative admission of arriving vehicles
     // its queue reuses the action stage: every lane is done with its action row when the admission starts
     // (the warp-wide shuffles at its top are the barrier), and 32 * N * 2 B <= 32 * A * sizeof(real)
@@ -248,7 +265,7 @@ __global__ void __launch_bounds__(SNG_STEP_MAXT, (EXACT || NCT / L > 32) ? 2 : (
         // the warp holds its slot with nothing in flight
         const bool early = !MULTI && (mode & STAGE_PDL_EARLY);
         if (!MULTI && !early) { pdl_wait(); pdl_launch_dependents(); }     // ordinary launch: no-ops
-        if (valid) load_state<real, NCT / L, L>(p, e, spot, st);
+        if (valid) load_state<real, NCT / L, L, FIXED>(p, e, spot, st);
         if (early) { pdl_wait(); pdl_launch_dependents(); }                // actions (and everything written below) after the predecessor
         if (tma_load) {
             if (lane == 0) {
@@ -266,8 +283,8 @@ __global__ void __launch_bounds__(SNG_STEP_MAXT, (EXACT || NCT / L > 32) ? 2 : (
                 if (k < act_vec) areg[j] = reinterpret_cast<const float4 *>(act_g)[k];
             }
         }
-        if (s == 0) publish_dep_table(p);     // CTA barrier; also orders the mbarrier init before the other lanes' waits
         if (!active) return;
+        if (s == 0) publish_dep_table_warp(p);     // per warp, no CTA barrier; its __syncwarp also orders the mbarrier init before the other lanes' waits
         // ---- action rows into shared memory ----
         if (tma_load) {
             if (MULTI) __syncwarp();
@@ -293,9 +310,9 @@ __global__ void __launch_bounds__(SNG_STEP_MAXT, (EXACT || NCT / L > 32) ? 2 : (
         if (valid) {
             const RowIO<real, L> io = {act_s + el * A + sub, act_s + el * A, obs_s + el * D, Offsets<NCT, ND>::soc(p) + sub,
                                        Offsets<NCT, ND>::dep(p) + sub};
-            arrivals = env_step<real, NCT, ND, EXACT, true, COOP, L>(p, e, spot, st, io, reward + slab, done + slab, sub);
+            arrivals = env_step<real, NCT, ND, EXACT, true, COOP, L, FIXED>(p, e, spot, st, io, reward + slab, done + slab, sub);
         }
-        if (COOP) admit_arrivals_warp<real, NCT>(p, e0, lane, spot - lane, arrivals, queue);
+        if (COOP) admit_arrivals_warp<real, NCT, FIXED>(p, e0, lane, spot - lane, arrivals, queue);
         // ---- observation rows out of shared memory ----
         if (tma_store) {
             fence_proxy_async();
@@ -481,6 +498,7 @@ public:
         p.b_cap = (real)c.b_cap; p.b_pmax = (real)c.b_pmax; p.b_eff = (real)c.b_eff; p.b_dod = (real)c.b_dod;
         p.b_soc0 = (real)c.b_soc0; p.sell = (real)c.sell_coeff; p.cost_w = (real)c.cost_weight;
         p.batt_w = (real)c.batt_pen_w; p.margin = (real)c.margin;
+        p.dt_cap = c.b_cap > 0 ? (real)(c.dt / c.b_cap) : (real)0; p.cap_dt = (real)(c.b_cap / c.dt);
         if (c.default_cap < 1 || c.default_cap > 255) { error = "sng_create: default_cap must be in 1..255"; return SNG_ERR_ARG; }
         // shared tables: 4 x table_len reals + the departure-normalisation table
         const int n = c.table_len;
@@ -673,18 +691,18 @@ public:
     static constexpr size_t kStaticSmem = kSmemTab * sizeof(float);
 
     // L lanes per env (see step_simple_kernel); L = 2 requires q.n_envs to be a multiple of 32.
-    template <int NCT, int ND, int L = 1>
+    template <int NCT, int ND, int L = 1, bool FIXED = false>
     int launch_simple(const Params<real> &q, const real *actions, float *obs, real *reward, uint8_t *done, int n_steps,
                       int bulk, cudaStream_t st)
     {
         constexpr int EPW = kBlock / L;
-        const size_t per_warp = align128((uint32_t)(EPW * p.A * sizeof(real))) + align128((uint32_t)(EPW * p.D * sizeof(float))) + 8;
+        const size_t per_warp = align128((uint32_t)(EPW * p.A * sizeof(real))) + align128((uint32_t)(EPW * p.D * sizeof(float)));
         int wpb = warps_per_cta > 0 ? warps_per_cta : 2;
         if (wpb * 32 > SNG_STEP_MAXT) wpb = SNG_STEP_MAXT / 32;
-        while (wpb > 1 && kStaticSmem + (size_t)wpb * per_warp > smem_optin) wpb >>= 1;
-        const size_t smem = (size_t)wpb * per_warp;
+        while (wpb > 1 && kStaticSmem + 128 + (size_t)wpb * per_warp > smem_optin) wpb >>= 1;
+        const size_t smem = 128 + (size_t)wpb * per_warp;   // mbarrier header + the warps' row stages
         if (kStaticSmem + smem > smem_optin) { error = "step kernel: one warp's action/observation rows do not fit in shared memory"; return SNG_ERR_UNSUPPORTED; }
-        auto kern = n_steps > 1 ? step_simple_kernel<real, NCT, ND, EXACT, true, L> : step_simple_kernel<real, NCT, ND, EXACT, false, L>;
+        auto kern = n_steps > 1 ? step_simple_kernel<real, NCT, ND, EXACT, true, L, FIXED> : step_simple_kernel<real, NCT, ND, EXACT, false, L, FIXED>;
         int rc = ensure_smem((const void *)kern, smem);
         if (rc) return rc;
         const long long groups = (q.n_envs + EPW - 1) / EPW;       // one warp each
@@ -731,7 +749,7 @@ public:
         return SNG_OK;
     }
 
-    template <int NCT, int ND>
+    template <int NCT, int ND, bool FIXED = false>
     int launch_step_n(const Params<real> &q, const real *actions, float *obs, real *reward, uint8_t *done, int n_steps,
                       int bulk, cudaStream_t st)
     {
@@ -743,7 +761,7 @@ public:
                 const long long e0 = n_blocks * kBlock;
                 if (e0 == q.n_envs) return SNG_OK;
                 const Params<real> tail = slice_of(q, e0, q.n_envs - e0);   // ragged last block
-                return launch_simple<NCT, ND>(tail, tail.actions, tail.obs, tail.reward, tail.done, 1, 0, st);
+                return launch_simple<NCT, ND, 1, FIXED>(tail, tail.actions, tail.obs, tail.reward, tail.done, 1, 0, st);
             }
             if (rc != SNG_ERR_UNSUPPORTED) return rc;
         }
@@ -754,18 +772,18 @@ public:
                 const long long full = q.n_envs / kBlock * kBlock;
                 const bool four = lanes_per_env != 2 && NCT % 4 == 0;      // default: four lanes per env (a warp covers 8 envs)
                 if (full == q.n_envs)
-                    return four ? launch_simple<NCT, ND, 4>(q, actions, obs, reward, done, n_steps, bulk, st)
-                                : launch_simple<NCT, ND, 2>(q, actions, obs, reward, done, n_steps, bulk, st);
+                    return four ? launch_simple<NCT, ND, 4, FIXED>(q, actions, obs, reward, done, n_steps, bulk, st)
+                                : launch_simple<NCT, ND, 2, FIXED>(q, actions, obs, reward, done, n_steps, bulk, st);
                 if (n_steps == 1 && actions == q.actions && obs == q.obs && reward == q.reward && done == q.done) {
                     const Params<real> head = slice_of(q, 0, full), tail = slice_of(q, full, q.n_envs - full);
-                    const int rc = four ? launch_simple<NCT, ND, 4>(head, head.actions, head.obs, head.reward, head.done, 1, bulk, st)
-                                        : launch_simple<NCT, ND, 2>(head, head.actions, head.obs, head.reward, head.done, 1, bulk, st);
+                    const int rc = four ? launch_simple<NCT, ND, 4, FIXED>(head, head.actions, head.obs, head.reward, head.done, 1, bulk, st)
+                                        : launch_simple<NCT, ND, 2, FIXED>(head, head.actions, head.obs, head.reward, head.done, 1, bulk, st);
                     if (rc) return rc;
-                    return launch_simple<NCT, ND, 1>(tail, tail.actions, tail.obs, tail.reward, tail.done, 1, STAGE_SCALAR, st);
+                    return launch_simple<NCT, ND, 1, FIXED>(tail, tail.actions, tail.obs, tail.reward, tail.done, 1, STAGE_SCALAR, st);
                 }
             }
         }
-        return launch_simple<NCT, ND>(q, actions, obs, reward, done, n_steps, bulk, st);
+        return launch_simple<NCT, ND, 1, FIXED>(q, actions, obs, reward, done, n_steps, bulk, st);
     }
 
     // q: parameters (possibly of a slice of envs starting at a multiple of 32)
@@ -785,6 +803,17 @@ public:
             // shape (PV on, 3 steps ahead: 8 disturbance entries); everything else runs the generic kernel
             // (keyed on the flags themselves: PV off with 7 steps ahead also has 8 disturbance entries, but a
             // different layout -- eight prices)
+            if (!use_generic && q.pv && q.H == 3 && q.pv_days == 1 && q.batt && !q.has_req) {
+                // ... and the rest of the reference's default station (battery, no requested-SoC plane) at compile time too
+                switch (q.N) {
+                case 4: return launch_step_n<4, 8, true>(q, actions, obs, reward, done, n_steps, bulk, st);
+                case 8: return launch_step_n<8, 8, true>(q, actions, obs, reward, done, n_steps, bulk, st);
+                case 10: return launch_step_n<10, 8, true>(q, actions, obs, reward, done, n_steps, bulk, st);
+                case 32: return launch_step_n<32, 8, true>(q, actions, obs, reward, done, n_steps, bulk, st);
+                case 64: return launch_step_n<64, 8, true>(q, actions, obs, reward, done, n_steps, bulk, st);
+                default: break;
+                }
+            }
             if (!use_generic && q.pv && q.H == 3 && q.pv_days == 1) {
                 switch (q.N) {
                 case 4: return launch_step_n<4, 8>(q, actions, obs, reward, done, n_steps, bulk, st);

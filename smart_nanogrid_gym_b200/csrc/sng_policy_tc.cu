@@ -34,7 +34,7 @@
 namespace {
 using namespace sng;
 long long *g_trace = nullptr;      // debugging aid: sng_policy_debug_trace
-int g_policy_pdl = 0;              // sng_policy_set_launch_mode
+int g_policy_pdl = 0;              // sng_policy_set_launch_mode: bit 0 programmatic dependent launch, bit 1 the CTA takes its SM's whole shared memory
 
 constexpr int H = 64;        // hidden width of SB3's default MlpPolicy
 constexpr int KP = 32;       // observation width padded to the K of layer 0 (obs_dim <= 30; columns 30, 31 = 1.0)
@@ -370,7 +370,7 @@ __global__ void __launch_bounds__(ALL_THREADS, 1)
                      const float *__restrict__ low, const float *__restrict__ high, float *raw_actions, float *actions,
                      float *values, float *log_probs, long long n_envs, int D, int A, int aligned, long long *trace,
                      const unsigned long long *rng_step, unsigned long long rng_offset, unsigned long long rng_seed,
-                     unsigned long long rng_gid0, float *noise_out)
+                     unsigned long long rng_gid0, float *noise_out, int early)
 {
     int tr = 0;
 #define TRACE() do { if (trace && blockIdx.x == 0 && threadIdx.x == 0 && tr < 64) trace[tr++] = clock64(); } while (0)
@@ -424,6 +424,14 @@ __global__ void __launch_bounds__(ALL_THREADS, 1)
         for (int i = 0; i < N_BARS; ++i)
             mbar_init(bars + i, (i == 7 || i == 8) ? IO_THREADS / 32 : ((i == 9 || i == 10) ? THREADS / 32 : 1));
         fence_mbar_init();
+        // `early` (programmatic dependent launch): the weight image was complete before the predecessor started, so the
+        // whole of it is requested while the predecessor is still running
+        if (early) {
+            fetch_weights(0);
+            if (!value_only) fetch_weights(1);
+            fetch_weights(2);
+            if (!value_only) fetch_weights(3);
+        }
     }
     if (warp == 1) tmem_alloc(tmem_slot, 512);
     // programmatic dependent launch: everything above ran while the predecessor (the step kernel that writes `obs`) was
@@ -435,15 +443,17 @@ __global__ void __launch_bounds__(ALL_THREADS, 1)
         // image is requested after the CTA barrier by a thread that would otherwise wait: issuing a bulk copy costs the
         // issuing thread ~100 cycles, and everybody waits for this thread at the barrier)
         if (tile_full(first_tile)) fetch_obs(first_tile, 0);
-        fetch_weights(0);
+        if (!early) fetch_weights(0);
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     if (threadIdx.x == 0) {                     // compute warp 0, about to wait for the first layer anyway
-        if (!value_only) fetch_weights(1);
-        fetch_weights(2);
-        if (!value_only) fetch_weights(3);
+        if (!early) {
+            if (!value_only) fetch_weights(1);
+            fetch_weights(2);
+            if (!value_only) fetch_weights(3);
+        }
         if (tile_full(first_tile + stride)) fetch_obs(first_tile + stride, 1);
     }
     const uint32_t tmem = *tmem_slot;
@@ -714,7 +724,7 @@ extern "C" void sng_policy_debug_trace(long long *device_buf) { g_trace = device
 
 extern "C" int sng_policy_set_launch_mode(int mode)
 {
-    if (mode < 0 || mode > 1) return SNG_ERR_ARG;
+    if (mode < 0 || mode > 3) return SNG_ERR_ARG;
     g_policy_pdl = mode;
     return SNG_OK;
 }
@@ -744,7 +754,14 @@ int launch_policy_tc(const void *packed, int obs_dim, int act_dim, const float *
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     const Smem sp = smem_plan(obs_dim, act_dim);
-    const size_t smem = sp.bars + 160;   // 19 mbarriers + the TMEM address slot
+    size_t smem = sp.bars + 160;   // 19 mbarriers + the TMEM address slot
+    if (g_policy_pdl & 2) {
+        // the CTA claims its SM's whole shared memory: no CTA of a kernel launched early behind this one (programmatic
+        // dependent launch) can become resident next to it and take issue slots from the compute warps
+        int optin = 0;
+        cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        if ((size_t)optin > smem) smem = (size_t)optin;
+    }
     if (ensure_smem(dev, (const void *)policy_tc_kernel, smem) != SNG_OK) return SNG_ERR_CUDA;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const long long n_tiles = (n_envs + TILE - 1) / TILE;
@@ -752,7 +769,7 @@ int launch_policy_tc(const void *packed, int obs_dim, int act_dim, const float *
     if (grid > sms) grid = sms;
     const int aligned = aligned16(obs) && aligned16(noise) && aligned16(raw_actions) && aligned16(actions) && aligned16(packed);
     if (!aligned16(packed)) return SNG_ERR_ARG;
-    if (g_policy_pdl) {
+    if (g_policy_pdl & 1) {
         cudaLaunchConfig_t lc = {};
         lc.gridDim = dim3((unsigned)grid); lc.blockDim = dim3(ALL_THREADS); lc.dynamicSmemBytes = smem; lc.stream = (cudaStream_t)stream;
         cudaLaunchAttribute at[1];
@@ -762,13 +779,13 @@ int launch_policy_tc(const void *packed, int obs_dim, int act_dim, const float *
         const cudaError_t e = cudaLaunchKernelEx(&lc, policy_tc_kernel, reinterpret_cast<const float *>(packed), obs, noise, low, high, raw_actions,
                                                  actions, values, log_probs, (long long)n_envs, obs_dim, act_dim, aligned, g_trace,
                                                  rng_step, (unsigned long long)rng_offset, (unsigned long long)rng_seed,
-                                                 (unsigned long long)rng_gid0, noise_out);
+                                                 (unsigned long long)rng_gid0, noise_out, 1);
         return e == cudaSuccess ? SNG_OK : SNG_ERR_CUDA;
     }
     policy_tc_kernel<<<(unsigned)grid, ALL_THREADS, smem, (cudaStream_t)stream>>>(reinterpret_cast<const float *>(packed), obs, noise, low, high,
                                                                              raw_actions, actions, values, log_probs,
                                                                              (long long)n_envs, obs_dim, act_dim, aligned, g_trace,
-                                                                             rng_step, rng_offset, rng_seed, rng_gid0, noise_out);
+                                                                             rng_step, rng_offset, rng_seed, rng_gid0, noise_out, 0);
     return cudaGetLastError() == cudaSuccess ? SNG_OK : SNG_ERR_CUDA;
 }
 }  // namespace

@@ -203,11 +203,12 @@ def collect_rollout(env, policy: MlpPolicy, buf: RolloutBuffer, obs: torch.Tenso
     the policy kernel (Philox keyed by rng_seed and the policy's step counter: no noise tensor, no RNG launch).
     pack=False / advance_counter=False: the caller packs the weights / advances the step counter itself (several
     shards collected side by side share both, see ShardedGraphedRollout).
-    pdl=True (fused kernel only): policy and step kernels are launched with programmatic dependent launch -- each starts
-    while the other is draining (block scheduling, barrier / TMEM set-up, and the step's state loads, which the policy
-    kernel does not touch) and waits for it before reading what it wrote.  Measured on a B200 at 65,536 envs: SLOWER
-    (33.6 vs 30.4 us per rollout step: early step CTAs spin next to the policy CTAs that are still running), so it is
-    off by default; for step-after-step launches of small batches it gains 4-6 % (bench.py --pdl)."""
+    pdl (fused kernel only): programmatic dependent launch inside the loop -- a kernel starts while its predecessor is
+    draining (block scheduling, barrier / TMEM set-up, the policy's weight image, the step's state loads, none of which
+    the predecessor writes) and waits for it before reading what it wrote.  "policy": only the policy kernel is
+    launched that way (behind the step kernel); "step": only the step kernel; True / "both": both; a trailing "+x"
+    ("policy+x", ...) makes the policy CTAs claim their SM's whole shared memory, so that early step CTAs cannot become
+    resident next to a running policy CTA.  DESIGN.md section 6 has the measurements."""
     low, high = env.action_low.float(), env.action_high.float()
     buf.observations[0].copy_(obs)
     buf.episode_starts[0].copy_(episode_starts.to(torch.uint8))    # episode_starts[s + 1] aliases dones[s]
@@ -217,30 +218,40 @@ def collect_rollout(env, policy: MlpPolicy, buf: RolloutBuffer, obs: torch.Tenso
         policy.pack_weights()          # once per rollout: the weights do not change while it is collected
     if in_kernel_noise and (getattr(policy, "rng_counter", None) is None or policy.rng_counter.device != obs.device):
         policy.rng_counter = torch.zeros(1, dtype=torch.int64, device=obs.device)   # rollout steps drawn so far
-    pdl = pdl and fused
-    if pdl:
+    pdl = pdl if fused else False
+    mode = "both" if pdl is True else (pdl or "")
+    exclusive = mode.endswith("+x")
+    mode = mode[:-2] if exclusive else mode
+    if mode not in ("", "both", "policy", "step"):
+        raise ValueError("pdl must be False, True, 'both', 'policy' or 'step' (optionally + '+x')")
+    if mode in ("both", "step"):
         env.set_launch_mode(2)         # the step's predecessor is the policy kernel: state loads ahead of the wait
-        nat.check(nat.lib().sng_policy_set_launch_mode(1))
+    policy_mode = (1 if mode in ("both", "policy") else 0) | (2 if exclusive else 0)
+    if policy_mode:
+        nat.check(nat.lib().sng_policy_set_launch_mode(policy_mode & 2))   # the first call follows the weight packing: ordinary launch
     try:
-        _rollout_steps(env, policy, buf, low, high, fused, in_kernel_noise, rng_seed, deterministic, generator)
+        _rollout_steps(env, policy, buf, low, high, fused, in_kernel_noise, rng_seed, deterministic, generator, policy_mode)
+        last_obs = buf.observations[buf.n_steps]
+        if fused:
+            policy.fused_forward(last_obs, None, None, None, None, None, buf.last_values, None, repack=False)
+        else:
+            buf.last_values.copy_(policy.predict_values(last_obs))
     finally:
-        if pdl:
+        if mode in ("both", "step"):
             env.set_launch_mode(0)
+        if policy_mode:
             nat.check(nat.lib().sng_policy_set_launch_mode(0))
     if in_kernel_noise and advance_counter:
         policy.rng_counter += buf.n_steps
-    last_obs = buf.observations[buf.n_steps]
-    if fused:
-        policy.fused_forward(last_obs, None, None, None, None, None, buf.last_values, None, repack=False)
-    else:
-        buf.last_values.copy_(policy.predict_values(last_obs))
     buf.compute_returns_and_advantage(buf.last_values, buf.dones[buf.n_steps - 1])
     return last_obs, buf.dones[buf.n_steps - 1]
 
 
-def _rollout_steps(env, policy, buf, low, high, fused, in_kernel_noise, rng_seed, deterministic, generator):
+def _rollout_steps(env, policy, buf, low, high, fused, in_kernel_noise, rng_seed, deterministic, generator, policy_mode=0):
     for s in range(buf.n_steps):
         o = buf.observations[s]
+        if s == 1 and policy_mode & 1:     # from the second call on the policy kernel follows a step kernel
+            nat.check(nat.lib().sng_policy_set_launch_mode(policy_mode))
         if in_kernel_noise:
             policy.fused_forward(o, None, low, high, buf.raw_actions[s], buf.actions[s], buf.values[s], buf.log_probs[s],
                                  repack=False, rng=(rng_seed, policy.rng_counter, s, env.env_gid0))
