@@ -611,7 +611,8 @@ def rollout_leg(ctx, wl_key, E, n_steps, shipped=False):
     buf = RolloutBuffer(n_steps, env.num_envs, env.cfg.obs_dim, env.cfg.act_dim, ctx.dev)
     obs = env.reset()
     starts = torch.ones(env.num_envs, dtype=torch.uint8, device=ctx.dev)
-    rpdl = ROLLOUT_PDL[0] if policy.fused_supported() else None
+    rpdl = (ROLLOUT_PDL[0] or "policy") if policy.fused_supported() else None   # measured: policy 29.5, off 30.5, both 31.6 us per step
+    rpdl = None if rpdl == "off" else rpdl
     collect = GraphedRollout(env, policy, buf, pdl=rpdl or False)
     state = [obs, starts]
 
@@ -783,12 +784,12 @@ def main():
                     "(1 for small batches, where kernel-to-kernel latency is a visible share of a step)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs")
     ap.add_argument("--rollout-pdl", default="", help="programmatic dependent launch inside the rollout loop of the c3 legs: "
-                    "policy, step, both (optionally +x: policy CTAs claim their SM's whole shared memory); default off")
+                    "off, policy (default), step, both (optionally +x: policy CTAs claim their SM's whole shared memory)")
     ap.add_argument("--legs", default="all", help="'all', 'none' or a comma list of c4_strong,c5,c3,c3_sharded,c3_sb3,c2,rollout_kernel,generic")
     ap.add_argument("--rollout", type=int, default=0, help="legacy: same as --legs c3 with this many steps per rollout")
     args = ap.parse_args()
     PDL_ARG[0] = args.pdl
-    ROLLOUT_PDL[0] = None if args.rollout_pdl in ("", "none", "off") else args.rollout_pdl
+    ROLLOUT_PDL[0] = args.rollout_pdl or None
     args.warmup = max(args.warmup, 3)
 
     if args.impl == "reference":

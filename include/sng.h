@@ -263,7 +263,11 @@ int sng_set_tuning(sng_env *env, int warps_per_cta, int use_generic_kernel, int 
  * 2: the same, and the per-env state is loaded BEFORE the wait: only valid when the predecessor in the stream does not
  * write this handle's state (e.g. the policy kernel of a rollout loop; NOT another sng_step of the same handle). */
 int sng_set_launch_mode(sng_env *env, int mode);
-/* The same switch for sng_policy_forward_packed / _sampled (process-wide): 1 = programmatic dependent launch. */
+/* The same switch for sng_policy_forward_packed / _sampled (process-wide), a bit mask.  Bit 0: programmatic dependent
+ * launch -- CTA set-up and the fetch of the packed weight image run while the predecessor in the stream (the step kernel
+ * that writes the observations) is draining; only valid when the predecessor does not write the weight image (i.e. not
+ * directly behind sng_policy_pack).  Bit 1: every CTA claims its SM's whole shared memory, so that no CTA of a kernel
+ * launched early behind this one can become resident beside it. */
 int sng_policy_set_launch_mode(int mode);
 
 /* Tuning knob: which step kernel runs: 0 (default) one 32-env block per warp, with four lanes per env for

@@ -220,17 +220,19 @@ __global__ void __launch_bounds__(SNG_STEP_MAXT, (EXACT || NCT / L > 32) ? 2 : (
     const int N = NCT ? NCT : p.N;
     const int A = FIXED ? NCT + 1 : p.A, D = FIXED ? ND + 2 * NCT + 1 : p.D;
     const uint32_t act_bytes = (uint32_t)(EPW * A * sizeof(real)), obs_bytes = (uint32_t)(EPW * D * sizeof(float));
-    const uint32_t per_warp = align128(act_bytes) + align128(obs_bytes);
-    // [one mbarrier per warp (128-byte header) | per warp: action rows, observation rows]
+    // the rollout keeps TWO action stages: the copy engine fetches the next step's rows while this step is computed
+    constexpr uint32_t NSTAGE = MULTI ? 2u : 1u;
+    const uint32_t act_stage = align128(act_bytes);
+    const uint32_t per_warp = NSTAGE * act_stage + align128(obs_bytes);
+    // [one mbarrier per warp (128-byte header) | per warp: action rows (x NSTAGE), observation rows]
     unsigned char *wbase = smem + 128 + (size_t)warp * per_warp;
-    real *act_s = reinterpret_cast<real *>(wbase);
-    float *obs_s = reinterpret_cast<float *>(wbase + align128(act_bytes));
+    real *act_s0 = reinterpret_cast<real *>(wbase);
+    float *obs_s = reinterpret_cast<float *>(wbase + NSTAGE * act_stage);
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem) + warp;
     static_assert(SNG_STEP_MAXT / 32 * 8 <= 128, "the mbarrier header holds one word per warp");
     constexpr bool COOP = !EXACT && NCT > 0 && NCT <= 16 && L == 1;   // warp-cooperative admission of arriving vehicles
-    // its queue reuses the action stage: every lane is done with its action row when the admission starts
-    // (the warp-wide shuffles at its top are the barrier), and 32 * N * 2 B <= 32 * A * sizeof(real)
-    uint16_t *queue = reinterpret_cast<uint16_t *>(act_s);
+    // (its queue reuses the step's action stage: every lane is done with its action row when the admission starts --
+    //  the warp-wide shuffles at its top are the barrier -- and 32 * N * 2 B <= 32 * A * sizeof(real))
 
     const int n_valid = active ? min(EPW, n_envs - e0) : 0;   // envs of this warp (L = 2: always EPW, see above)
     const bool full = n_valid == EPW;
@@ -252,11 +254,14 @@ __global__ void __launch_bounds__(SNG_STEP_MAXT, (EXACT || NCT / L > 32) ? 2 : (
         float *obs_g = obs_out + (slab + (size_t)e0) * D;
         StateRegs<real, NCT / L> st;
         float4 areg[AV];
+        // this step's action rows: with the copy engine the rollout alternates between the two stages
+        real *act_s = (MULTI && tma_load && (s & 1)) ? reinterpret_cast<real *>(wbase + act_stage) : act_s0;
+        uint16_t *queue = reinterpret_cast<uint16_t *>(act_s);
         // ---- put everything this block needs in flight first ----
         if (MULTI && s > 0) {
-            // the stages are reused: the previous step's bulk store must have read obs_s before any lane writes
-            // it again, and the admission queue's generic-proxy writes to act_s must be ordered before the copy
-            // engine overwrites it
+            // the stages are reused: the previous step's bulk store must have read obs_s before any lane writes it
+            // again, and every lane's generic-proxy writes to its action stage (the admission queue) are ordered
+            // before the copy engine refills that stage (requested below, behind a __syncwarp)
             if (tma_load) fence_proxy_async();
             if (tma_store && lane == 0) bulk_wait_read<0>();
             __syncwarp();
@@ -268,11 +273,9 @@ __global__ void __launch_bounds__(SNG_STEP_MAXT, (EXACT || NCT / L > 32) ? 2 : (
         if (valid) load_state<real, NCT / L, L, FIXED>(p, e, spot, st);
         if (early) { pdl_wait(); pdl_launch_dependents(); }                // actions (and everything written below) after the predecessor
         if (tma_load) {
-            if (lane == 0) {
-                if (s == 0) {
-                    mbar_init(bar, 1);
-                    fence_mbar_init();
-                }
+            if (lane == 0 && s == 0) {         // (the rows of the later steps of a rollout were requested one step ahead, below)
+                mbar_init(bar, 1);
+                fence_mbar_init();
                 mbar_expect_tx(bar, act_bytes);
                 bulk_g2s(act_s, act_g, act_bytes, bar);
             }
@@ -289,6 +292,13 @@ __global__ void __launch_bounds__(SNG_STEP_MAXT, (EXACT || NCT / L > 32) ? 2 : (
         if (tma_load) {
             if (MULTI) __syncwarp();
             mbar_wait(bar, (uint32_t)(s & 1));
+            if (MULTI && s + 1 < n_steps && lane == 0) {
+                // the next step's rows, into the other stage: its last users (the action reads and the admission queue
+                // of step s - 1) are complete and fenced (top of this iteration)
+                mbar_expect_tx(bar, act_bytes);
+                bulk_g2s(reinterpret_cast<unsigned char *>(act_s0) + ((s + 1) & 1) * act_stage,
+                         actions + ((size_t)(s + 1) * (size_t)n_envs + (size_t)e0) * A, act_bytes, bar);
+            }
         } else if (vec) {
             if (NCT && sizeof(real) == 4) {
 #pragma unroll
@@ -696,7 +706,7 @@ public:
                       int bulk, cudaStream_t st)
     {
         constexpr int EPW = kBlock / L;
-        const size_t per_warp = align128((uint32_t)(EPW * p.A * sizeof(real))) + align128((uint32_t)(EPW * p.D * sizeof(float)));
+        const size_t per_warp = (n_steps > 1 ? 2 : 1) * align128((uint32_t)(EPW * p.A * sizeof(real))) + align128((uint32_t)(EPW * p.D * sizeof(float)));
         int wpb = warps_per_cta > 0 ? warps_per_cta : 2;
         if (wpb * 32 > SNG_STEP_MAXT) wpb = SNG_STEP_MAXT / 32;
         while (wpb > 1 && kStaticSmem + 128 + (size_t)wpb * per_warp > smem_optin) wpb >>= 1;

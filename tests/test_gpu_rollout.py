@@ -245,7 +245,8 @@ def test_graphed_rollout_with_in_kernel_noise_advances_between_replays():
 
 def test_programmatic_dependent_launch_changes_nothing_but_timing():
     """sng_set_launch_mode / sng_policy_set_launch_mode: the same rollout with and without programmatic dependent launch
-    (step kernel in mode 2: state loads ahead of the wait; policy kernel in mode 1) is bit-identical, eager and graphed;
+    (step kernel in mode 2: state loads ahead of the wait; policy kernel in mode 1: weight image ahead of the wait; either
+    one alone; policy CTAs claiming the whole shared memory) is bit-identical, eager and graphed;
     step-after-step launches in mode 1 equal ordinary launches."""
     from smart_nanogrid_gym_b200 import BatchedSmartNanogridEnv
     from smart_nanogrid_gym_b200.rollout import GraphedRollout, MlpPolicy, RolloutBuffer
@@ -253,7 +254,7 @@ def test_programmatic_dependent_launch_changes_nothing_but_timing():
     torch.manual_seed(2)
     policy = MlpPolicy(29, 11).to("cuda:0")
     res = []
-    for pdl in (False, True):
+    for pdl in (False, True, "policy", "step+x"):
         env = BatchedSmartNanogridEnv(E, device="cuda:0", seed=3, **KW)
         buf = RolloutBuffer(n, E, 29, 11, "cuda:0")
         env.reset()
@@ -266,8 +267,9 @@ def test_programmatic_dependent_launch_changes_nothing_but_timing():
         res.append((buf.raw_actions.clone(), buf.rewards.clone(), buf.observations.clone(), buf.advantages.clone(), env._spot.clone()))
         assert env.error_flags() == 0
         env.close()
-    for a, b in zip(res[0], res[1]):
-        assert torch.equal(a, b)
+    for other in res[1:]:
+        for a, b in zip(res[0], other):
+            assert torch.equal(a, b)
     envs = [BatchedSmartNanogridEnv(E, device="cuda:0", seed=5, **KW) for _ in range(2)]
     envs[1].set_launch_mode(1)
     for e in envs:
