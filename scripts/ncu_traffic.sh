@@ -15,6 +15,6 @@ for spec in "c4 1048576" "c4 524288" "c4 262144" "c4 131072" "c4 65536" "c4 4096
   echo "$1 $2 rc=$?"
 done
 # launch list of the default bench command (per-launch times are cold-cache and serialised: shares, not absolutes)
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $out/r2_launches.csv \
-    python bench.py --steps 48 --warmup 24 --no-cpu --e2e-steps 2 --graph-steps 0 --legs c5,c3 > $out/r2_ncu_launches.log 2>&1
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $out/r3_launches.csv \
+    python bench.py --steps 48 --warmup 24 --no-cpu --e2e-steps 2 --graph-steps 0 --legs c5,c3 > $out/r3_ncu_launches.log 2>&1
 echo "launch list rc=$?"
