@@ -596,7 +596,7 @@ def load_shipped_policy(ctx, obs_dim, act_dim):
     return pol.to(ctx.dev)
 
 
-def rollout_leg(ctx, wl_key, E, n_steps, shipped=False):
+def rollout_leg(ctx, wl_key, E, n_steps, shipped=False, fuse_step=False):
     """BASELINE config 3: PPO rollout collection, policy in the loop.  Reported beside the headline, not as it."""
     torch = ctx.torch
     from smart_nanogrid_gym_b200.rollout import GraphedRollout, MlpPolicy, RolloutBuffer
@@ -613,7 +613,8 @@ def rollout_leg(ctx, wl_key, E, n_steps, shipped=False):
     starts = torch.ones(env.num_envs, dtype=torch.uint8, device=ctx.dev)
     rpdl = (ROLLOUT_PDL[0] or "policy") if policy.fused_supported() else None   # measured: policy 29.5, off 30.5, both 31.6 us per step
     rpdl = None if rpdl == "off" else rpdl
-    collect = GraphedRollout(env, policy, buf, pdl=rpdl or False)
+    fuse_step = bool(fuse_step and policy.fused_supported() and env.supports_policy_step())
+    collect = GraphedRollout(env, policy, buf, pdl=rpdl or False, fuse_step=fuse_step)
     state = [obs, starts]
 
     def run(reps):
@@ -646,7 +647,8 @@ def rollout_leg(ctx, wl_key, E, n_steps, shipped=False):
     flops = 2.0 * 2 * (env.cfg.obs_dim * 64 + 64 * 64) + 2.0 * 64 * (env.cfg.act_dim + 1)    # per env: actor + critic + heads
     out = {"value": E * ctx.n_gpus * steps / (ms_max * 1e-3), "unit": UNIT, "ms_per_step": ms_max / steps, "steps": steps,
            "n_steps_per_rollout": n_steps, "envs_per_gpu": E, "total_envs": E * ctx.n_gpus,
-           "launch": "one CUDA graph per rollout (n_steps x [policy kernel, step kernel] + bootstrap value + GAE)%s" % (
+           "launch": "one CUDA graph per rollout (n_steps x %s + bootstrap value + GAE)%s" % (
+               "[ONE kernel: policy forward + env step, sng_policy_step]" if fuse_step else "[policy kernel, step kernel]",
                ", programmatic dependent launch: %s" % rpdl if rpdl else ""),
            "policy": "%s tanh MLP %d-64-64-%d actor + critic%s, actions sampled and clipped to the Box, GAE by sng_gae" % (
                "the reference's shipped SB3 PPO checkpoint:" if shipped else "fresh-init (torch seed 0)",
@@ -785,7 +787,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs")
     ap.add_argument("--rollout-pdl", default="", help="programmatic dependent launch inside the rollout loop of the c3 legs: "
                     "off, policy (default), step, both (optionally +x: policy CTAs claim their SM's whole shared memory)")
-    ap.add_argument("--legs", default="all", help="'all', 'none' or a comma list of c4_strong,c5,c3,c3_sharded,c3_sb3,c2,rollout_kernel,generic")
+    ap.add_argument("--legs", default="all", help="'all', 'none' or a comma list of c4_strong,c5,c3,c3_fused,c3_sharded,c3_sb3,c2,rollout_kernel,generic")
     ap.add_argument("--rollout", type=int, default=0, help="legacy: same as --legs c3 with this many steps per rollout")
     args = ap.parse_args()
     PDL_ARG[0] = args.pdl
@@ -877,6 +879,9 @@ def main():
                 elif name == "c3":
                     legs[name] = rollout_leg(ctx, "c4", 65536, args.rollout or 24)
                     legs[name]["what"] = "BASELINE config 3: PPO rollout collection over 65,536 envs per GPU, N=10 station"
+                elif name == "c3_fused":
+                    legs[name] = rollout_leg(ctx, "c4", 65536, args.rollout or 24, fuse_step=True)
+                    legs[name]["what"] = "BASELINE config 3 with ONE launch per rollout step (policy forward + env step fused, sng_policy_step)"
                 elif name == "c3_sharded":
                     legs[name] = rollout_sharded_leg(ctx, "c4", 65536, args.rollout or 24, shards=2)
                     legs[name]["what"] = "BASELINE config 3, 65,536 envs per GPU as two 32,768-env shards collected side by side"

@@ -239,6 +239,22 @@ int sng_policy_forward_sampled(const void *packed, int obs_dim, int act_dim, con
                                const float *high, float *raw_actions, float *actions, float *values, float *log_probs,
                                float *noise_out, int64_t n_envs, void *stream);
 
+/* ONE launch for a whole rollout step: the forward pass of sng_policy_forward_packed / _sampled over `env`'s batch FUSED
+ * with sng_step.  The io warps of the tensor-core kernel (thread = row = env, one warp = one 32-env state block: the step
+ * kernel's own mapping) run the env step of their tile as soon as its clipped actions are in shared memory, so the
+ * actions never travel through HBM to a second kernel and one kernel boundary per rollout step disappears.  Same
+ * env-step body as sng_step: observations, rewards, done flags and the handle's state are bit-identical to the two
+ * separate launches.  obs [E][obs_dim] is what the policy sees (the current observation), obs_next / reward / done
+ * receive the step's results (SB3: collect_rollouts' policy(obs) -> clip -> env.step, solvers/RL/ppo_train.py:89-102).
+ * noise = NULL draws the exploration noise in the kernel (seed, step_counter, step_offset as for
+ * sng_policy_forward_sampled; the handle's env_gid0 keys it).  Available for the reference's default station (PV with
+ * 3 steps ahead, battery, no requested-SoC plane) at 4 and 10 spots, float32, batches that are a multiple of 128 envs
+ * and 16-byte aligned buffers; otherwise SNG_ERR_UNSUPPORTED (launch the two kernels separately). */
+int sng_policy_step(sng_env *env, const void *packed, const float *obs, const float *noise, uint64_t seed,
+                    const uint64_t *step_counter, uint64_t step_offset, const float *low, const float *high,
+                    float *raw_actions, float *actions, float *values, float *log_probs, float *noise_out,
+                    float *obs_next, void *reward, uint8_t *done, void *stream);
+
 /* Launches an EMPTY kernel on `stream`: lets a caller measure the device's kernel-to-kernel launch latency (the
  * floor under one sng_step per step for batches that live in L2; bench.py reports it beside those numbers). */
 int sng_null_launch(void *stream);

@@ -215,6 +215,36 @@ class BatchedSmartNanogridEnv:
         nat.check(self._lib.sng_step(self._h, self._stream()))
         return o[0], o[1], o[2], self.truncated, {}
 
+    def supports_policy_step(self) -> bool:
+        """sng_policy_step (policy forward + env step in one launch) exists for the reference's default station -- PV with
+        three steps ahead, battery, every vehicle requesting SoC 1.0 -- at 4 and 10 spots, float32, sampled schedules,
+        batches that are a multiple of 128 envs."""
+        c = self.cfg
+        return (self.precision == nat.SNG_F32 and c.pv and c.batt and c.hours_ahead == 3 and c.n_spots in (4, 10) and
+                not c.enable_requested_state_of_charge and int(self._c.pv_days) <= 1 and self._plan is None and
+                self.num_envs % 128 == 0)
+
+    def policy_step(self, packed, obs, low, high, raw_actions, actions, values, log_probs, out, noise=None, rng=None,
+                    noise_out=None):
+        """ONE launch for a rollout step: the tensor-core policy forward on `obs` (weight image `packed` from
+        MlpPolicy.pack_weights) fused with this env's step on the clipped actions it samples (include/sng.h
+        sng_policy_step).  `out=(obs_next, reward, done)` receive the step's results; raw_actions / actions / values /
+        log_probs what SB3's rollout buffer stores.  noise [E, A] standard normals, or rng=(seed, step_counter, step_offset)
+        to draw them in the kernel.  Bit-identical to MlpPolicy.fused_forward followed by step()."""
+        p = lambda t: None if t is None else C.c_void_p(t.data_ptr())  # noqa: E731
+        o = tuple(out)
+        self._check_tensor(obs, (self.num_envs, self.cfg.obs_dim), torch.float32, "obs")
+        self._check_tensor(o[0], (self.num_envs, self.cfg.obs_dim), torch.float32, "out[0] (obs)")
+        self._check_tensor(o[1], (self.num_envs,), self.real, "out[1] (reward)")
+        self._check_tensor(o[2], (self.num_envs,), torch.uint8, "out[2] (done)")
+        self._check_tensor(actions, (self.num_envs, self.cfg.act_dim), torch.float32, "actions")
+        self._check_tensor(raw_actions, (self.num_envs, self.cfg.act_dim), torch.float32, "raw_actions")
+        seed, counter, offset = (0, None, 0) if rng is None else rng
+        nat.check(self._lib.sng_policy_step(self._h, p(packed), p(obs), p(noise), int(seed) & (2 ** 64 - 1), p(counter), int(offset),
+                                            p(low), p(high), p(raw_actions), p(actions), p(values), p(log_probs), p(noise_out),
+                                            p(o[0]), p(o[1]), p(o[2]), self._stream()))
+        return o[0], o[1], o[2], self.truncated, {}
+
     # SB3 VecEnv-style aliases
     def step_async(self, actions):
         self._pending = actions

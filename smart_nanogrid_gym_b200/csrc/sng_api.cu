@@ -214,6 +214,19 @@ int sng_gae(const float *rewards, const float *values, const uint8_t *episode_st
     return SNG_OK;
 }
 
+int sng_policy_step(sng_env *env, const void *packed, const float *obs, const float *noise, uint64_t seed,
+                    const uint64_t *step_counter, uint64_t step_offset, const float *low, const float *high,
+                    float *raw_actions, float *actions, float *values, float *log_probs, float *noise_out,
+                    float *obs_next, void *reward, uint8_t *done_flags, void *stream)
+{
+    SNG_ENV_CHECK(env);
+    sng::PolicyStepArgs a;
+    a.packed = packed; a.obs = obs; a.noise = noise; a.step_counter = step_counter; a.step_offset = step_offset; a.seed = seed;
+    a.low = low; a.high = high; a.raw_actions = raw_actions; a.actions = actions; a.values = values; a.log_probs = log_probs;
+    a.noise_out = noise_out; a.obs_next = obs_next; a.reward = (float *)reward; a.done = done_flags;
+    return done(env, env->eng->policy_step(a, (cudaStream_t)stream));
+}
+
 int sng_set_launch_mode(sng_env *env, int mode)
 {
     SNG_ENV_CHECK(env);

@@ -18,8 +18,23 @@
 
 namespace sng {
 
+// sng_policy_step: the actor-critic forward pass of one rollout step fused with the env step (sng_policy_tc.cu)
+struct PolicyStepArgs {
+    const void *packed;                 // sng_policy_pack image
+    const float *obs;                   // [E][D] what the policy sees (rollout slab s)
+    const float *noise;                 // [E][A] standard normals, or null: drawn in the kernel (seed, step_counter, step_offset)
+    const uint64_t *step_counter;
+    uint64_t step_offset, seed;
+    const float *low, *high;            // [A]
+    float *raw_actions, *actions, *values, *log_probs, *noise_out;
+    float *obs_next, *reward;           // [E][D] (rollout slab s + 1), [E]
+    uint8_t *done;                      // [E]
+};
+int launch_policy_step(const Params<float> &p, const PolicyStepArgs &a, cudaStream_t st);
+
 struct EngineBase {
     virtual ~EngineBase() {}
+    virtual int policy_step(const PolicyStepArgs &a, cudaStream_t st) = 0;
     virtual int bind(const sng_buffers *b) = 0;
     virtual int reset(uint64_t seed, const uint8_t *mask, int reset_battery, cudaStream_t st) = 0;
     virtual int load_schedule(const sng_schedule_view *v, cudaStream_t st) = 0;
@@ -1005,6 +1020,29 @@ public:
         SNG_CUDA(cudaMemcpyAsync(out, d_flag, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         SNG_CUDA(cudaStreamSynchronize(st));
         return SNG_OK;
+    }
+
+    // The fused kernel exists for the reference's default station at 4 and 10 spots (what the policy of BASELINE config 3
+    // drives); everything else answers SNG_ERR_UNSUPPORTED and the caller launches policy and step separately.
+    int policy_step(const PolicyStepArgs &a, cudaStream_t st) override
+    {
+        int rc = check_ready(true);
+        if (rc) return rc;
+        if constexpr (!EXACT && std::is_same<real, float>::value) {
+            const bool fixed = p.pv && p.H == 3 && p.pv_days == 1 && p.batt && !p.has_req && (p.N == 4 || p.N == 10);
+            if (!fixed || use_generic || p.n_envs % 128 != 0) { error = "sng_policy_step: unsupported station shape or batch size"; return SNG_ERR_UNSUPPORTED; }
+            if (!a.packed || !a.obs || !a.low || !a.high || !a.raw_actions || !a.actions || !a.values || !a.log_probs || !a.obs_next ||
+                !a.reward || !a.done || (!a.noise && !a.step_counter)) { error = "sng_policy_step: null argument"; return SNG_ERR_ARG; }
+            DeviceGuard guard(device);
+            rc = launch_policy_step(p, a, st);
+            if (rc == SNG_ERR_UNSUPPORTED) error = "sng_policy_step: buffers must be 16-byte aligned";
+            else if (rc) error = std::string("sng_policy_step: ") + cudaGetErrorString(cudaGetLastError());
+            else ++launches;
+            return rc;
+        } else {
+            error = "sng_policy_step: float32 build only";
+            return SNG_ERR_UNSUPPORTED;
+        }
     }
 
     int set_tuning(int w, int g, int b, int hc) override

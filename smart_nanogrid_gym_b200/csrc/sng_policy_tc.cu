@@ -22,6 +22,7 @@
 // The weights are split and laid out in the canonical no-swizzle K-major core-matrix order once per weight update by
 // sng_policy_pack (a [K/4][N][4] float image: core matrix = 8 rows x 16 bytes, SBO = 128 B, LBO = N * 16 B).
 #include <cstdint>
+#include <cstring>
 #include <map>
 #include <mutex>
 #include <utility>
@@ -29,6 +30,7 @@
 #include <cuda_runtime.h>
 
 #include "../../include/sng.h"
+#include "sng_engine.cuh"
 #include "sng_tma.cuh"
 
 namespace {
@@ -260,19 +262,6 @@ __device__ __forceinline__ void tanh2_split(uint32_t &a, uint32_t &b, uint32_t &
 
 // ---- in-kernel exploration noise: Philox4x32-10 (Salmon et al., SC'11) keyed by (seed, step), counter = (global env, column
 //      block); one block yields the four standard normals of a thread's four action columns (Box-Muller) ----
-__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t (&out)[4])
-{
-#pragma unroll
-    for (int r = 0; r < 10; ++r) {
-        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
-        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
-        const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
-        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
-        k0 += 0x9E3779B9u;
-        k1 += 0xBB67AE85u;
-    }
-    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
-}
 // u in (0, 1): 24 random bits, centred; z0 = sqrt(-2 ln u1) cos(2 pi u2), z1 = ... sin(2 pi u2)
 __device__ __forceinline__ void box_muller(uint32_t x1, uint32_t x2, float &z0, float &z1)
 {
@@ -303,15 +292,19 @@ __device__ __forceinline__ void tanh_epilogue(uint32_t src, uint32_t dst_lo)
 
 struct Smem {
     // byte offsets into dynamic shared memory
-    uint32_t obs_stage, row_stage, stages, consts, bars;
+    uint32_t obs_stage, row_stage, stages, rows, out_rows, consts, bars;
 };
-__host__ __device__ inline Smem smem_plan(int D, int A)
+// `sets` io-warp sets (1, or 2 with the fused env step); each set owns one observation stage's parity, three row stages
+// (noise | raw actions | clipped actions) and -- fused env step -- one stage of next-observation rows
+__host__ __device__ inline Smem smem_plan(int D, int A, int sets, bool env_step = true)
 {
     Smem s;
     s.obs_stage = align128((uint32_t)(TILE * D * sizeof(float)));
     s.row_stage = align128((uint32_t)(TILE * A * sizeof(float)));
-    s.stages = align128(IMG_SMEM_BYTES);                                // obs x 2 | noise | raw actions | clipped actions
-    s.consts = s.stages + 2 * s.obs_stage + 3 * s.row_stage;      // std | log_std | low | high, 16 floats each
+    s.stages = align128(IMG_SMEM_BYTES);                                // obs x 2 | per set: noise | raw actions | clipped actions
+    s.rows = s.stages + 2 * s.obs_stage;
+    s.out_rows = s.rows + (uint32_t)sets * 3 * s.row_stage;            // per set (fused env step only): next-observation rows
+    s.consts = s.out_rows + ((sets > 1 && env_step) ? (uint32_t)sets * s.obs_stage : 0u);   // std | log_std | low | high, 16 floats each
     s.bars = s.consts + 4 * NH * (uint32_t)sizeof(float);
     return s;
 }
@@ -363,38 +356,60 @@ __device__ __forceinline__ void issue_phase(int phase, uint32_t tn, uint32_t x, 
 // ------------------------------------------------------------------------------------------
 constexpr int IO_THREADS = TILE;
 constexpr int ALL_THREADS = THREADS + 32 + IO_THREADS;
-__device__ __forceinline__ void io_barrier() { asm volatile("bar.sync 2, %0;" ::"n"(IO_THREADS) : "memory"); }
+// named barrier of io set `set` (ids 2, 3)
+__device__ __forceinline__ void io_barrier(int set) { asm volatile("bar.sync %0, %1;" ::"r"(2 + set), "n"(IO_THREADS) : "memory"); }
 
-__global__ void __launch_bounds__(ALL_THREADS, 1)
+// The env step fused behind the forward pass (NCT > 0): what the step writes besides the handle's own state.
+struct StepOut {
+    float *obs_next;      // [E][D] the observation after the step (the rollout buffer's next slab)
+    float *reward;        // [E]
+    uint8_t *done;        // [E]
+};
+
+// NCT = 0: the forward pass alone.  NCT > 0: FUSED POLICY + ENV STEP for a default station of NCT spots (battery on, PV with
+// three steps ahead, no requested-SoC plane: obs_dim = 8 + 2 NCT + 1, act_dim = NCT + 1).  The io warps -- thread = row = env,
+// one warp = one 32-env state block, exactly the step kernel's mapping -- carry on with the env step of their tile as soon
+// as its clipped actions are in shared memory: same env_step() body, same warp-cooperative admission of arrivals, so
+// the results are bit-identical to sng_policy_forward_* followed by sng_step.  The env step is ~1,100 dependent-ish
+// instructions per warp, longer than a tile's tensor-core work, so TWO io sets alternate over the tiles (set = parity of
+// the CTA's tile number = its X buffer): a set has two tiles' time for staging X, the heads' tail and the env step.
+template <int NCT, int IO_SETS>
+__global__ void __launch_bounds__(ALL_THREADS + (IO_SETS - 1) * IO_THREADS, 1)
     policy_tc_kernel(const float *__restrict__ img, const float *__restrict__ obs, const float *__restrict__ noise,
                      const float *__restrict__ low, const float *__restrict__ high, float *raw_actions, float *actions,
                      float *values, float *log_probs, long long n_envs, int D, int A, int aligned, long long *trace,
                      const unsigned long long *rng_step, unsigned long long rng_offset, unsigned long long rng_seed,
-                     unsigned long long rng_gid0, float *noise_out, int early)
+                     unsigned long long rng_gid0, float *noise_out, int early, const Params<float> envp, const StepOut so)
 {
+    static_assert(IO_SETS == 1 || IO_SETS == 2, "one or two io sets");
+    static_assert(NCT == 0 || IO_SETS == 2, "the fused env step needs two io sets");
     int tr = 0;
 #define TRACE() do { if (trace && blockIdx.x == 0 && threadIdx.x == 0 && tr < 64) trace[tr++] = clock64(); } while (0)
+    // the same for the first thread of io set 0 (slots 64..127) and of io set 1 (slots 128..191)
+#define TRACE_IO() do { if (trace && blockIdx.x == 0 && tio == 0 && tr < 64) trace[64 * (1 + set) + tr++] = clock64(); } while (0)
     if (trace && blockIdx.x == 0 && threadIdx.x == 0) trace[255] = clock64();
     extern __shared__ __align__(128) unsigned char smem[];
-    const Smem sp = smem_plan(D, A);
+    const Smem sp = smem_plan(D, A, IO_SETS, NCT > 0);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const bool issuer = warp == THREADS / 32, io = warp > THREADS / 32;
+    const int set = io ? (warp - THREADS / 32 - 1) / (IO_THREADS / 32) : 0;      // io set of this warp
     const int cb = warp >> 2;                               // column block of a compute warp in the epilogues
     const int t = (warp & 3) * 32 + lane;                   // row of the tile = TMEM lane = env (compute and io warps)
     float *obs_s0 = reinterpret_cast<float *>(smem + sp.stages);
-    float *noise_s = reinterpret_cast<float *>(smem + sp.stages + 2 * sp.obs_stage);
-    float *raw_s = reinterpret_cast<float *>(smem + sp.stages + 2 * sp.obs_stage + sp.row_stage);
-    float *act_s = reinterpret_cast<float *>(smem + sp.stages + 2 * sp.obs_stage + 2 * sp.row_stage);
+    float *noise_s = reinterpret_cast<float *>(smem + sp.rows + (uint32_t)set * 3 * sp.row_stage);
+    float *raw_s = reinterpret_cast<float *>(smem + sp.rows + (uint32_t)set * 3 * sp.row_stage + sp.row_stage);
+    float *act_s = reinterpret_cast<float *>(smem + sp.rows + (uint32_t)set * 3 * sp.row_stage + 2 * sp.row_stage);
+    float *oout_s = reinterpret_cast<float *>(smem + sp.out_rows + (uint32_t)set * sp.obs_stage);     // NCT > 0
     float *const_s = reinterpret_cast<float *>(smem + sp.consts);
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + sp.bars);
     uint64_t *wbar = bars;                                  // [4] weight image: critic layer 0 | actor layer 0 | rest of the critic | rest of the actor
     uint64_t *obar = bars + 4;                              // [2] observation rows of the even / odd tiles have landed
-    uint64_t *nbar = bars + 6;                              // noise rows have landed
+    uint64_t *nbar = bars + 6;                              // noise rows have landed (io set 1: bars + 19)
     uint64_t *xbar = bars + 7;                              // [2] io -> issuer (4 warp arrivals): X of an even / odd tile is in TMEM
     uint64_t *rbar = bars + 9;                              // [2] compute -> issuer (16 warp arrivals): tanh(critic / actor layer) is in TMEM
     uint64_t *mbar = bars + 11;                             // [2][2] issuer -> compute: layer 0 / layer 1 of the critic / the actor is complete
     uint64_t *hbar = bars + 15;                             // [2][2] issuer -> io, compute: the critic's / the actor's head of an even / odd tile
-    constexpr int N_BARS = 19;
+    constexpr int N_BARS = 20;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + N_BARS);
     const bool value_only = actions == nullptr;
     const int n_nets = value_only ? 1 : 2;
@@ -537,7 +552,8 @@ __global__ void __launch_bounds__(ALL_THREADS, 1)
         }
     } else if (my_tiles > 0) {
         // ---- io warps ----
-        const int tio = (int)threadIdx.x - (THREADS + 32);                    // 0 .. 127
+        const int tio = (int)threadIdx.x - (THREADS + 32) - set * IO_THREADS;   // 0 .. 127 within the set
+        uint64_t *nbar_s = set ? bars + 19 : nbar;
         const uint32_t row_bytes = (uint32_t)(TILE * A * sizeof(float));
         const bool rng = !value_only && noise == nullptr && rng_step != nullptr;      // in-kernel Gaussian noise
         const bool sample = !value_only && noise != nullptr;                         // caller-supplied noise rows
@@ -563,7 +579,7 @@ __global__ void __launch_bounds__(ALL_THREADS, 1)
                 mbar_wait(obar + buf, (uint32_t)((it >> 1) & 1));
             } else {                                                     // ragged last tile / unaligned rows: plain loads
                 for (int k = tio; k < nv * D; k += IO_THREADS) obs_s[k] = obs[e0 * D + k];
-                io_barrier();
+                io_barrier(set);
             }
             const float *row = obs_s + t * D;
             __syncwarp();
@@ -582,15 +598,16 @@ __global__ void __launch_bounds__(ALL_THREADS, 1)
             tmem_wait_st();
             tc_fence_before();
             mbar_arrive_warp(xbar + buf);
-            io_barrier();                                                // every io thread is done with this observation stage
+            io_barrier(set);                                                // every io thread is done with this observation stage
             if (tio == 0 && tile_full(tile + 2 * stride)) fetch_obs(tile + 2 * stride, buf);
         };
 
-        stage_x(first_tile, 0);
-        if (my_tiles > 1) stage_x(first_tile + stride, 1);
+        // set `set` owns the CTA's tiles number set, set + IO_SETS, ... (one set: all of them)
+        for (int k = set; k < 2 && k < my_tiles; k += IO_SETS) stage_x(first_tile + (long long)k * stride, k);
+        if (NCT) publish_dep_table_warp(envp);          // the env step's departure / arrival-gap table (per warp, no CTA barrier)
 
 #pragma unroll 1
-        for (int it = 0; it < my_tiles; ++it) {
+        for (int it = set; it < my_tiles; it += IO_SETS) {
             const long long tile = first_tile + (long long)it * stride;
             const long long e0 = tile * TILE;
             const int nv = (int)((n_envs - e0) < TILE ? (n_envs - e0) : TILE);
@@ -600,12 +617,37 @@ __global__ void __launch_bounds__(ALL_THREADS, 1)
             if (sample) {                                                // noise_s: the previous tail ended with a barrier
                 if (full) {
                     if (tio == 0) {
-                        mbar_expect_tx(nbar, row_bytes);
-                        bulk_g2s(noise_s, noise + e0 * A, row_bytes, nbar);
+                        mbar_expect_tx(nbar_s, row_bytes);
+                        bulk_g2s(noise_s, noise + e0 * A, row_bytes, nbar_s);
                     }
                 } else {
                     for (int k = tio; k < nv * A; k += IO_THREADS) noise_s[k] = noise[e0 * A + k];
-                    io_barrier();
+                    io_barrier(set);
+                }
+            }
+            if (rng) {
+                // In-kernel exploration noise, drawn BEFORE the heads are waited for (it does not depend on them: this is idle
+                // time of the io warps): one Philox block per four action columns, keyed by (seed, step), counter = (global
+                // env, column block), Box-Muller; each thread parks its own row in the noise stage
+                const unsigned long long gid = rng_gid0 + (unsigned long long)(e0 + t);
+#pragma unroll
+                for (int q = 0; q < NH / 4; ++q) {
+                    if (4 * q < A) {                                     // warp-uniform
+                        uint32_t x[4];
+                        float zz[4];
+                        philox4x32_10((uint32_t)gid, (uint32_t)(gid >> 32), (uint32_t)q, (uint32_t)step, (uint32_t)rng_seed,
+                                      (uint32_t)(rng_seed >> 32) ^ (uint32_t)(step >> 32), x);
+                        box_muller(x[0], x[1], zz[0], zz[1]);
+                        box_muller(x[2], x[3], zz[2], zz[3]);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const int a = 4 * q + j;
+                            if (a < A) {
+                                noise_s[t * A + a] = zz[j];
+                                if (noise_out && t < nv) noise_out[(e0 + t) * A + a] = zz[j];
+                            }
+                        }
+                    }
                 }
             }
             // ---- this tile's heads: value (column 32 of its X buffer), action means (columns 48..63), into registers ----
@@ -622,36 +664,27 @@ __global__ void __launch_bounds__(ALL_THREADS, 1)
                 tmem_ld16(xb + 48, out);
             }
             tmem_wait_ld();
+            TRACE_IO();
             // The X buffer is free now (the heads' commits cover every MMA that read it, and their outputs are in
             // registers): stage the tile that uses it next -- two tiles on -- BEFORE the sampling work, so that the
             // issuer finds X of the next tile ready a whole tile early and can run its layer 0 ahead of the heads.
             if (it + 2 < my_tiles) stage_x(tile + 2 * stride, it + 2);
+            TRACE_IO();
             if (t < nv) values[e0 + t] = __uint_as_float(value_bits);
             if (n_nets == 2) {
-                if (sample && full) { mbar_wait(nbar, n_phase); n_phase ^= 1u; }
-                // DiagGaussian sample, clip to the Box, log-probability.  In-kernel noise: one Philox block per four
-                // action columns, keyed by (seed, step), counter = (global env, column block)
+                if (sample && full) { mbar_wait(nbar_s, n_phase); n_phase ^= 1u; }
+                // DiagGaussian sample, clip to the Box, log-probability (z: this thread's row of the noise stage)
                 float lp = 0.f;
 #pragma unroll
                 for (int q = 0; q < NH / 4; ++q) {
                     if (4 * q < A) {                                     // warp-uniform
-                        float zz[4] = {0.f, 0.f, 0.f, 0.f};
-                        if (rng) {
-                            const unsigned long long gid = rng_gid0 + (unsigned long long)(e0 + t);
-                            uint32_t x[4];
-                            philox4x32_10((uint32_t)gid, (uint32_t)(gid >> 32), (uint32_t)q, (uint32_t)step, (uint32_t)rng_seed,
-                                          (uint32_t)(rng_seed >> 32) ^ (uint32_t)(step >> 32), x);
-                            box_muller(x[0], x[1], zz[0], zz[1]);
-                            box_muller(x[2], x[3], zz[2], zz[3]);
-                        }
                         float part = 0.f;
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
                             const int a = 4 * q + j;
                             if (a < A) {
                                 const float sd = const_s[a], ls = const_s[NH + a];
-                                const float z = sample ? noise_s[t * A + a] : zz[j];
-                                if (rng && noise_out && t < nv) noise_out[(e0 + t) * A + a] = z;
+                                const float z = (sample || rng) ? noise_s[t * A + a] : 0.f;
                                 const float x = fmaf(z, sd, __uint_as_float(out[a]));
                                 raw_s[t * A + a] = x;
                                 act_s[t * A + a] = fminf(fmaxf(x, const_s[2 * NH + a]), const_s[3 * NH + a]);   // SB3 clips Box actions before env.step
@@ -662,7 +695,7 @@ __global__ void __launch_bounds__(ALL_THREADS, 1)
                     }
                 }
                 if (t < nv) log_probs[e0 + t] = lp;
-                io_barrier();                                            // all rows of the two slabs are in shared memory
+                io_barrier(set);                                            // all rows of the two slabs are in shared memory
                 if (full) {                                              // coalesced 16-byte stores
                     const int nvec = (int)(row_bytes / 16);
                     const float4 *rs = reinterpret_cast<const float4 *>(raw_s), *as = reinterpret_cast<const float4 *>(act_s);
@@ -677,7 +710,33 @@ __global__ void __launch_bounds__(ALL_THREADS, 1)
                         actions[e0 * A + k] = act_s[k];
                     }
                 }
-                io_barrier();                                            // the slabs may be overwritten by the next tile
+                io_barrier(set);                                            // the slabs may be overwritten by the next tile
+            }
+            TRACE_IO();
+            if constexpr (NCT > 0) {
+                // ---- the env step of this tile's 128 envs: warp = one 32-env state block, thread = env; the clipped action
+                //      rows are in act_s, the next observation is assembled in oout_s and leaves as one coalesced slab ----
+                typedef WordOf<float>::type word;
+                const long long e = e0 + t;
+                word *spot = envp.spot + (size_t)(e / kBlock) * (size_t)(NCT * kPlanes * kBlock) + (size_t)(e % kBlock);
+                StateRegs<float, NCT> st;
+                load_state<float, NCT, 1, true>(envp, e, spot, st);
+                const RowIO<float, 1> rio = {act_s + t * A, act_s + t * A, oout_s + t * D, 8, 8 + NCT};
+                const Arrivals arr = env_step<float, NCT, 8, false, true, true, 1, true>(envp, e, spot, st, rio, so.reward, so.done);
+                TRACE_IO();
+                // the admission queue reuses this warp's own action rows (every lane is done with its row: the shuffles at
+                // the top of the admission are the warp's barrier)
+                admit_arrivals_warp<float, NCT, true>(envp, e - lane, lane, spot - lane, arr, reinterpret_cast<uint16_t *>(act_s + (t - lane) * A));
+                TRACE_IO();
+                io_barrier(set);                                         // all 128 rows of the next observation are in shared memory
+                {
+                    const int nvec = (int)(TILE * D * sizeof(float) / 16);
+                    const float4 *os = reinterpret_cast<const float4 *>(oout_s);
+                    float4 *og = reinterpret_cast<float4 *>(so.obs_next + e0 * D);
+                    for (int k = tio; k < nvec; k += IO_THREADS) og[k] = os[k];
+                }
+                io_barrier(set);                                         // the stage may be overwritten by the set's next tile
+                TRACE_IO();
             }
             tc_fence_before();
         }
@@ -742,10 +801,12 @@ extern "C" int sng_policy_pack(const sng_mlp *mlp, void *packed, void *stream)
 }
 
 namespace {
+// nct = 0: the forward pass alone; 4 / 10: fused with the env step of that default station (envp, so)
 int launch_policy_tc(const void *packed, int obs_dim, int act_dim, const float *obs, const float *noise, const float *low,
                      const float *high, float *raw_actions, float *actions, float *values, float *log_probs, int64_t n_envs,
                      const unsigned long long *rng_step, unsigned long long rng_offset, unsigned long long rng_seed,
-                     unsigned long long rng_gid0, float *noise_out, void *stream)
+                     unsigned long long rng_gid0, float *noise_out, void *stream, int nct = 0, const Params<float> *envp = nullptr,
+                     const StepOut *so = nullptr)
 {
     if (!packed || !obs || !values || n_envs < 1) return SNG_ERR_ARG;
     if (actions && (!raw_actions || !log_probs || !low || !high)) return SNG_ERR_ARG;
@@ -753,8 +814,13 @@ int launch_policy_tc(const void *packed, int obs_dim, int act_dim, const float *
     PointerDeviceGuard guard(obs);
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
-    const Smem sp = smem_plan(obs_dim, act_dim);
-    size_t smem = sp.bars + 160;   // 19 mbarriers + the TMEM address slot
+    // two io sets whenever the io warps carry more than the plain tail: the env step, or drawing the exploration noise
+    // (Philox + Box-Muller: ~500 instructions per thread and tile; measured on C3: 29.9 -> 28.1 us per rollout step)
+    const int sets = (nct || (actions && rng_step)) ? 2 : 1;
+    const Smem sp = smem_plan(obs_dim, act_dim, sets, nct > 0);
+    size_t smem = sp.bars + 176;   // 20 mbarriers + the TMEM address slot
+    const void *kern = nct == 10 ? (const void *)policy_tc_kernel<10, 2> : (nct == 4 ? (const void *)policy_tc_kernel<4, 2> :
+                       (sets == 2 ? (const void *)policy_tc_kernel<0, 2> : (const void *)policy_tc_kernel<0, 1>));
     if (g_policy_pdl & 2) {
         // the CTA claims its SM's whole shared memory: no CTA of a kernel launched early behind this one (programmatic
         // dependent launch) can become resident next to it and take issue slots from the compute warps
@@ -762,33 +828,48 @@ int launch_policy_tc(const void *packed, int obs_dim, int act_dim, const float *
         cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
         if ((size_t)optin > smem) smem = (size_t)optin;
     }
-    if (ensure_smem(dev, (const void *)policy_tc_kernel, smem) != SNG_OK) return SNG_ERR_CUDA;
+    if (ensure_smem(dev, kern, smem) != SNG_OK) return SNG_ERR_CUDA;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const long long n_tiles = (n_envs + TILE - 1) / TILE;
     long long grid = n_tiles;
     if (grid > sms) grid = sms;
-    const int aligned = aligned16(obs) && aligned16(noise) && aligned16(raw_actions) && aligned16(actions) && aligned16(packed);
+    int aligned = aligned16(obs) && aligned16(noise) && aligned16(raw_actions) && aligned16(actions) && aligned16(packed);
     if (!aligned16(packed)) return SNG_ERR_ARG;
-    if (g_policy_pdl & 1) {
-        cudaLaunchConfig_t lc = {};
-        lc.gridDim = dim3((unsigned)grid); lc.blockDim = dim3(ALL_THREADS); lc.dynamicSmemBytes = smem; lc.stream = (cudaStream_t)stream;
-        cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        at[0].val.programmaticStreamSerializationAllowed = 1;
-        lc.attrs = at; lc.numAttrs = 1;
-        const cudaError_t e = cudaLaunchKernelEx(&lc, policy_tc_kernel, reinterpret_cast<const float *>(packed), obs, noise, low, high, raw_actions,
-                                                 actions, values, log_probs, (long long)n_envs, obs_dim, act_dim, aligned, g_trace,
-                                                 rng_step, (unsigned long long)rng_offset, (unsigned long long)rng_seed,
-                                                 (unsigned long long)rng_gid0, noise_out, 1);
-        return e == cudaSuccess ? SNG_OK : SNG_ERR_CUDA;
+    Params<float> ep;
+    StepOut eo = {nullptr, nullptr, nullptr};
+    memset(&ep, 0, sizeof(ep));
+    if (nct) {
+        // the fused kernel handles whole, aligned tiles only (the caller falls back to two launches otherwise)
+        if (!envp || !so || !actions || !aligned || !aligned16(so->obs_next) || n_envs % TILE != 0) return SNG_ERR_UNSUPPORTED;
+        ep = *envp;
+        eo = *so;
     }
-    policy_tc_kernel<<<(unsigned)grid, ALL_THREADS, smem, (cudaStream_t)stream>>>(reinterpret_cast<const float *>(packed), obs, noise, low, high,
-                                                                             raw_actions, actions, values, log_probs,
-                                                                             (long long)n_envs, obs_dim, act_dim, aligned, g_trace,
-                                                                             rng_step, rng_offset, rng_seed, rng_gid0, noise_out, 0);
-    return cudaGetLastError() == cudaSuccess ? SNG_OK : SNG_ERR_CUDA;
+    const int pdl = g_policy_pdl & 1;
+    long long nenv = (long long)n_envs;
+    int early = pdl;
+    const float *img = reinterpret_cast<const float *>(packed);
+    void *args[] = {&img, &obs, &noise, &low, &high, &raw_actions, &actions, &values, &log_probs, &nenv, &obs_dim, &act_dim, &aligned,
+                    &g_trace, &rng_step, &rng_offset, &rng_seed, &rng_gid0, &noise_out, &early, &ep, &eo};
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = dim3((unsigned)grid); lc.blockDim = dim3(ALL_THREADS + (sets - 1) * IO_THREADS); lc.dynamicSmemBytes = smem; lc.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    lc.attrs = at; lc.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelExC(&lc, kern, args) == cudaSuccess ? SNG_OK : SNG_ERR_CUDA;
 }
 }  // namespace
+
+// Fused policy forward + env step (called by Engine<float>::policy_step through sng_policy_step).
+namespace sng {
+int launch_policy_step(const Params<float> &p, const PolicyStepArgs &a, cudaStream_t st)
+{
+    const StepOut so = {a.obs_next, a.reward, a.done};
+    return launch_policy_tc(a.packed, p.D, p.A, a.obs, a.noise, a.low, a.high, a.raw_actions, a.actions, a.values, a.log_probs, p.n_envs,
+                            reinterpret_cast<const unsigned long long *>(a.step_counter), a.step_offset, a.seed, p.gid0, a.noise_out, (void *)st,
+                            p.N, &p, &so);
+}
+}  // namespace sng
 
 extern "C" int sng_policy_forward_packed(const void *packed, int obs_dim, int act_dim, const float *obs, const float *noise,
                                          const float *low, const float *high, float *raw_actions, float *actions,

@@ -195,7 +195,8 @@ class RolloutBuffer:
 @torch.no_grad()
 def collect_rollout(env, policy: MlpPolicy, buf: RolloutBuffer, obs: torch.Tensor, episode_starts: torch.Tensor,
                     generator: torch.Generator | None = None, deterministic: bool = False, fused: bool = True,
-                    rng_seed: int | None = None, pack: bool = True, advance_counter: bool = True, pdl: bool = False):
+                    rng_seed: int | None = None, pack: bool = True, advance_counter: bool = True, pdl: bool = False,
+                    fuse_step: bool = False):
     """SB3 OnPolicyAlgorithm.collect_rollouts for a BatchedSmartNanogridEnv: n_steps policy + env steps,
     then GAE.  `obs` [E, D] is the current observation (from reset() or the previous rollout),
     `episode_starts` [E] u8.  Returns (last_obs, last_dones) to carry into the next call.
@@ -203,6 +204,8 @@ def collect_rollout(env, policy: MlpPolicy, buf: RolloutBuffer, obs: torch.Tenso
     the policy kernel (Philox keyed by rng_seed and the policy's step counter: no noise tensor, no RNG launch).
     pack=False / advance_counter=False: the caller packs the weights / advances the step counter itself (several
     shards collected side by side share both, see ShardedGraphedRollout).
+    fuse_step (fused kernel only, env.supports_policy_step()): ONE launch per rollout step -- the policy kernel's io warps
+    run the env step of their tile themselves (env.policy_step, sng_policy_step); bit-identical to the two launches.
     pdl (fused kernel only): programmatic dependent launch inside the loop -- a kernel starts while its predecessor is
     draining (block scheduling, barrier / TMEM set-up, the policy's weight image, the step's state loads, none of which
     the predecessor writes) and waits for it before reading what it wrote.  "policy": only the policy kernel is
@@ -218,6 +221,7 @@ def collect_rollout(env, policy: MlpPolicy, buf: RolloutBuffer, obs: torch.Tenso
         policy.pack_weights()          # once per rollout: the weights do not change while it is collected
     if in_kernel_noise and (getattr(policy, "rng_counter", None) is None or policy.rng_counter.device != obs.device):
         policy.rng_counter = torch.zeros(1, dtype=torch.int64, device=obs.device)   # rollout steps drawn so far
+    fuse_step = bool(fuse_step and fused and env.supports_policy_step())
     pdl = pdl if fused else False
     mode = "both" if pdl is True else (pdl or "")
     exclusive = mode.endswith("+x")
@@ -230,7 +234,7 @@ def collect_rollout(env, policy: MlpPolicy, buf: RolloutBuffer, obs: torch.Tenso
     if policy_mode:
         nat.check(nat.lib().sng_policy_set_launch_mode(policy_mode & 2))   # the first call follows the weight packing: ordinary launch
     try:
-        _rollout_steps(env, policy, buf, low, high, fused, in_kernel_noise, rng_seed, deterministic, generator, policy_mode)
+        _rollout_steps(env, policy, buf, low, high, fused, in_kernel_noise, rng_seed, deterministic, generator, policy_mode, fuse_step)
         last_obs = buf.observations[buf.n_steps]
         if fused:
             policy.fused_forward(last_obs, None, None, None, None, None, buf.last_values, None, repack=False)
@@ -247,11 +251,21 @@ def collect_rollout(env, policy: MlpPolicy, buf: RolloutBuffer, obs: torch.Tenso
     return last_obs, buf.dones[buf.n_steps - 1]
 
 
-def _rollout_steps(env, policy, buf, low, high, fused, in_kernel_noise, rng_seed, deterministic, generator, policy_mode=0):
+def _rollout_steps(env, policy, buf, low, high, fused, in_kernel_noise, rng_seed, deterministic, generator, policy_mode=0,
+                   fuse_step=False):
     for s in range(buf.n_steps):
         o = buf.observations[s]
         if s == 1 and policy_mode & 1:     # from the second call on the policy kernel follows a step kernel
             nat.check(nat.lib().sng_policy_set_launch_mode(policy_mode))
+        if fuse_step:                      # one kernel: policy forward, sampling, clipping, env step, next observation
+            noise = None
+            if not in_kernel_noise:
+                noise = torch.zeros(buf.n_envs, buf.actions.shape[2], device=o.device) if deterministic else \
+                    torch.randn(buf.n_envs, buf.actions.shape[2], device=o.device, generator=generator)
+            env.policy_step(policy._packed, o, low, high, buf.raw_actions[s], buf.actions[s], buf.values[s], buf.log_probs[s],
+                            out=(buf.observations[s + 1], buf.rewards[s], buf.dones[s]), noise=noise,
+                            rng=(rng_seed, policy.rng_counter, s) if in_kernel_noise else None)
+            continue
         if in_kernel_noise:
             policy.fused_forward(o, None, low, high, buf.raw_actions[s], buf.actions[s], buf.values[s], buf.log_probs[s],
                                  repack=False, rng=(rng_seed, policy.rng_counter, s, env.env_gid0))
@@ -277,7 +291,7 @@ class GraphedRollout:
     or -- rng_seed=None -- by torch's default CUDA generator (graph-safe); `deterministic=True` uses the mean."""
 
     def __init__(self, env, policy: MlpPolicy, buf: RolloutBuffer, deterministic: bool = False, fused: bool = True,
-                 rng_seed: int | None = 0, pdl: bool = False):
+                 rng_seed: int | None = 0, pdl: bool = False, fuse_step: bool = False):
         dev = buf.rewards.device
         self.env, self.policy, self.buf = env, policy, buf
         self.obs_in = torch.zeros(buf.n_envs, buf.observations.shape[2], device=dev)
@@ -286,12 +300,12 @@ class GraphedRollout:
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):                     # warm-up outside capture (lazy inits, cuBLAS workspaces)
             self.obs_in.copy_(env.obs)
-            collect_rollout(env, policy, buf, self.obs_in, self.starts_in, deterministic=deterministic, fused=fused, rng_seed=rng_seed, pdl=pdl)
+            collect_rollout(env, policy, buf, self.obs_in, self.starts_in, deterministic=deterministic, fused=fused, rng_seed=rng_seed, pdl=pdl, fuse_step=fuse_step)
         torch.cuda.current_stream(dev).wait_stream(side)
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.last_obs, self.last_dones = collect_rollout(env, policy, buf, self.obs_in, self.starts_in,
-                                                             deterministic=deterministic, fused=fused, rng_seed=rng_seed, pdl=pdl)
+                                                             deterministic=deterministic, fused=fused, rng_seed=rng_seed, pdl=pdl, fuse_step=fuse_step)
 
     def __call__(self, obs: torch.Tensor, episode_starts: torch.Tensor):
         self.obs_in.copy_(obs)

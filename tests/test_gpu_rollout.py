@@ -284,6 +284,42 @@ def test_programmatic_dependent_launch_changes_nothing_but_timing():
         e.close()
 
 
+@pytest.mark.parametrize("E,n_spots", [(1024, 10), (65536, 10), (38272, 10), (4096, 4)])
+def test_fused_policy_step_equals_policy_then_step(E, n_spots):
+    """sng_policy_step (ONE launch per rollout step: the policy kernel's io warps run the env step of their tile) gives bit
+    for bit what the policy kernel followed by the step kernel gives: everything the rollout buffer stores, and the env
+    state.  30 steps > one 24-step episode, so the fused auto-reset is crossed; 65,536 envs = four tiles per CTA,
+    38,272 envs = CTAs with two and with three tiles."""
+    from smart_nanogrid_gym_b200 import BatchedSmartNanogridEnv
+    from smart_nanogrid_gym_b200.rollout import GraphedRollout, MlpPolicy, RolloutBuffer
+    kw = dict(KW, number_of_chargers=n_spots)
+    n = 30
+    torch.manual_seed(6)
+    res = []
+    policy = None
+    for fuse in (False, True):
+        env = BatchedSmartNanogridEnv(E, device="cuda:0", seed=11, **kw)
+        if policy is None:
+            policy = MlpPolicy(env.cfg.obs_dim, env.cfg.act_dim).to("cuda:0")
+        assert env.supports_policy_step()
+        buf = RolloutBuffer(n, E, env.cfg.obs_dim, env.cfg.act_dim, "cuda:0")
+        env.reset()
+        collect = GraphedRollout(env, policy, buf, rng_seed=4, fuse_step=fuse, pdl="policy" if fuse else False)
+        obs = env.reset(reset_battery=True)
+        policy.rng_counter.zero_()
+        starts = torch.ones(E, dtype=torch.uint8, device="cuda:0")
+        for _ in range(2):
+            obs, starts = collect(obs, starts)
+        torch.cuda.synchronize()
+        res.append([x.clone() for x in (buf.raw_actions, buf.actions, buf.values, buf.log_probs, buf.rewards, buf.observations,
+                                        buf.dones, buf.advantages, env._spot, env._envst, env.last_return)])
+        assert env.error_flags() == 0
+        env.close()
+    for a, b in zip(res[0], res[1]):
+        assert torch.equal(a, b)
+    assert int(res[0][6].sum()) > 0          # episodes ended inside the rollouts
+
+
 def test_sharded_rollout_equals_the_unsharded_one():
     """Two env shards collected side by side (ShardedGraphedRollout: parallel graph branches, in-kernel noise keyed by
     global env id) produce bit for bit what one env of the summed size does."""
