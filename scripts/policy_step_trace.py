@@ -1,5 +1,6 @@
-"""In-kernel clock64 trace of one CTA of the fused policy + env step kernel (sng_policy_step): compute warp 0 (slots 0..63),
-first thread of io set 0 (64..127) and of io set 1 (128..191)."""
+"""In-kernel clock64 trace of one CTA of the policy kernel with in-kernel exploration noise (two io sets), or -- argument
+`fused` -- of the fused policy + env step kernel (sng_policy_step): compute warp 0 (slots 0..63), first thread of io set 0
+(64..127) and of io set 1 (128..191).  Usage: policy_step_trace.py [forward|fused]"""
 import os, sys, ctypes as C, torch
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 from smart_nanogrid_gym_b200 import BatchedSmartNanogridEnv, _native as nat
@@ -14,8 +15,12 @@ tr = torch.zeros(256, dtype=torch.int64, device=dev)
 lib = nat.lib(); lib.sng_policy_debug_trace.argtypes = [C.c_void_p]
 lib.sng_policy_debug_trace(C.c_void_p(tr.data_ptr()))
 low, high = env.action_low.float(), env.action_high.float()
-env.policy_step(policy._packed, buf.observations[0], low, high, buf.raw_actions[0], buf.actions[0], buf.values[0], buf.log_probs[0],
-                out=(buf.observations[1], buf.rewards[0], buf.dones[0]), rng=(1, policy.rng_counter, 0))
+if len(sys.argv) > 1 and sys.argv[1] == "fused":
+    env.policy_step(policy._packed, buf.observations[0], low, high, buf.raw_actions[0], buf.actions[0], buf.values[0], buf.log_probs[0],
+                    out=(buf.observations[1], buf.rewards[0], buf.dones[0]), rng=(1, policy.rng_counter, 0))
+else:
+    policy.fused_forward(buf.observations[0], None, low, high, buf.raw_actions[0], buf.actions[0], buf.values[0], buf.log_probs[0],
+                         repack=False, rng=(1, policy.rng_counter, 0, 0))
 torch.cuda.synchronize()
 lib.sng_policy_debug_trace(None)
 t = tr.cpu().tolist(); base = t[255]
