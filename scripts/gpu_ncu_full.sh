@@ -4,12 +4,12 @@
 out=gpurun_out; mkdir -p $out
 B="python bench.py --steps 24 --warmup 24 --no-cpu --e2e-steps 2 --graph-steps 0 --legs none"
 timeout 300 $B > $out/ncu_plain_c4.log 2>&1 && \
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:step_ -s 30 -c 1 -o $out/r2_step_c4_full -f $B > $out/ncu_c4.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:step_ -s 30 -c 1 -o $out/r3_step_c4_full -f $B > $out/ncu_c4.log 2>&1
 tail -1 $out/ncu_c4.log
 timeout 300 $B --workload c5 > $out/ncu_plain_c5.log 2>&1 && \
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:step_ -s 30 -c 1 -o $out/r2_step_c5_full -f $B --workload c5 > $out/ncu_c5.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:step_ -s 30 -c 1 -o $out/r3_step_c5_full -f $B --workload c5 > $out/ncu_c5.log 2>&1
 tail -1 $out/ncu_c5.log
 timeout 300 python scripts/policy_tc_prof.py > $out/ncu_plain_tc.log 2>&1 && \
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:policy_tc -s 4 -c 1 -o $out/r2_policy_tc_v2 -f python scripts/policy_tc_prof.py > $out/ncu_tc.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:policy_tc -s 4 -c 1 -o $out/r3_policy_tc -f python scripts/policy_tc_prof.py > $out/ncu_tc.log 2>&1
 tail -1 $out/ncu_tc.log
 echo done

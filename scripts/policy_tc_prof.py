@@ -10,7 +10,8 @@ low = torch.zeros(11, device=dev); high = torch.ones(11, device=dev)
 raw, act = torch.empty(E, 11, device=dev), torch.empty(E, 11, device=dev)
 val, lp = torch.empty(E, device=dev), torch.empty(E, device=dev)
 policy.pack_weights()
-for _ in range(6):
-    policy.fused_forward(obs, noise, low, high, raw, act, val, lp, repack=False)
+ctr = torch.zeros(1, dtype=torch.int64, device=dev)
+for _ in range(6):      # the rollout's call: exploration noise drawn in the kernel (two io-warp sets)
+    policy.fused_forward(obs, None, low, high, raw, act, val, lp, repack=False, rng=(1, ctr, 0, 0))
 torch.cuda.synchronize()
 print("done")
