@@ -596,6 +596,43 @@ def load_shipped_policy(ctx, obs_dim, act_dim):
     return pol.to(ctx.dev)
 
 
+def pattern_ceiling_leg(ctx, E):
+    """What the step kernel's ACCESS PATTERN alone costs on this machine: sng_debug_traffic_skeleton performs the same loads
+    and stores from the same launch geometry and occupancy, without the arithmetic.  The copy-bandwidth roofline assumes
+    two perfectly sequential streams; the step moves five read streams and five write streams in 128-byte to 3.7 KB
+    granules per warp.  Reported beside the roofline (rank 0's GPU), not instead of it."""
+    import ctypes as C
+    torch = ctx.torch
+    env = make_env(ctx, "c4", E, ctx.rank * E)
+    env.reset()
+    g = torch.Generator(device=ctx.dev).manual_seed(7)
+    env.step(env.sample_actions(g))
+    lib, h = env._lib, env._h
+    stream = C.c_void_p(torch.cuda.current_stream(ctx.dev).cuda_stream)
+
+    def run(n, variant=0):
+        for _ in range(n):
+            rc = lib.sng_debug_traffic_skeleton(h, variant, stream)
+            if rc != 0:
+                raise RuntimeError("sng_debug_traffic_skeleton: %d" % rc)
+    run(30)
+    n = 300
+    ms = timed_ms(ctx, lambda: run(n)) / n
+    what_if = {}
+    for name, variant in (("two_plane_layout", 1), ("loads_only", 2), ("obs_rows_by_copy_engine", 4), ("stores_only", 3)):
+        run(10, variant)
+        what_if[name] = timed_ms(ctx, lambda: run(n, variant)) / n
+    traffic = ncu_traffic_bytes("c4", E)
+    out = {"ms_per_launch": ms, "launches": n, "envs_per_gpu": E,
+           "what": "the step kernel's loads and stores without its arithmetic (same geometry, occupancy and byte counts)",
+           "what_if_ms": what_if}
+    if traffic:
+        out["gbs_real_traffic"] = traffic / (ms * 1e-3) / 1e9
+        out["frac_of_copy_peak"] = out["gbs_real_traffic"] / ctx.peak
+    env.close()
+    return out
+
+
 def rollout_leg(ctx, wl_key, E, n_steps, shipped=False, fuse_step=False):
     """BASELINE config 3: PPO rollout collection, policy in the loop.  Reported beside the headline, not as it."""
     torch = ctx.torch
@@ -787,7 +824,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs")
     ap.add_argument("--rollout-pdl", default="", help="programmatic dependent launch inside the rollout loop of the c3 legs: "
                     "off, policy (default), step, both (optionally +x: policy CTAs claim their SM's whole shared memory)")
-    ap.add_argument("--legs", default="all", help="'all', 'none' or a comma list of c4_strong,c5,c3,c3_fused,c3_sharded,c3_sb3,c2,rollout_kernel,generic")
+    ap.add_argument("--legs", default="all", help="'all', 'none' or a comma list of c4_strong,pattern_ceiling,c5,c3,c3_fused,c3_sharded,c3_sb3,c2,rollout_kernel,generic")
     ap.add_argument("--rollout", type=int, default=0, help="legacy: same as --legs c3 with this many steps per rollout")
     args = ap.parse_args()
     PDL_ARG[0] = args.pdl
@@ -861,7 +898,7 @@ def main():
     want = args.legs
     if args.rollout > 0 and want in ("none", ""):
         want = "c3"
-    names = ["c4_strong", "c5", "c3", "c3_sb3", "c2", "rollout_kernel", "generic"] if want == "all" else [x for x in want.split(",") if x and x != "none"]
+    names = ["c4_strong", "pattern_ceiling", "c5", "c3", "c3_sb3", "c2", "rollout_kernel", "generic"] if want == "all" else [x for x in want.split(",") if x and x != "none"]
     legs = {}
     if names:
         floor_us = launch_floor_us(ctx)
@@ -897,6 +934,8 @@ def main():
                     for wl in ("c4_h5", "c4_pv2d", "c4_nopv"):
                         legs["generic_" + wl] = step_leg(ctx, wl, WORKLOADS[wl]["envs"], ctx.rank * WORKLOADS[wl]["envs"], floor_us, min_ms=120.0)
                         legs["generic_" + wl]["what"] = "SURVEY 8f row 4: " + WORKLOADS[wl]["name"] + ", 1,048,576 envs per GPU"
+                elif name == "pattern_ceiling":
+                    legs[name] = pattern_ceiling_leg(ctx, WORKLOADS["c4"]["envs"])
                 elif name == "rollout_kernel":
                     for n in (65536, 131072):
                         legs["rollout_kernel_%d" % n] = rollout_kernel_leg(ctx, "c4", n, floor_us)

@@ -97,7 +97,7 @@ typedef struct {
     int32_t plan_slots;     /* SNG_MAX_VEHICLES */
     int32_t diag_count;     /* reals per env in the optional diagnostics row */
     int32_t env_block;      /* 32: the per-spot state array is blocked by 32 envs (see sng_buffers.spot) */
-    int32_t spot_planes;    /* 3: planes of the per-spot state (header word, requested SoC, SoC) */
+    int32_t spot_planes;    /* 3: planes of the per-spot state (header word, SoC, requested SoC) */
 } sng_layout;
 
 /* Device buffers.  `real` = float (SNG_F32) or double (SNG_F64).  Optional pointers may be NULL.
@@ -105,9 +105,9 @@ typedef struct {
  * env_block = 32 envs: word (env e, spot i, plane f) lives at index
  *     (((e / 32) * n_spots + i) * 3 + f) * 32 + e % 32
  * with plane 0 = header word (arrival | departure << 8 | capacity << 16 | next arrival << 24, zero
- * extended), plane 1 = requested SoC (not maintained while every vehicle requests 1.0, i.e. sampled
- * schedules without enable_requested_state_of_charge), plane 2 = SoC column the next step starts from
- * (both `real` bit patterns).  The caller allocates ceil(E / 32) * n_spots * 3 * 32 words of real_bytes
+ * extended), plane 1 = SoC column the next step starts from, plane 2 = requested SoC (not maintained
+ * while every vehicle requests 1.0, i.e. sampled schedules without enable_requested_state_of_charge; last,
+ * so that the two planes every step reads are adjacent) (both `real` bit patterns).  The caller allocates ceil(E / 32) * n_spots * 3 * 32 words of real_bytes
  * bytes. */
 typedef struct {
     uint32_t struct_size;
@@ -262,6 +262,14 @@ int sng_null_launch(void *stream);
 /* Test hook: evaluates the step kernels' arrival-gap function (the number of failed Bernoulli(0.4) arrival trials a
  * 32-bit Philox word encodes: charging_station.py:213-214 sampled per vehicle) on n device words. */
 int sng_debug_arrival_gap(sng_env *env, const uint32_t *x, uint32_t *gap, int64_t n, void *stream);
+
+/* Measurement hook: ONE launch that performs the step kernel's memory traffic without its arithmetic (same geometry,
+ * occupancy, loads and stores; default 10-spot station, whole 32-env blocks).  Its duration is what the access pattern
+ * alone costs: the practical ceiling bench.py reports under the step kernel beside the copy-bandwidth roofline.  The
+ * handle's state is written back unchanged; obs / reward / done receive meaningless values.  variant 0 = the step
+ * kernel's own pattern; what-if patterns with the same byte counts: 1 header and SoC planes adjacent (a two-plane block
+ * layout), 2 loads only, 3 stores only (overwrites the state: reset afterwards), 4 observation rows through the copy engine. */
+int sng_debug_traffic_skeleton(sng_env *env, int variant, void *stream);
 
 /* Kernels launched by this handle so far (bench.py's gpu_launches claim). */
 int64_t sng_launch_count(const sng_env *env);

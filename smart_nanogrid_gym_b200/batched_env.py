@@ -67,7 +67,7 @@ class BatchedSmartNanogridEnv:
         self.done = z(E, dtype=torch.uint8)
         self.terminal_obs = z(E, D, dtype=torch.float32) if want_terminal_obs else None
         # per-spot state: one array of real-sized words, a structure of arrays blocked by 32 envs:
-        # [ceil(E/32)][N][3 planes: header | requested SoC | SoC][32] (include/sng.h sng_buffers.spot)
+        # [ceil(E/32)][N][3 planes: header | SoC | requested SoC][32] (include/sng.h sng_buffers.spot)
         B = self.layout.env_block
         self._blocks = (E + B - 1) // B
         self._word = torch.int32 if self.precision == nat.SNG_F32 else torch.int64
@@ -150,7 +150,7 @@ class BatchedSmartNanogridEnv:
     @property
     def soc(self):
         """[E, N] SoC column the next step starts from (a de-blocked copy of the kernel state)."""
-        return self._plane(2).view(self.real)
+        return self._plane(1).view(self.real)
 
     def spot_state(self):
         """Decoded per-spot state as numpy arrays [E, N]: arrival, departure, capacity, next arrival
@@ -158,7 +158,7 @@ class BatchedSmartNanogridEnv:
         h = self._plane(0).cpu().numpy().astype(np.int64)
         return dict(arr=(h & 0xFF).astype(np.int32), dep=((h >> 8) & 0xFF).astype(np.int32),
                     cap=((h >> 16) & 0xFF).astype(np.int32), next=((h >> 24) & 0xFF).astype(np.int32),
-                    req=self._plane(1).view(self.real).cpu().numpy().astype(np.float64),
+                    req=self._plane(2).view(self.real).cpu().numpy().astype(np.float64),
                     soc=self.soc.cpu().numpy().astype(np.float64))
 
     @property

@@ -227,6 +227,12 @@ int sng_policy_step(sng_env *env, const void *packed, const float *obs, const fl
     return done(env, env->eng->policy_step(a, (cudaStream_t)stream));
 }
 
+int sng_debug_traffic_skeleton(sng_env *env, int variant, void *stream)
+{
+    SNG_ENV_CHECK(env);
+    return done(env, env->eng->traffic_skeleton(variant, (cudaStream_t)stream));
+}
+
 int sng_set_launch_mode(sng_env *env, int mode)
 {
     SNG_ENV_CHECK(env);

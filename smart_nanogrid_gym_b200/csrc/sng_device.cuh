@@ -24,8 +24,8 @@ namespace sng {
 // State layout in HBM (DESIGN.md "Data layout")
 // ------------------------------------------------------------------------------------------
 constexpr int kBlock = 32;          // envs per state block = lanes of a warp
-constexpr int kPlanes = 3;          // per-spot state planes: header word, requested SoC, SoC
-enum : int { PL_HDR = 0, PL_REQ = 1, PL_SOC = 2 };
+constexpr int kPlanes = 3;          // per-spot state planes: header word, SoC, requested SoC
+enum : int { PL_HDR = 0, PL_SOC = 1, PL_REQ = 2 };   // header and SoC (read every step) adjacent: 256-byte runs; the requested SoC last
 
 // State words are as wide as `real` (uint32 / uint64) so that one array holds all three planes.
 template <typename real> struct WordOf;

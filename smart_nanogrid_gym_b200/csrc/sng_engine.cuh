@@ -44,6 +44,7 @@ struct EngineBase {
     virtual int sample_plan(cudaStream_t st) = 0;
     virtual int error_flags(uint32_t *out, cudaStream_t st) = 0;
     virtual int probe_arrival_gap(const uint32_t *x, uint32_t *g, long long n, cudaStream_t st) = 0;
+    virtual int traffic_skeleton(int variant, cudaStream_t st) = 0;
     virtual int set_tuning(int warps_per_cta, int use_generic, int use_bulk, int host_chunks) = 0;
     virtual int set_pipeline(int kernel_variant, int ctas_per_sm) = 0;
     virtual int set_launch_mode(int mode) = 0;
@@ -376,6 +377,97 @@ __global__ void __launch_bounds__(SNG_STEP_MAXT, (EXACT || NCT / L > 32) ? 2 : (
         }
     }
     if (tma_store && lane == 0) bulk_wait_read<0>();   // shared memory must stay valid until the store has read it
+}
+
+// Measurement hook (sng_debug_traffic_skeleton): the step kernel's memory traffic WITHOUT its arithmetic -- same launch
+// geometry, shared-memory footprint and register cap (so the same 32 resident warps per SM), the same loads (per-spot
+// header and SoC words, env scalars, the block's action rows through the copy engine) and the same stores (SoC words,
+// env scalars, reward, done flag, the block's observation rows as coalesced 16-byte stores).  Its duration is what the
+// access pattern alone costs on this machine: the practical ceiling under the step kernel, next to the copy-bandwidth
+// roofline.  State is written back unchanged (variant 3 overwrites it: reset the handle afterwards); obs / reward / done
+// receive meaningless values.  Default station, whole 32-env blocks only.
+// `variant` (what-if patterns, same byte counts): 0 the step kernel's own; 1 header and SoC planes adjacent (a two-plane
+// block layout: 2.5 KB contiguous per block instead of two lines out of every three); 2 loads only; 3 stores only;
+// 4 observation rows through the copy engine.
+template <typename real, int NCT>
+__global__ void __launch_bounds__(SNG_STEP_MAXT, SNG_STEP_MINB) traffic_skeleton_kernel(const Params<real> p, int variant)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    typedef typename WordOf<real>::type word;
+    constexpr int A = NCT + 1, D = 8 + 2 * NCT + 1;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const int blk = blockIdx.x * wpb + warp;
+    const int e0 = blk * kBlock;
+    if (e0 + kBlock > (int)p.n_envs) return;
+    constexpr uint32_t act_bytes = (uint32_t)(kBlock * A * sizeof(real)), obs_bytes = (uint32_t)(kBlock * D * sizeof(float));
+    constexpr uint32_t per_warp = align128(act_bytes) + align128(obs_bytes);
+    unsigned char *wbase = smem + 128 + (size_t)warp * per_warp;
+    real *act_s = reinterpret_cast<real *>(wbase);
+    float *obs_s = reinterpret_cast<float *>(wbase + align128(act_bytes));
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem) + warp;
+    const int e = e0 + lane;
+    word *spot = p.spot + (size_t)blk * (size_t)(NCT * kPlanes * kBlock) + lane;
+    const int sp = variant == 1 ? 2 * kBlock : kPlanes * kBlock, so = variant == 1 ? kBlock : PL_SOC * kBlock;   // spot stride, SoC plane
+    const bool do_ld = variant != 3, do_st = variant != 2;
+    word h[NCT], sw[NCT];
+    EnvSt<real> es;
+    memset(&es, 0, sizeof(es));
+    if (do_ld) {
+#pragma unroll
+        for (int j = 0; j < NCT; ++j) {
+            h[j] = spot[(size_t)j * sp + PL_HDR * kBlock];
+            sw[j] = spot[(size_t)j * sp + so];
+        }
+        es = p.envst[e];
+        if (lane == 0) {
+            mbar_init(bar, 1);
+            fence_mbar_init();
+            mbar_expect_tx(bar, act_bytes);
+            bulk_g2s(act_s, p.actions + (size_t)e0 * A, act_bytes, bar);
+        }
+        __syncwarp();
+        mbar_wait(bar, 0u);
+    } else {
+#pragma unroll
+        for (int j = 0; j < NCT; ++j) { h[j] = (word)j; sw[j] = (word)lane; }
+    }
+    word acc = 0;
+    real asum = 0;
+#pragma unroll
+    for (int j = 0; j < NCT; ++j) acc |= h[j] & sw[j];
+    if (do_ld) {
+#pragma unroll
+        for (int k = 0; k < A; ++k) asum += act_s[lane * A + k];
+    }
+    if (!do_st) {
+        if (acc == 0x12345u && asum == (real)7) p.done[e] = 1;    // keeps the loads alive; never true in practice
+        return;
+    }
+#pragma unroll
+    for (int j = 0; j < NCT; ++j) spot[(size_t)j * sp + so] = sw[j];
+    p.envst[e] = es;
+    p.reward[e] = asum;
+    p.done[e] = (uint8_t)(acc & 1u);
+#pragma unroll
+    for (int k = 0; k < D; ++k) obs_s[lane * D + k] = (float)asum;
+    if (variant == 4) {
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+            bulk_s2g(p.obs + (size_t)e0 * D, obs_s, obs_bytes);
+            bulk_commit();
+            bulk_wait_read<0>();
+        }
+        return;
+    }
+    __syncwarp();
+    const float4 *src = reinterpret_cast<const float4 *>(obs_s);
+    float4 *dst = reinterpret_cast<float4 *>(p.obs + (size_t)e0 * D);
+#pragma unroll
+    for (int j = 0; j < (8 * D + 31) / 32; ++j) {
+        const int k = lane + 32 * j;
+        if (k < 8 * D) dst[k] = src[k];
+    }
 }
 
 // Test hook (sng_debug_arrival_gap): the table-based geometric gap of the step kernels, evaluated on given words with
@@ -794,6 +886,9 @@ public:
             // large stations (64 spots): four (or two) lanes per env over the whole 32-env blocks, the ragged last block one lane
             // per env (a 32-spot station already reaches 85 % of the HBM roofline with one lane per env)
             if (lanes_per_env != 1 && q.n_envs >= kBlock) {
+                // rows of 65 / 137 floats: the observation rows leave through the copy engine as well (measured on C5:
+                // 0.0828 vs 0.0877 ms per step; at 10 spots the two are equal)
+                if (use_bulk == 1 && (bulk & STAGE_ALIGNED)) bulk |= STAGE_TMA_STORE;
                 const long long full = q.n_envs / kBlock * kBlock;
                 const bool four = lanes_per_env != 2 && NCT % 4 == 0;      // default: four lanes per env (a warp covers 8 envs)
                 if (full == q.n_envs)
@@ -1004,6 +1099,33 @@ public:
         ++launches;
         SNG_CUDA(cudaGetLastError());
         return SNG_OK;
+    }
+
+    int traffic_skeleton(int variant, cudaStream_t st) override
+    {
+        int rc = check_ready(true);
+        if (rc) return rc;
+        if constexpr (!EXACT) {
+            const bool fixed = p.pv && p.H == 3 && p.pv_days == 1 && p.batt && !p.has_req && p.N == 10;
+            if (variant < 0 || variant > 4) { error = "sng_debug_traffic_skeleton: variant must be in 0..4"; return SNG_ERR_ARG; }
+            if (!fixed || p.n_envs % kBlock != 0 || !aligned16(p.actions) || !aligned16(p.obs)) {
+                error = "sng_debug_traffic_skeleton: default 10-spot station, whole 32-env blocks, aligned buffers only";
+                return SNG_ERR_UNSUPPORTED;
+            }
+            DeviceGuard guard(device);
+            const int wpb = 2;
+            const size_t smem = 128 + (size_t)wpb * row_bytes(1);
+            auto kern = traffic_skeleton_kernel<real, 10>;
+            rc = ensure_smem((const void *)kern, smem);
+            if (rc) return rc;
+            kern<<<(unsigned)((p.n_envs / kBlock + wpb - 1) / wpb), wpb * 32, smem, st>>>(p, variant);
+            ++launches;
+            SNG_CUDA(cudaGetLastError());
+            return SNG_OK;
+        } else {
+            error = "sng_debug_traffic_skeleton: float32 build only";
+            return SNG_ERR_UNSUPPORTED;
+        }
     }
 
     int error_flags(uint32_t *out, cudaStream_t st) override

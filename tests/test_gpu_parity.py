@@ -273,6 +273,55 @@ def test_sampler_matches_cpu_mirror_bit_exact():
         env.close()
 
 
+def test_traffic_skeleton_leaves_the_state_alone():
+    """sng_debug_traffic_skeleton (bench.py's pattern-ceiling leg: the step kernel's loads and stores without its arithmetic)
+    writes the state back unchanged, and refuses stations it was not written for."""
+    import ctypes as C
+    env = _env(4096, "float32", seed=5, number_of_chargers=10)
+    env.reset()
+    g = torch.Generator(device="cuda:0").manual_seed(2)
+    for _ in range(3):
+        env.step(env.sample_actions(g))
+    spot, envst = env._spot.clone(), env._envst.clone()
+    stream = C.c_void_p(torch.cuda.current_stream(env.device).cuda_stream)
+    for variant in (0, 1, 2, 4):
+        assert env._lib.sng_debug_traffic_skeleton(env._h, variant, stream) == 0
+    torch.cuda.synchronize()
+    assert torch.equal(spot, env._spot) and torch.equal(envst, env._envst)
+    env.close()
+    other = _env(64, "float32", seed=5, number_of_chargers=4)
+    other.reset()
+    assert other._lib.sng_debug_traffic_skeleton(other._h, 0, stream) == -4       # SNG_ERR_UNSUPPORTED (include/sng.h)
+    other.close()
+
+
+@pytest.mark.parametrize("n_spots", [10, 4, 64])
+def test_default_station_kernel_equals_the_replay_kernel(n_spots):
+    """The production kernel of the default station (battery on and no requested-SoC plane known at compile time: sampling
+    mode) and the kernel that replays a schedule (requested-SoC plane read at run time) walk the same day identically: one
+    env samples its episode in the step, the other replays that episode's plan (sample_plan -> load_schedule)."""
+    kw = dict(number_of_chargers=n_spots, time_interval="15min" if n_spots == 64 else "1h")
+    E = 2048 + 32
+    a_env, b_env = _env(E, "float32", seed=31, **kw), _env(E, "float32", seed=31, **kw)
+    o_a = a_env.reset().clone()
+    b_env.reset()
+    o_b = b_env.load_schedule(b_env.sample_plan())
+    o_b = b_env.obs if o_b is None else o_b
+    assert torch.equal(o_a, o_b)
+    g = torch.Generator(device="cuda:0").manual_seed(8)
+    T = a_env.cfg.n_steps
+    for s in range(T):
+        a = a_env.sample_actions(g)
+        ra, rb = a_env.step(a), b_env.step(a)
+        assert torch.equal(ra[1], rb[1]) and torch.equal(ra[2], rb[2]), s
+        if s < T - 1:                      # the last step ends the day: the sampling env draws a new one, the other replays
+            assert torch.equal(ra[0], rb[0]), s
+            assert torch.equal(a_env._spot[:, :, 1], b_env._spot[:, :, 1]), s          # SoC plane
+    assert a_env.error_flags() == 0 and b_env.error_flags() == 0
+    a_env.close()
+    b_env.close()
+
+
 # ------------------------------------------------------------------------------------------
 # structural properties of the CUDA path
 # ------------------------------------------------------------------------------------------
