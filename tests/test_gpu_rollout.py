@@ -320,6 +320,37 @@ def test_fused_policy_step_equals_policy_then_step(E, n_spots):
     assert int(res[0][6].sum()) > 0          # episodes ended inside the rollouts
 
 
+def test_fused_policy_step_with_supplied_noise():
+    """sng_policy_step with caller-supplied noise rows (per io set: its own noise stage and mbarrier) and with zero noise
+    equals sng_policy_forward_packed followed by sng_step, step after step across an auto-reset."""
+    from smart_nanogrid_gym_b200 import BatchedSmartNanogridEnv
+    from smart_nanogrid_gym_b200.rollout import MlpPolicy
+    E = 148 * 128 * 2 + 5 * 128            # CTAs with two and with three tiles
+    torch.manual_seed(8)
+    policy = MlpPolicy(29, 11).to("cuda:0")
+    policy.pack_weights()
+    envs = [BatchedSmartNanogridEnv(E, device="cuda:0", seed=13, **KW) for _ in range(2)]
+    obs = [e.reset().clone() for e in envs]
+    low, high = envs[0].action_low.float(), envs[0].action_high.float()
+    z = lambda *shape, dtype=torch.float32: torch.zeros(*shape, dtype=dtype, device="cuda:0")  # noqa: E731
+    bufs = [dict(raw=z(E, 11), act=z(E, 11), val=z(E), lp=z(E), obs=z(E, 29), rew=z(E), done=z(E, dtype=torch.uint8)) for _ in range(2)]
+    g = torch.Generator(device="cuda:0").manual_seed(3)
+    for s in range(27):
+        noise = torch.randn(E, 11, device="cuda:0", generator=g) if s % 3 else torch.zeros(E, 11, device="cuda:0")
+        a, b = bufs
+        policy.fused_forward(obs[0], noise, low, high, a["raw"], a["act"], a["val"], a["lp"], repack=False)
+        envs[0].step(a["act"], out=(a["obs"], a["rew"], a["done"]))
+        envs[1].policy_step(policy._packed, obs[1], low, high, b["raw"], b["act"], b["val"], b["lp"],
+                            out=(b["obs"], b["rew"], b["done"]), noise=noise)
+        for k in a:
+            assert torch.equal(a[k], b[k]), (s, k)
+        obs = [a["obs"].clone(), b["obs"].clone()]
+    assert torch.equal(envs[0]._spot, envs[1]._spot) and torch.equal(envs[0]._envst, envs[1]._envst)
+    for e in envs:
+        assert e.error_flags() == 0
+        e.close()
+
+
 def test_sharded_rollout_equals_the_unsharded_one():
     """Two env shards collected side by side (ShardedGraphedRollout: parallel graph branches, in-kernel noise keyed by
     global env id) produce bit for bit what one env of the summed size does."""
