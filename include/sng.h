@@ -271,6 +271,10 @@ int sng_debug_arrival_gap(sng_env *env, const uint32_t *x, uint32_t *gap, int64_
  * layout), 2 loads only, 3 stores only (overwrites the state: reset afterwards), 4 observation rows through the copy engine. */
 int sng_debug_traffic_skeleton(sng_env *env, int variant, void *stream);
 
+/* Measurement hook: a one-thread kernel that writes the device's %globaltimer (ns) to *slot.  Capturable in a CUDA graph:
+ * stamps between the kernels of a captured loop give each kernel's span on one clock (scripts/rollout_timeline.py). */
+int sng_debug_stamp(uint64_t *slot, void *stream);
+
 /* Kernels launched by this handle so far (bench.py's gpu_launches claim). */
 int64_t sng_launch_count(const sng_env *env);
 

@@ -22,7 +22,7 @@ DIAG = ("total_ch", "total_dis", "solar", "batt_power", "grid_power", "grid_cost
 EXPORTS = ("sng_abi_version", "sng_sizeof", "sng_last_error", "sng_query_layout", "sng_create", "sng_destroy", "sng_bind",
            "sng_reset", "sng_load_schedule", "sng_step", "sng_rollout", "sng_step_host", "sng_sample_plan",
            "sng_error_flags", "sng_launch_count", "sng_set_tuning", "sng_set_pipeline", "sng_gae", "sng_policy_forward", "sng_null_launch",
-           "sng_policy_packed_bytes", "sng_policy_pack", "sng_policy_forward_packed", "sng_policy_forward_sampled", "sng_debug_arrival_gap", "sng_set_launch_mode", "sng_policy_set_launch_mode", "sng_policy_step", "sng_debug_traffic_skeleton")
+           "sng_policy_packed_bytes", "sng_policy_pack", "sng_policy_forward_packed", "sng_policy_forward_sampled", "sng_debug_arrival_gap", "sng_set_launch_mode", "sng_policy_set_launch_mode", "sng_policy_step", "sng_debug_traffic_skeleton", "sng_debug_stamp")
 
 
 class SngConfig(C.Structure):
@@ -123,6 +123,7 @@ def lib():
                                                   C.c_uint64] + [C.c_void_p] * 7 + [C.c_int64, C.c_void_p])
         L.sng_policy_step.argtypes = ([C.c_void_p] * 4 + [C.c_uint64, C.c_void_p, C.c_uint64] + [C.c_void_p] * 11)
         L.sng_debug_traffic_skeleton.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.sng_debug_stamp.argtypes = [C.c_void_p, C.c_void_p]
         if L.sng_abi_version() != 3:
             raise NativeError("libsng.so ABI version mismatch")
         for which, st in enumerate((SngConfig, SngLayout, SngBuffers, SngScheduleView)):

@@ -43,6 +43,12 @@ __global__ void __launch_bounds__(256) gae_kernel(const float *__restrict__ rewa
 }
 
 static __global__ void null_kernel() {}
+static __global__ void stamp_kernel(unsigned long long *slot)
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    *slot = t;
+}
 
 struct sng_env {
     sng::EngineBase *eng;
@@ -225,6 +231,13 @@ int sng_policy_step(sng_env *env, const void *packed, const float *obs, const fl
     a.low = low; a.high = high; a.raw_actions = raw_actions; a.actions = actions; a.values = values; a.log_probs = log_probs;
     a.noise_out = noise_out; a.obs_next = obs_next; a.reward = (float *)reward; a.done = done_flags;
     return done(env, env->eng->policy_step(a, (cudaStream_t)stream));
+}
+
+int sng_debug_stamp(uint64_t *slot, void *stream)
+{
+    if (!slot) return fail(SNG_ERR_ARG, "sng_debug_stamp: null slot");
+    stamp_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(reinterpret_cast<unsigned long long *>(slot));
+    return cudaGetLastError() == cudaSuccess ? SNG_OK : fail(SNG_ERR_CUDA, "sng_debug_stamp: launch failed");
 }
 
 int sng_debug_traffic_skeleton(sng_env *env, int variant, void *stream)
