@@ -281,8 +281,9 @@ int64_t sng_launch_count(const sng_env *env);
 /* Tuning knobs for experiments and tests: warps (= blocks of 32 envs) per CTA (0 = auto); force the
  * generic runtime-N kernel instead of the specialised one; how action / observation rows are staged
  * through shared memory when the buffers are 16-byte aligned: -1 scalar loads / stores, 0 coalesced
- * 16-byte vector loads / stores, 1 copy-engine (cp.async.bulk) loads + vector stores, 3 copy engine
- * both ways (unaligned buffers and a partial last block always take the scalar path); number of env
+ * 16-byte vector loads / stores, 1 (default) copy-engine (cp.async.bulk) loads + vector stores -- copy
+ * engine both ways for stations of more than 32 spots --, 3 copy engine both ways (unaligned buffers
+ * and a partial last block always take the scalar path); number of env
  * chunks sng_step_host pipelines over PCIe (0 = auto). */
 int sng_set_tuning(sng_env *env, int warps_per_cta, int use_generic_kernel, int use_bulk_copy, int host_chunks);
 /* How sng_step launches its kernel.  0 (default): an ordinary launch.  1: programmatic dependent launch -- the kernel may

@@ -1,7 +1,7 @@
 // sng_device.cuh -- device-side types, the counter-based schedule sampler and the per-environment
 // step body.
 //
-// Thread mapping: ONE THREAD PER ENVIRONMENT, 32 consecutive envs per warp (two lanes per env, 16 envs
+// Thread mapping: ONE THREAD PER ENVIRONMENT, 32 consecutive envs per warp (four lanes per env, 8 envs
 // per warp, for 64-spot stations whose rows would otherwise leave 8 warps per SM).  Per-spot state is a
 // structure of arrays blocked by 32 envs ([E/32][N][3 planes][32]), so lane l of a warp reads plane f
 // of spot i of its env from word  ((block*N + i)*3 + f)*32 + l : every state load / store of a warp is
@@ -399,7 +399,7 @@ template <typename real, int NCT> struct StateRegs {
     word h[Chunk<NCT>::value], r[Chunk<NCT>::value], s[Chunk<NCT>::value];
 };
 
-// L lanes share an env (L = 1, or 2 for large stations): lane `sub` owns the spots sub, sub + L, ...;
+// L lanes share an env (L = 1, or 4 / 2 for large stations): lane `sub` owns the spots sub, sub + L, ...;
 // `spot` points at its first one and its k-th ("virtual") spot is L * kPlanes * kBlock words further.
 template <typename real, int CH, int L>
 __device__ __forceinline__ void load_spots(const typename WordOf<real>::type *spot, int c, bool has_req,
@@ -484,7 +484,7 @@ struct Arrivals {
 
 // L > 1 (specialised float32 kernels of large stations): L lanes of the warp share the env, lane `sub`
 // (= lane / (32 / L)) owns the spots sub, sub + L, ...; `spot` and the RowIO are advanced to its first
-// spot, the partial station sums are combined with a shuffle, every lane computes the env-level phase
+// spot, the partial station sums are combined with shuffles, every lane computes the env-level phase
 // and lane 0 alone writes its results.  All 32 lanes of the warp must be in env_step together then.
 // FIXED: the reference's default station besides the observation shape -- battery on, every vehicle requests SoC 1.0
 // (no requested-SoC plane) -- known at compile time.
