@@ -23,7 +23,7 @@ policy = MlpPolicy(29, 11).to(dev)
 buf = RolloutBuffer(6, env.num_envs, 29, 11, dev)
 obs = env.reset()
 starts = torch.ones(env.num_envs, dtype=torch.uint8, device=dev)
-for kwargs in (dict(rng_seed=3), dict(generator=g), dict(deterministic=True), dict(rng_seed=3, pdl=True)):
+for kwargs in (dict(rng_seed=3), dict(generator=g), dict(deterministic=True), dict(rng_seed=3, pdl=True), dict(rng_seed=3, pdl="policy")):
     obs, starts = collect_rollout(env, policy, buf, obs, starts, **kwargs)
     torch.cuda.synchronize()
     print("rollout ok", kwargs.keys(), flush=True)
@@ -36,3 +36,19 @@ policy.fused_forward(o, None, None, None, None, None, val, None, repack=False)
 policy.fused_forward(o, torch.randn(E, 11, device=dev), low, high, raw, act, val, lp, cuda_cores=True)
 torch.cuda.synchronize()
 print("policy ok", flush=True)
+# fused policy + env step (sng_policy_step): in-kernel noise, supplied noise, programmatic launch; two tiles per CTA at most
+env = BatchedSmartNanogridEnv(128 * 5, device=dev, seed=4, number_of_chargers=10, **KW)
+buf = RolloutBuffer(26, env.num_envs, 29, 11, dev)
+obs = env.reset()
+starts = torch.ones(env.num_envs, dtype=torch.uint8, device=dev)
+for kwargs in (dict(rng_seed=3, fuse_step=True), dict(generator=g, fuse_step=True), dict(rng_seed=3, fuse_step=True, pdl="policy")):
+    obs, starts = collect_rollout(env, policy, buf, obs, starts, **kwargs)
+    torch.cuda.synchronize()
+    print("fused rollout ok", sorted(kwargs.keys()), flush=True)
+assert env.error_flags() == 0
+import ctypes as C
+stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+for variant in (0, 1, 2, 4):
+    assert env._lib.sng_debug_traffic_skeleton(env._h, variant, stream) == 0
+torch.cuda.synchronize()
+print("skeleton ok", flush=True)
