@@ -619,7 +619,7 @@ def pattern_ceiling_leg(ctx, E):
     n = 300
     ms = timed_ms(ctx, lambda: run(n)) / n
     what_if = {}
-    for name, variant in (("two_plane_layout", 1), ("loads_only", 2), ("obs_rows_by_copy_engine", 4), ("stores_only", 3)):
+    for name, variant in (("planes_interleaved_per_spot_r2_layout", 1), ("loads_only", 2), ("obs_rows_by_copy_engine", 4), ("stores_only", 3)):
         run(10, variant)
         what_if[name] = timed_ms(ctx, lambda: run(n, variant)) / n
     traffic = ncu_traffic_bytes("c4", E)

@@ -101,13 +101,14 @@ typedef struct {
 } sng_layout;
 
 /* Device buffers.  `real` = float (SNG_F32) or double (SNG_F64).  Optional pointers may be NULL.
- * The per-spot state `spot` is ONE array of real-sized words, a structure of arrays blocked by
- * env_block = 32 envs: word (env e, spot i, plane f) lives at index
- *     (((e / 32) * n_spots + i) * 3 + f) * 32 + e % 32
+ * The per-spot state `spot` is ONE array of real-sized words, a structure of arrays, plane-major and
+ * blocked by env_block = 32 envs: word (env e, spot i, plane f) lives at index
+ *     f * (ceil(E / 32) * n_spots * 32) + ((e / 32) * n_spots + i) * 32 + e % 32
  * with plane 0 = header word (arrival | departure << 8 | capacity << 16 | next arrival << 24, zero
  * extended), plane 1 = SoC column the next step starts from, plane 2 = requested SoC (not maintained
- * while every vehicle requests 1.0, i.e. sampled schedules without enable_requested_state_of_charge; last,
- * so that the two planes every step reads are adjacent) (both `real` bit patterns).  The caller allocates ceil(E / 32) * n_spots * 3 * 32 words of real_bytes
+ * while every vehicle requests 1.0, i.e. sampled schedules without enable_requested_state_of_charge)
+ * (both `real` bit patterns).  A 32-env block's n_spots lines of one plane are contiguous.  The caller
+ * allocates 3 * ceil(E / 32) * n_spots * 32 words of real_bytes
  * bytes. */
 typedef struct {
     uint32_t struct_size;
@@ -267,8 +268,9 @@ int sng_debug_arrival_gap(sng_env *env, const uint32_t *x, uint32_t *gap, int64_
  * occupancy, loads and stores; default 10-spot station, whole 32-env blocks).  Its duration is what the access pattern
  * alone costs: the practical ceiling bench.py reports under the step kernel beside the copy-bandwidth roofline.  The
  * handle's state is written back unchanged; obs / reward / done receive meaningless values.  variant 0 = the step
- * kernel's own pattern; what-if patterns with the same byte counts: 1 header and SoC planes adjacent (a two-plane block
- * layout), 2 loads only, 3 stores only (overwrites the state: reset afterwards), 4 observation rows through the copy engine. */
+ * kernel's own pattern; what-if patterns with the same byte counts: 1 the state planes interleaved per spot (the layout of
+ * rounds 1-2), 2 loads only, 3 stores only (overwrites the state: reset afterwards), 4 observation rows through the copy
+ * engine, 5 like 1 with two planes per spot. */
 int sng_debug_traffic_skeleton(sng_env *env, int variant, void *stream);
 
 /* Measurement hook: a one-thread kernel that writes the device's %globaltimer (ns) to *slot.  Capturable in a CUDA graph:

@@ -66,12 +66,12 @@ class BatchedSmartNanogridEnv:
         self.reward = z(E, dtype=self.real)
         self.done = z(E, dtype=torch.uint8)
         self.terminal_obs = z(E, D, dtype=torch.float32) if want_terminal_obs else None
-        # per-spot state: one array of real-sized words, a structure of arrays blocked by 32 envs:
-        # [ceil(E/32)][N][3 planes: header | SoC | requested SoC][32] (include/sng.h sng_buffers.spot)
+        # per-spot state: one array of real-sized words, a structure of arrays, plane-major and blocked by 32 envs:
+        # [3 planes: header | SoC | requested SoC][ceil(E/32)][N][32] (include/sng.h sng_buffers.spot)
         B = self.layout.env_block
         self._blocks = (E + B - 1) // B
         self._word = torch.int32 if self.precision == nat.SNG_F32 else torch.int64
-        self._spot = z(self._blocks, N, self.layout.spot_planes, B, dtype=self._word)
+        self._spot = z(self.layout.spot_planes, self._blocks, N, B, dtype=self._word)
         self._envst = z(E * self.layout.envst_bytes, dtype=torch.uint8)
         self._plan = None
         self.err = z(E, dtype=torch.int32)
@@ -145,7 +145,7 @@ class BatchedSmartNanogridEnv:
 
     def _plane(self, f):
         """Plane f of the blocked per-spot state -> a de-blocked [E, N] copy (words)."""
-        return self._spot[:, :, f, :].permute(0, 2, 1).reshape(-1, self.cfg.n_spots)[:self.num_envs].contiguous()
+        return self._spot[f].permute(0, 2, 1).reshape(-1, self.cfg.n_spots)[:self.num_envs].contiguous()
 
     @property
     def soc(self):

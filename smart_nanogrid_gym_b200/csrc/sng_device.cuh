@@ -3,9 +3,11 @@
 //
 // Thread mapping: ONE THREAD PER ENVIRONMENT, 32 consecutive envs per warp (four lanes per env, 8 envs
 // per warp, for 64-spot stations whose rows would otherwise leave 8 warps per SM).  Per-spot state is a
-// structure of arrays blocked by 32 envs ([E/32][N][3 planes][32]), so lane l of a warp reads plane f
-// of spot i of its env from word  ((block*N + i)*3 + f)*32 + l : every state load / store of a warp is
-// one full 128-byte line, and all of a thread's accesses are constant offsets from one base pointer.
+// structure of arrays, plane-major and blocked by 32 envs ([3 planes][E/32][N][32]), so lane l of a warp
+// reads plane f of spot i of its env from word  f*plane + (block*N + i)*32 + l : every state load /
+// store of a warp is one full 128-byte line, a block's N lines of one plane are contiguous (1.25 KB at
+// 10 spots: r3 -- with the planes interleaved per spot the same traffic cost 7 % more DRAM time), and all
+// of a thread's accesses are constant offsets from one base pointer per plane.
 // Spots are walked sequentially inside the thread; the station sums are kept per spot parity and combined
 // in a fixed order, so results do not depend on the kernel variant or on how envs are split over GPUs.
 // DESIGN.md section 3.1 has the measurements behind this choice (a warp-per-env mapping leaves 22 of 32
@@ -86,12 +88,14 @@ template <typename real> struct Params {
     const real *pv_power, *irr_norm, *price, *price_norm;  // [table_len]
     const float *dep_norm;                                 // [kSmemTab]: float(k / 24.0), k < kDepTab | gap thresholds (uint32 bits)
     // caller-owned buffers
+    long long plane;       // words between the planes of `spot` (= ceil(E_bound / 32) * N * 32 of the WHOLE bound array: a
+                           // slice of envs keeps it)
     const real *actions;   // [E][A]
     float *obs;            // [E][D]
     real *reward;          // [E]
     uint8_t *done;         // [E]
     float *tobs;           // [E][D] or null
-    typename WordOf<real>::type *spot;  // [E/32][N][3][32]: header word | requested SoC | SoC column the next step starts from
+    typename WordOf<real>::type *spot;  // [3][E/32][N][32]: header word | SoC column the next step starts from | requested SoC
     EnvSt<real> *envst;    // [E]
     const PlanRec<real> *plan;  // [E][N][kMaxVehicles] or null
     uint32_t *err;
@@ -245,13 +249,13 @@ __device__ __forceinline__ Vehicle<real> fetch_vehicle(const Params<real> &p, in
     return v;
 }
 
-// Install vehicle `v` at the spot whose plane-0 word is *sp (planes are kBlock words apart).
+// Install vehicle `v` at the spot whose plane-0 word is *sp (planes are `plane` words apart).
 template <typename real>
-__device__ __forceinline__ void store_vehicle(typename WordOf<real>::type *sp, const Vehicle<real> &v, bool has_req)
+__device__ __forceinline__ void store_vehicle(typename WordOf<real>::type *sp, size_t plane, const Vehicle<real> &v, bool has_req)
 {
-    sp[PL_HDR * kBlock] = v.hdr;
-    if (has_req) sp[PL_REQ * kBlock] = real_to_word(v.req);
-    sp[PL_SOC * kBlock] = real_to_word(v.soc0);   // the step at `arr` starts from the arrival SoC (charger.py:62-67)
+    sp[PL_HDR * plane] = v.hdr;
+    if (has_req) sp[PL_REQ * plane] = real_to_word(v.req);
+    sp[PL_SOC * plane] = real_to_word(v.soc0);   // the step at `arr` starts from the arrival SoC (charger.py:62-67)
 }
 
 __device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
@@ -378,7 +382,7 @@ __device__ __forceinline__ void begin_episode(const Params<real> &p, int N, long
         if (next == 0u) v = fetch_vehicle<real, SMEM>(p, N, e, i, episode, 0, dep_base);
         // the dense SoC array holds the arrival SoC at slot `arr` (charging_station.py:257-259),
         // so the reset observation shows it for vehicles arriving at t = 0
-        store_vehicle<real>(spot + (size_t)(i / L) * (L * kPlanes * kBlock), v, !FIXED && p.has_req != 0);
+        store_vehicle<real>(spot + (size_t)(i / L) * (L * kBlock), (size_t)p.plane, v, !FIXED && p.has_req != 0);
         const bool present = (v.hdr & 0xFFu) == 0u;
         obs[off_soc + i] = present ? (float)v.soc0 : 0.0f;
         obs[off_dep + i] = present ? dep_lookup<SMEM>(p, dep_base, (int)((v.hdr >> 8) & 0xFFu)) : 0.0f;
@@ -400,18 +404,18 @@ template <typename real, int NCT> struct StateRegs {
 };
 
 // L lanes share an env (L = 1, or 4 / 2 for large stations): lane `sub` owns the spots sub, sub + L, ...;
-// `spot` points at its first one and its k-th ("virtual") spot is L * kPlanes * kBlock words further.
+// `spot` points at its first one and its k-th ("virtual") spot is L * kBlock words further.
 template <typename real, int CH, int L>
-__device__ __forceinline__ void load_spots(const typename WordOf<real>::type *spot, int c, bool has_req,
+__device__ __forceinline__ void load_spots(const typename WordOf<real>::type *spot, size_t plane, int c, bool has_req,
                                            typename WordOf<real>::type (&h)[CH], typename WordOf<real>::type (&r)[CH],
                                            typename WordOf<real>::type (&s)[CH])
 {
 #pragma unroll
     for (int j = 0; j < CH; ++j) {
-        const typename WordOf<real>::type *sp = spot + (size_t)(c + j) * (L * kPlanes * kBlock);
-        h[j] = sp[PL_HDR * kBlock];
-        r[j] = has_req ? sp[PL_REQ * kBlock] : real_to_word((typename std::conditional<sizeof(typename WordOf<real>::type) == 4, float, double>::type)1);
-        s[j] = sp[PL_SOC * kBlock];
+        const typename WordOf<real>::type *sp = spot + (size_t)(c + j) * (L * kBlock);
+        h[j] = sp[PL_HDR * plane];
+        r[j] = has_req ? sp[PL_REQ * plane] : real_to_word((typename std::conditional<sizeof(typename WordOf<real>::type) == 4, float, double>::type)1);
+        s[j] = sp[PL_SOC * plane];
     }
 }
 
@@ -422,7 +426,7 @@ __device__ __forceinline__ void load_state(const Params<real> &p, long long e, c
                                            StateRegs<real, MCT> &st)
 {
     st.es = p.envst[e];
-    load_spots<real, Chunk<MCT>::value, L>(spot, 0, !FIXED && p.has_req != 0, st.h, st.r, st.s);
+    load_spots<real, Chunk<MCT>::value, L>(spot, (size_t)p.plane, 0, !FIXED && p.has_req != 0, st.h, st.r, st.s);
 }
 
 // Discharging an EV (V2X) -- Charger.discharge_vehicle, charger.py:108-140.  Kept out of line: the
@@ -503,7 +507,8 @@ __device__ __forceinline__ Arrivals env_step(const Params<real> &p, long long e,
     const int N = NCT ? NCT : p.N;
     const int M = NCT ? MCT : p.N;                             // spots this lane walks
     constexpr int CH = Chunk<MCT>::value;
-    constexpr int SP = L * kPlanes * kBlock;                   // words between consecutive spots of this lane
+    constexpr int SP = L * kBlock;                             // words between consecutive spots of this lane
+    const size_t plane = (size_t)p.plane;                      // words between the state planes
     const bool lead = (L == 1) || sub == 0;                    // writes the env-level results
     const int off_soc = Offsets<NCT, ND>::soc(p), off_dep = Offsets<NCT, ND>::dep(p);
     EnvSt<real> es = st.es;
@@ -559,7 +564,7 @@ __device__ __forceinline__ Arrivals env_step(const Params<real> &p, long long e,
 #pragma unroll
             for (int j = 0; j < CH; ++j) { wh[j] = st.h[j]; wr[j] = st.r[j]; ws[j] = st.s[j]; }
         } else {
-            load_spots<real, CH, L>(spot, c, has_req, wh, wr, ws);
+            load_spots<real, CH, L>(spot, plane, c, has_req, wh, wr, ws);
         }
 #pragma unroll
         for (int j = 0; j < CH; ++j) {
@@ -630,14 +635,14 @@ __device__ __forceinline__ Arrivals env_step(const Params<real> &p, long long e,
                 }
             }
             word *sp = spot + (size_t)i * SP;
-            sp[PL_SOC * kBlock] = real_to_word(s_new);
+            sp[PL_SOC * plane] = real_to_word(s_new);
             io.put_spot(c, j, (float)s_new,                                    // charging_station.py:114-117
                         present ? dep_lookup<SMEM>(p, dep_base, dep - t) : 0.0f);     // :92-112, "/ 24" env:208
             if ((hd >> 24) == tn_key) {
                 if (NCT) {
                     arrivals |= (decltype(arrivals))1 << i;
                 } else {                                   // generic kernel: admit the arriving vehicle in place
-                    store_vehicle<real>(sp, fetch_vehicle<real, SMEM>(p, N, e, i * L + sub, episode, tn, dep_base), has_req);
+                    store_vehicle<real>(sp, plane, fetch_vehicle<real, SMEM>(p, N, e, i * L + sub, episode, tn, dep_base), has_req);
                 }
             }
         }
@@ -650,7 +655,7 @@ __device__ __forceinline__ Arrivals env_step(const Params<real> &p, long long e,
     }
     if (DEFER && special) {   // cold: find those spots again (their headers are unchanged so far)
         for (int i = 0; i < M; ++i) {
-            const uint32_t hd = (uint32_t)spot[(size_t)i * SP + PL_HDR * kBlock];
+            const uint32_t hd = (uint32_t)spot[(size_t)i * SP + PL_HDR * plane];
             const bool present = (int)(hd & 0xFFu) <= t && t < (int)((hd >> 8) & 0xFFu);
             if (present && !(io.action(i, 0) >= (real)0)) discharging |= (decltype(discharging))1 << i;
         }
@@ -659,8 +664,8 @@ __device__ __forceinline__ Arrivals env_step(const Params<real> &p, long long e,
         const int i = (MCT > 32) ? __ffsll((long long)discharging) - 1 : __ffs((int)discharging) - 1;
         discharging &= discharging - 1;
         word *sp = spot + (size_t)i * SP;
-        const uint32_t hd = (uint32_t)sp[PL_HDR * kBlock];
-        const real s_prev = word_to_real(sp[PL_SOC * kBlock], (real)0);   // the hot loop stored it back unchanged
+        const uint32_t hd = (uint32_t)sp[PL_HDR * plane];
+        const real s_prev = word_to_real(sp[PL_SOC * plane], (real)0);   // the hot loop stored it back unchanged
         const PowerSoc<real> r = discharge_vehicle(io.action(i, 0) * p.ev_pmax * p.ev_eff, p.dt, s_prev, (real)((hd >> 16) & 0xFFu));
 #pragma unroll
         for (int k = 0; k < NLC; ++k) {                   // DEFER implies NCT > 0: the class is i % NLC
@@ -669,7 +674,7 @@ __device__ __forceinline__ Arrivals env_step(const Params<real> &p, long long e,
                 if (r.P > 0) pos_l[k] += r.P;
             }
         }
-        sp[PL_SOC * kBlock] = real_to_word(r.soc);
+        sp[PL_SOC * plane] = real_to_word(r.soc);
         io.fix_soc(i, (float)r.soc);
         if (p.spot_power) p.spot_power[(size_t)e * N + (i * L + sub)] = r.P;
     }
@@ -764,7 +769,7 @@ __device__ __forceinline__ Arrivals env_step(const Params<real> &p, long long e,
         // diagnostics only (cold): the power of the charging / idle spots is a function of the action and of the
         // header, which is unchanged until the arrivals are admitted below; discharging spots were written above
         for (int i = 0; i < M; ++i) {
-            const uint32_t hd = (uint32_t)spot[(size_t)i * SP + PL_HDR * kBlock];
+            const uint32_t hd = (uint32_t)spot[(size_t)i * SP + PL_HDR * plane];
             const real a = io.action(i, 0);
             const bool present = (int)(hd & 0xFFu) <= t && t < (int)((hd >> 8) & 0xFFu);
             if (!present || a >= (real)0)
@@ -791,7 +796,7 @@ __device__ __forceinline__ Arrivals env_step(const Params<real> &p, long long e,
         while (!COOP && arrivals) {
             const int i = (MCT > 32) ? __ffsll((long long)arrivals) - 1 : __ffs((int)arrivals) - 1;
             arrivals &= arrivals - 1;
-            store_vehicle<real>(spot + (size_t)i * SP, fetch_vehicle<real, SMEM>(p, N, e, i * L + sub, episode, tn, dep_base), has_req);
+            store_vehicle<real>(spot + (size_t)i * SP, plane, fetch_vehicle<real, SMEM>(p, N, e, i * L + sub, episode, tn, dep_base), has_req);
         }
         es.t_ep = (episode << 8) | (uint32_t)tn;
     } else {
@@ -835,7 +840,7 @@ __device__ __forceinline__ Arrivals env_step(const Params<real> &p, long long e,
 // arrivals of the whole 32-env block are compacted into a shared-memory queue (prefix sum over the
 // lanes) and dealt out 32 at a time: ceil(total / 32) rounds (~1.9).  Any lane can admit any (env, spot)
 // of the block: the vehicle is a pure function of (seed, global env, spot, episode, step) and its state
-// words live at block_spot[(spot * 3 + plane) * 32 + env_lane].
+// words live at block_spot[plane * p.plane + spot * 32 + env_lane].
 // All 32 lanes must call this (lanes without a valid env pass mask = 0); queue holds 32 * N entries.
 template <typename real, int NCT, bool FIXED = false>
 __device__ __forceinline__ void admit_arrivals_warp(const Params<real> &p, long long e0, int lane,
@@ -864,7 +869,7 @@ __device__ __forceinline__ void admit_arrivals_warp(const Params<real> &p, long 
         const uint32_t episode = __shfl_sync(FULL, a.episode, src);
         const int tn = __shfl_sync(FULL, a.tn, src);
         if (mine)
-            store_vehicle<real>(block_spot + (size_t)i * (kPlanes * kBlock) + src,
+            store_vehicle<real>(block_spot + (size_t)i * kBlock + src, (size_t)p.plane,
                                 fetch_vehicle<real, true>(p, NCT, e0 + src, i, episode, tn, tab_base), !FIXED && p.has_req != 0);
     }
     __syncwarp();                                 // the queue may be refilled by the next step

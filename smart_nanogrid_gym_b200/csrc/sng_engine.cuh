@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(SNG_PIPE_THREADS, SNG_PIPE_MINB)
         fence_mbar_init();
     }
     __syncwarp();
-    const size_t blk_words = (size_t)N * (kPlanes * kBlock);
+    const size_t blk_words = (size_t)N * kBlock;
     StateRegs<real, NCT> cur, nxt;
     load_state<real, NCT>(p, blk * kBlock + lane, p.spot + (size_t)blk * blk_words + lane, cur);
     if (lane == 0) {
@@ -257,8 +257,8 @@ __global__ void __launch_bounds__(SNG_STEP_MAXT, (EXACT || NCT / L > 32) ? 2 : (
     const int el = lane % EPW, sub = lane / EPW;                 // env within the warp's group, lane within the env
     const bool valid = el < n_valid;
     const int e = e0 + el;
-    // (this env, the lane's first spot, plane 0) in the 32-env blocked state array
-    word *spot = p.spot + (size_t)(e / kBlock) * (size_t)(N * kPlanes * kBlock) + (e % kBlock) + sub * (kPlanes * kBlock);
+    // (this env, the lane's first spot, plane 0) in the plane-major, 32-env blocked state array
+    word *spot = p.spot + (size_t)(e / kBlock) * (size_t)(N * kBlock) + (e % kBlock) + sub * kBlock;
     // float4 per lane of a group's action rows held in registers by the vector path (specialised kernels)
     constexpr int AV = (NCT && sizeof(real) == 4) ? ((NCT + 1) * EPW / 4 + 31) / 32 : 1;
     const int act_vec = (int)(act_bytes / 16);                    // float4 per block of action rows
@@ -386,9 +386,10 @@ __global__ void __launch_bounds__(SNG_STEP_MAXT, (EXACT || NCT / L > 32) ? 2 : (
 // access pattern alone costs on this machine: the practical ceiling under the step kernel, next to the copy-bandwidth
 // roofline.  State is written back unchanged (variant 3 overwrites it: reset the handle afterwards); obs / reward / done
 // receive meaningless values.  Default station, whole 32-env blocks only.
-// `variant` (what-if patterns, same byte counts): 0 the step kernel's own; 1 header and SoC planes adjacent (a two-plane
-// block layout: 2.5 KB contiguous per block instead of two lines out of every three); 2 loads only; 3 stores only;
-// 4 observation rows through the copy engine.
+// `variant` (what-if patterns, same byte counts): 0 the step kernel's own (plane-major state: a block's ten header lines
+// and its ten SoC lines are each 1.25 KB contiguous); 1 the state planes interleaved per spot ([block][spot][3][32]: the
+// layout of rounds 1-2, two lines read out of every three); 2 loads only; 3 stores only; 4 observation rows through the
+// copy engine; 5 like 1 with two planes per spot.
 template <typename real, int NCT>
 __global__ void __launch_bounds__(SNG_STEP_MAXT, SNG_STEP_MINB) traffic_skeleton_kernel(const Params<real> p, int variant)
 {
@@ -406,8 +407,15 @@ __global__ void __launch_bounds__(SNG_STEP_MAXT, SNG_STEP_MINB) traffic_skeleton
     float *obs_s = reinterpret_cast<float *>(wbase + align128(act_bytes));
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem) + warp;
     const int e = e0 + lane;
-    word *spot = p.spot + (size_t)blk * (size_t)(NCT * kPlanes * kBlock) + lane;
-    const int sp = variant == 1 ? 2 * kBlock : kPlanes * kBlock, so = variant == 1 ? kBlock : PL_SOC * kBlock;   // spot stride, SoC plane
+    word *spot = p.spot + (size_t)blk * (size_t)(NCT * kBlock) + lane;
+    int sp = kBlock;                                                               // words between a block's spots
+    size_t so = PL_SOC * (size_t)p.plane;                                          // from a spot's header word to its SoC word
+    if (variant == 1 || variant == 5) {                                            // planes interleaved per spot: [block][spot][plane][32]
+        const int np = variant == 1 ? kPlanes : 2;
+        spot = p.spot + (size_t)blk * (size_t)(NCT * np * kBlock) + lane;
+        sp = np * kBlock;
+        so = kBlock;
+    }
     const bool do_ld = variant != 3, do_st = variant != 2;
     word h[NCT], sw[NCT];
     EnvSt<real> es;
@@ -415,7 +423,7 @@ __global__ void __launch_bounds__(SNG_STEP_MAXT, SNG_STEP_MINB) traffic_skeleton
     if (do_ld) {
 #pragma unroll
         for (int j = 0; j < NCT; ++j) {
-            h[j] = spot[(size_t)j * sp + PL_HDR * kBlock];
+            h[j] = spot[(size_t)j * sp];
             sw[j] = spot[(size_t)j * sp + so];
         }
         es = p.envst[e];
@@ -499,7 +507,7 @@ __global__ void __launch_bounds__(256) reset_kernel(const Params<real> p, const 
     }
     if (init || reset_battery) soc_b = p.batt ? p.b_soc0 : (real)0;
     if (p.mode == MODE_SAMPLE) shift = sample_pv_shift(p, p.N, p.gid0 + (unsigned long long)e, episode);
-    typename WordOf<real>::type *spot = p.spot + (size_t)(e / kBlock) * p.N * (kPlanes * kBlock) + (size_t)(e % kBlock);
+    typename WordOf<real>::type *spot = p.spot + (size_t)(e / kBlock) * p.N * kBlock + (size_t)(e % kBlock);
     begin_episode<real, 0, 0, false>(p, p.N, e, spot, episode, shift, soc_b, p.obs + (size_t)e * p.D);
     es.soc_b = soc_b;
     es.pv_shift = shift;
@@ -599,6 +607,7 @@ public:
         }
         memset(&p, 0, sizeof(p));
         p.n_envs = c.n_envs;
+        p.plane = (c.n_envs + kBlock - 1) / kBlock * (long long)c.n_spots * kBlock;
         p.gid0 = (unsigned long long)c.env_gid0;
         p.N = c.n_spots; p.T = c.n_steps; p.H = c.horizon;
         p.pv = c.pv != 0; p.batt = c.batt != 0; p.v2x = c.v2x != 0;
@@ -985,7 +994,7 @@ public:
         q.gid0 = src.gid0 + (unsigned long long)e0;
         q.actions += (size_t)e0 * src.A; q.obs += (size_t)e0 * src.D; q.reward += e0; q.done += e0;
         if (q.tobs) q.tobs += (size_t)e0 * src.D;
-        q.spot += (size_t)e0 * src.N * kPlanes; q.envst += e0;
+        q.spot += (size_t)e0 * src.N; q.envst += e0;        // plane-major: the slice starts e0 / 32 blocks into every plane
         if (q.plan) q.plan += (size_t)e0 * src.N * kMaxVehicles;
         if (q.err) q.err += e0;
         if (q.diag) q.diag += (size_t)e0 * D_COUNT;
@@ -1107,7 +1116,7 @@ public:
         if (rc) return rc;
         if constexpr (!EXACT) {
             const bool fixed = p.pv && p.H == 3 && p.pv_days == 1 && p.batt && !p.has_req && p.N == 10;
-            if (variant < 0 || variant > 4) { error = "sng_debug_traffic_skeleton: variant must be in 0..4"; return SNG_ERR_ARG; }
+            if (variant < 0 || variant > 5) { error = "sng_debug_traffic_skeleton: variant must be in 0..5"; return SNG_ERR_ARG; }
             if (!fixed || p.n_envs % kBlock != 0 || !aligned16(p.actions) || !aligned16(p.obs)) {
                 error = "sng_debug_traffic_skeleton: default 10-spot station, whole 32-env blocks, aligned buffers only";
                 return SNG_ERR_UNSUPPORTED;

@@ -718,7 +718,7 @@ __global__ void __launch_bounds__(ALL_THREADS + (IO_SETS - 1) * IO_THREADS, 1)
                 //      rows are in act_s, the next observation is assembled in oout_s and leaves as one coalesced slab ----
                 typedef WordOf<float>::type word;
                 const long long e = e0 + t;
-                word *spot = envp.spot + (size_t)(e / kBlock) * (size_t)(NCT * kPlanes * kBlock) + (size_t)(e % kBlock);
+                word *spot = envp.spot + (size_t)(e / kBlock) * (size_t)(NCT * kBlock) + (size_t)(e % kBlock);
                 StateRegs<float, NCT> st;
                 load_state<float, NCT, 1, true>(envp, e, spot, st);
                 const RowIO<float, 1> rio = {act_s + t * A, act_s + t * A, oout_s + t * D, 8, 8 + NCT};

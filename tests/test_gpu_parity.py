@@ -316,7 +316,7 @@ def test_default_station_kernel_equals_the_replay_kernel(n_spots):
         assert torch.equal(ra[1], rb[1]) and torch.equal(ra[2], rb[2]), s
         if s < T - 1:                      # the last step ends the day: the sampling env draws a new one, the other replays
             assert torch.equal(ra[0], rb[0]), s
-            assert torch.equal(a_env._spot[:, :, 1], b_env._spot[:, :, 1]), s          # SoC plane
+            assert torch.equal(a_env._spot[1], b_env._spot[1]), s          # SoC plane
     assert a_env.error_flags() == 0 and b_env.error_flags() == 0
     a_env.close()
     b_env.close()
