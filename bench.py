@@ -817,7 +817,7 @@ def main():
     ap.add_argument("--generic", action="store_true", help="tuning: use the generic runtime-N kernel")
     ap.add_argument("--bulk", type=int, default=1, help="tuning: row staging: -1 scalar, 0 vector loads/stores, 1 copy-engine loads + vector stores, 3 copy engine both ways")
     ap.add_argument("--host-chunks", type=int, default=0, help="tuning: env chunks of the pipelined host path")
-    ap.add_argument("--variant", type=int, default=0, help="tuning: 0 default, 1 persistent pipelined kernel, 2 one lane per env even for large stations, 3 two lanes per env")
+    ap.add_argument("--variant", type=int, default=0, help="tuning: 0 default, 1 persistent pipelined kernel, 2 one lane per env even for large stations, 3 two lanes per env, 4 one lane per SPOT at every batch size, 5 never one lane per spot")
     ap.add_argument("--ctas", type=int, default=0, help="tuning: cap on resident CTAs per SM (pipelined kernel)")
     ap.add_argument("--pdl", type=int, default=-1, help="step-kernel launch mode: 0 ordinary, 1 programmatic dependent launch; -1 = auto "
                     "(1 for small batches, where kernel-to-kernel latency is a visible share of a step)")
@@ -930,6 +930,8 @@ def main():
                     legs[name]["what"] = "BASELINE config 2: 4,096 envs per GPU, one sng_step launch per step"
                     legs["c2_rollout_kernel"] = rollout_kernel_leg(ctx, "c4", 4096, floor_us, min_ms=100.0)
                     legs["c2_rollout_kernel"]["what"] = "BASELINE config 2 through sng_rollout (24 steps per launch)"
+                    for k in (name, "c2_rollout_kernel"):
+                        legs[k]["kernel"] = "step_lanes_kernel: one lane per charging spot, two envs per warp (the default for small batches; bit-identical to the one-block-per-warp kernel)"
                 elif name == "generic":
                     for wl in ("c4_h5", "c4_pv2d", "c4_nopv"):
                         legs["generic_" + wl] = step_leg(ctx, wl, WORKLOADS[wl]["envs"], ctx.rank * WORKLOADS[wl]["envs"], floor_us, min_ms=120.0)

@@ -133,8 +133,9 @@ class BatchedSmartNanogridEnv:
         nat.check(self._lib.sng_set_tuning(self._h, warps_per_cta, use_generic_kernel, use_bulk_copy, host_chunks))
 
     def set_pipeline(self, kernel_variant=0, ctas_per_sm=0):
-        """0 default (four lanes per env for stations of more than 32 spots), 1 persistent pipelined kernel, 2 always
-        one lane per env, 3 two lanes per env for large stations (include/sng.h)."""
+        """0 default (four lanes per env for stations of more than 32 spots; one lane per SPOT for batches of at most 16,384
+        envs of the default station shapes), 1 persistent pipelined kernel, 2 always one lane per env, 3 two lanes per env for
+        large stations, 4 one lane per spot at every batch size, 5 like 0 but never one lane per spot (include/sng.h)."""
         nat.check(self._lib.sng_set_pipeline(self._h, kernel_variant, ctas_per_sm))
 
     def set_launch_mode(self, mode=0):

@@ -379,6 +379,10 @@ __global__ void __launch_bounds__(SNG_STEP_MAXT, (EXACT || NCT / L > 32) ? 2 : (
     if (tma_store && lane == 0) bulk_wait_read<0>();   // shared memory must stay valid until the store has read it
 }
 
+}  // namespace sng
+#include "sng_lanes.cuh"   // step_lanes_kernel: one lane per charging spot, for latency-bound batches
+namespace sng {
+
 // Measurement hook (sng_debug_traffic_skeleton): the step kernel's memory traffic WITHOUT its arithmetic -- same launch
 // geometry, shared-memory footprint and register cap (so the same 32 resident warps per SM), the same loads (per-spot
 // header and SoC words, env scalars, the block's action rows through the copy engine) and the same stores (SoC words,
@@ -569,6 +573,12 @@ public:
     int use_generic = 0, use_bulk = 1, host_chunks = 0, ctas_per_sm = 0;
     int launch_mode = 0;      // 0 ordinary launches, 1 programmatic dependent launch, 2 the same with the state loads ahead of the wait
     int kernel_variant = 0;   // 0 / 2 one block per warp, 1 persistent pipelined
+    int lanes_kernel = 0;     // the one-lane-per-spot kernel (sng_lanes.cuh): 0 auto (small batches, below), 1 whenever
+                              // the station has an instantiation, -1 never
+    // measured on a B200 (scripts/lanes_sweep.py, us per step, this kernel vs one block per warp): per-step launches
+    // 4,096 envs 3.1 vs 3.6, 8,192 envs 4.2 vs 3.7; 24 steps per launch 4,096 envs 1.45 vs 3.34, 8,192 envs 2.5 vs 3.4,
+    // 16,384 envs 4.6 vs 3.6
+    static constexpr long long kLanesMaxEnvsStep = 4096, kLanesMaxEnvsRollout = 8192;
     int lanes_per_env = 0;    // 0 auto (4 for specialised stations of more than 32 spots), 1 / 2: that many lanes per env
     int num_sms = 148;
     size_t smem_optin = 0;
@@ -850,6 +860,34 @@ public:
         return SNG_OK;
     }
 
+    // One lane per charging spot, two envs per warp (sng_lanes.cuh): float32, the reference's default station shape.
+    template <int NCT>
+    int launch_lanes(const Params<real> &q, const real *actions, float *obs, real *reward, uint8_t *done, int n_steps, cudaStream_t st)
+    {
+        if constexpr (!EXACT && NCT <= kLaneGroup) {
+            auto kern = n_steps > 1 ? step_lanes_kernel<NCT, true> : step_lanes_kernel<NCT, false>;
+            constexpr int wpb = 4;
+            const long long warps = (q.n_envs + 1) / 2;
+            const unsigned grid = (unsigned)((warps + wpb - 1) / wpb);
+            if (launch_mode > 0 && n_steps == 1) {
+                cudaLaunchConfig_t lc = {};
+                lc.gridDim = dim3(grid); lc.blockDim = dim3(wpb * 32); lc.dynamicSmemBytes = 0; lc.stream = st;
+                cudaLaunchAttribute at[1];
+                at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+                at[0].val.programmaticStreamSerializationAllowed = 1;
+                lc.attrs = at; lc.numAttrs = 1;
+                SNG_CUDA(cudaLaunchKernelEx(&lc, kern, q, actions, obs, reward, done, n_steps));
+            } else {
+                kern<<<grid, wpb * 32, 0, st>>>(q, actions, obs, reward, done, n_steps);
+            }
+            ++launches;
+            SNG_CUDA(cudaGetLastError());
+            return SNG_OK;
+        } else {
+            return SNG_ERR_UNSUPPORTED;
+        }
+    }
+
     // Persistent pipelined kernel over the full 32-env blocks of q; returns SNG_ERR_UNSUPPORTED (without
     // launching) when a warp's stages do not fit in shared memory.
     template <int NCT, int ND> int launch_pipelined(const Params<real> &q, long long n_blocks, cudaStream_t st)
@@ -934,6 +972,15 @@ public:
             // different layout -- eight prices)
             if (!use_generic && q.pv && q.H == 3 && q.pv_days == 1 && q.batt && !q.has_req) {
                 // ... and the rest of the reference's default station (battery, no requested-SoC plane) at compile time too
+                // latency-bound batches: one lane per spot (bit-identical; 4,096 envs are 128 warps of the kernel below)
+                if (kernel_variant == 0 && (lanes_kernel > 0 || (lanes_kernel == 0 && q.n_envs <= (n_steps > 1 ? kLanesMaxEnvsRollout : kLanesMaxEnvsStep)))) {
+                    switch (q.N) {
+                    case 4: return launch_lanes<4>(q, actions, obs, reward, done, n_steps, st);
+                    case 8: return launch_lanes<8>(q, actions, obs, reward, done, n_steps, st);
+                    case 10: return launch_lanes<10>(q, actions, obs, reward, done, n_steps, st);
+                    default: break;
+                    }
+                }
                 switch (q.N) {
                 case 4: return launch_step_n<4, 8, true>(q, actions, obs, reward, done, n_steps, bulk, st);
                 case 8: return launch_step_n<8, 8, true>(q, actions, obs, reward, done, n_steps, bulk, st);
@@ -1196,9 +1243,10 @@ public:
 
     int set_pipeline(int up, int cps) override
     {
-        if (cps < 0 || up < 0 || up > 3) { error = "sng_set_pipeline: bad arguments"; return SNG_ERR_ARG; }
+        if (cps < 0 || up < 0 || up > 5) { error = "sng_set_pipeline: bad arguments"; return SNG_ERR_ARG; }
         kernel_variant = up >= 2 ? 0 : up;
         lanes_per_env = up == 2 ? 1 : (up == 3 ? 2 : 0);
+        lanes_kernel = up == 4 ? 1 : (up == 0 ? 0 : -1);      // 2, 3, 5: the one-block-per-warp kernel at every batch size
         ctas_per_sm = cps;
         return SNG_OK;
     }

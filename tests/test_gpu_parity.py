@@ -344,7 +344,10 @@ def test_kernel_variants_are_bit_identical(kw):
                 (dict(use_bulk_copy=-1), dict()), (dict(use_bulk_copy=3), dict()), (dict(use_bulk_copy=1, use_generic_kernel=1), dict()),
                 (dict(warps_per_cta=1), dict(kernel_variant=1, ctas_per_sm=1)), (dict(), dict(kernel_variant=1)),
                 (dict(warps_per_cta=4, use_generic_kernel=1), dict(kernel_variant=1)), (dict(), dict(kernel_variant=2)),
-                (dict(), dict(kernel_variant=3))]      # 2: one lane per env, 3: two lanes per env (default for 64 spots: four)
+                (dict(), dict(kernel_variant=3)),      # 2: one lane per env, 3: two lanes per env (default for 64 spots: four)
+                # 4: one lane per SPOT (sng_lanes.cuh; the default station shapes up to 16 spots -- which the default
+                # settings pick at this batch size -- else the default kernel), 5: never that kernel
+                (dict(), dict(kernel_variant=4)), (dict(), dict(kernel_variant=5)), (dict(warps_per_cta=4, use_bulk_copy=0), dict(kernel_variant=5))]
     envs = []
     for tune, pipe in variants:
         env = _env(E, "float32", seed=21, **kw)
@@ -366,13 +369,15 @@ def test_kernel_variants_are_bit_identical(kw):
         e.close()
 
 
-def test_rollout_equals_repeated_step_and_step_host():
+@pytest.mark.parametrize("lanes_rollout", [4, 5])
+def test_rollout_equals_repeated_step_and_step_host(lanes_rollout):
     E, n = 2777, 30
     env_a = _env(E, "float32", number_of_chargers=10, seed=11)
     env_b = _env(E, "float32", number_of_chargers=10, seed=11)
     env_c = _env(E, "float32", number_of_chargers=10, seed=11)
     env_c.set_tuning(host_chunks=3)    # pipelined host path: chunks of envs, ragged last chunk
-    for e in (env_a, env_b, env_c):
+    env_a.set_pipeline(lanes_rollout)  # the rollout on the one-lane-per-spot kernel (state in registers between the steps) / on
+    for e in (env_a, env_b, env_c):    # the one-block-per-warp kernel; the single steps on whatever the defaults pick
         e.reset()
     g = torch.Generator(device="cuda:0").manual_seed(1)
     actions = torch.stack([env_a.sample_actions(g) for _ in range(n)])
@@ -386,6 +391,7 @@ def test_rollout_equals_repeated_step_and_step_host():
         env_c.step_host(ah, oh, rh, dh)
         assert torch.equal(oh, o.cpu()) and torch.equal(rh, r.cpu()) and torch.equal(dh, d.cpu())
     assert done_r[23].all() and done_r.sum().item() == E
+    assert torch.equal(env_a._spot, env_b._spot) and torch.equal(env_a._envst, env_b._envst)
     for e in (env_a, env_b, env_c):
         e.close()
 
