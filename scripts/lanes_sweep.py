@@ -29,6 +29,7 @@ def main():
     ap.add_argument("--sizes", default="1024,4096,8192,16384,32768,65536,131072")
     ap.add_argument("--spots", type=int, default=10)
     ap.add_argument("--steps", type=int, default=24)
+    ap.add_argument("--warps", type=int, default=0, help="warps per CTA (0 = default)")
     args = ap.parse_args()
     dev = "cuda:0"
     out = {}
@@ -38,6 +39,7 @@ def main():
             env = BatchedSmartNanogridEnv(E, device=dev, seed=0, precision="float32", auto_reset=True, number_of_chargers=args.spots,
                                           charging_mode="bounded", vehicle_uncharged_penalty_mode="sparse", time_interval="1h")
             env.set_pipeline(variant)
+            env.set_tuning(warps_per_cta=args.warps)
             env.reset()
             g = torch.Generator(device=dev).manual_seed(5)
             acts = torch.stack([env.sample_actions(g) for _ in range(args.steps)]).contiguous()

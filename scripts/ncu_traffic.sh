@@ -11,10 +11,10 @@ for spec in "c4 1048576" "c4 524288" "c4 262144" "c4 131072" "c4 65536" "c4 4096
   set -- $spec
   cmd="python bench.py --workload $1 --envs $2 --steps 40 --warmup 24 --graph-steps 0 --no-cpu --e2e-steps 1 --legs none"
   $cmd > $out/traffic_plain_$1_$2.log 2>&1 &&
-  ncu --metrics $M --clock-control none -k regex:step_simple -s 30 -c 5 --csv --log-file $out/traffic_$1_$2.csv $cmd > $out/traffic_ncu_$1_$2.log 2>&1
+  ncu --metrics $M --clock-control none -k "regex:step_(simple|lanes)" -s 30 -c 5 --csv --log-file $out/traffic_$1_$2.csv $cmd > $out/traffic_ncu_$1_$2.log 2>&1
   echo "$1 $2 rc=$?"
 done
 # launch list of the default bench command (per-launch times are cold-cache and serialised: shares, not absolutes)
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $out/r3_launches.csv \
-    python bench.py --steps 48 --warmup 24 --no-cpu --e2e-steps 2 --graph-steps 0 --legs c5,c3 > $out/r3_ncu_launches.log 2>&1
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file $out/${TAG:-r4}_launches.csv \
+    python bench.py --steps 48 --warmup 24 --no-cpu --e2e-steps 2 --graph-steps 0 --legs c2,c5,c3 > $out/${TAG:-r4}_ncu_launches.log 2>&1
 echo "launch list rc=$?"

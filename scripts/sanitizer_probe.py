@@ -6,10 +6,14 @@ from smart_nanogrid_gym_b200.rollout import MlpPolicy, RolloutBuffer, collect_ro
 dev = "cuda:0"
 KW = dict(charging_mode="bounded", vehicle_uncharged_penalty_mode="sparse", time_interval="1h")
 g = torch.Generator(device=dev).manual_seed(0)
-for kw, E in ((dict(number_of_chargers=10), 333), (dict(number_of_chargers=10, hours_ahead=5), 97),
-              (dict(number_of_chargers=64, time_interval="15min"), 96), (dict(number_of_chargers=7, vehicle_to_everything=True), 65)):
+# (small batches of the default station shapes run the one-lane-per-spot kernel; variant 5 keeps them on the block kernel)
+for kw, E, variant in ((dict(number_of_chargers=10), 333, 0), (dict(number_of_chargers=10), 333, 5),
+                       (dict(number_of_chargers=4, vehicle_to_everything=True, vehicle_uncharged_penalty_mode="dense"), 77, 4),
+                       (dict(number_of_chargers=10, hours_ahead=5), 97, 0),
+                       (dict(number_of_chargers=64, time_interval="15min"), 96, 0), (dict(number_of_chargers=7, vehicle_to_everything=True), 65, 0)):
     k = dict(KW); k.update(kw)
     env = BatchedSmartNanogridEnv(E, device=dev, seed=1, want_terminal_obs=True, want_diagnostics=True, **k)
+    env.set_pipeline(variant)
     env.reset()
     for s in range(env.cfg.n_steps + 3):
         env.step(env.sample_actions(g))
@@ -17,7 +21,7 @@ for kw, E in ((dict(number_of_chargers=10), 333), (dict(number_of_chargers=10, h
     env.rollout(acts)
     assert env.error_flags() == 0
     env.close()
-    print("step ok", kw, flush=True)
+    print("step ok", kw, "variant", variant, flush=True)
 env = BatchedSmartNanogridEnv(640 + 17, device=dev, seed=2, number_of_chargers=10, **KW)
 policy = MlpPolicy(29, 11).to(dev)
 buf = RolloutBuffer(6, env.num_envs, 29, 11, dev)

@@ -866,7 +866,7 @@ public:
     {
         if constexpr (!EXACT && NCT <= kLaneGroup) {
             auto kern = n_steps > 1 ? step_lanes_kernel<NCT, true> : step_lanes_kernel<NCT, false>;
-            constexpr int wpb = 4;
+            const int wpb = (warps_per_cta > 0 && warps_per_cta < 4) ? warps_per_cta : 4;
             const long long warps = (q.n_envs + 1) / 2;
             const unsigned grid = (unsigned)((warps + wpb - 1) / wpb);
             if (launch_mode > 0 && n_steps == 1) {
