@@ -30,12 +30,13 @@ def main():
     ap.add_argument("--spots", type=int, default=10)
     ap.add_argument("--steps", type=int, default=24)
     ap.add_argument("--warps", type=int, default=0, help="warps per CTA (0 = default)")
+    ap.add_argument("--two", action="store_true", help="also the block kernel with two lanes per env (set_pipeline 3)")
     args = ap.parse_args()
     dev = "cuda:0"
     out = {}
     for E in [int(x) for x in args.sizes.split(",")]:
         row = {}
-        for name, variant in (("block_per_warp", 5), ("lane_per_spot", 4)):
+        for name, variant in (("block_per_warp", 5), ("lane_per_spot", 4), ("two_lanes_per_env", 3))[:3 if args.two else 2]:
             env = BatchedSmartNanogridEnv(E, device=dev, seed=0, precision="float32", auto_reset=True, number_of_chargers=args.spots,
                                           charging_mode="bounded", vehicle_uncharged_penalty_mode="sparse", time_interval="1h")
             env.set_pipeline(variant)

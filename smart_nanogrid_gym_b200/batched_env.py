@@ -133,9 +133,10 @@ class BatchedSmartNanogridEnv:
         nat.check(self._lib.sng_set_tuning(self._h, warps_per_cta, use_generic_kernel, use_bulk_copy, host_chunks))
 
     def set_pipeline(self, kernel_variant=0, ctas_per_sm=0):
-        """0 default (four lanes per env for stations of more than 32 spots; one lane per SPOT for batches of at most 16,384
-        envs of the default station shapes), 1 persistent pipelined kernel, 2 always one lane per env, 3 two lanes per env for
-        large stations, 4 one lane per spot at every batch size, 5 like 0 but never one lane per spot (include/sng.h)."""
+        """0 default (four lanes per env for stations of more than 32 spots; for the default station shapes one lane per SPOT
+        for small batches and two lanes per env for 10-spot batches of up to 16,384 / 65,536 envs per step / rollout launch),
+        1 persistent pipelined kernel, 2 always one lane per env, 3 two lanes per env (64 and 10 spots), 4 one lane per spot at
+        every batch size, 5 like 0 without the two small-batch forms (include/sng.h)."""
         nat.check(self._lib.sng_set_pipeline(self._h, kernel_variant, ctas_per_sm))
 
     def set_launch_mode(self, mode=0):

@@ -221,7 +221,7 @@ enum : int {
 // FIXED: battery on and no requested-SoC plane, known at compile time (the reference's default station): the row widths
 // A and D and every shared-memory offset are then constants.
 template <typename real, int NCT, int ND, bool EXACT, bool MULTI, int L, bool FIXED>
-__global__ void __launch_bounds__(SNG_STEP_MAXT, (EXACT || NCT / L > 32) ? 2 : (NCT / L > 16 ? 4 : (L > 1 ? SNG_STEP_MINB_LANES : SNG_STEP_MINB)))   // large rows: shared memory bounds occupancy, not registers
+__global__ void __launch_bounds__(SNG_STEP_MAXT, (EXACT || NCT / L > 32) ? 2 : (NCT / L > 16 ? 4 : ((L > 1 && NCT > 16) ? SNG_STEP_MINB_LANES : SNG_STEP_MINB)))   // large rows: shared memory bounds occupancy, not registers
     step_simple_kernel(const Params<real> p, const real *actions, float *obs_out, real *reward, uint8_t *done, int n_steps,
                        int mode)
 {
@@ -576,9 +576,10 @@ public:
     int lanes_kernel = 0;     // the one-lane-per-spot kernel (sng_lanes.cuh): 0 auto (small batches, below), 1 whenever
                               // the station has an instantiation, -1 never
     // measured on a B200 (scripts/lanes_sweep.py, us per step, this kernel vs one block per warp): per-step launches
-    // 4,096 envs 3.1 vs 3.6, 8,192 envs 4.2 vs 3.7; 24 steps per launch 4,096 envs 1.45 vs 3.34, 8,192 envs 2.5 vs 3.4,
-    // 16,384 envs 4.6 vs 3.6
-    static constexpr long long kLanesMaxEnvsStep = 4096, kLanesMaxEnvsRollout = 8192;
+    // 4,096 envs 3.0 vs 3.6, 8,192 envs 4.2 vs 3.7; 24 steps per launch 4,096 envs 1.37 vs 3.34, 6,144 envs 2.06 vs 3.41,
+    // 8,192 envs 2.31 vs 3.35 (two lanes per env: 2.14), 16,384 envs 4.6 vs 3.6
+    static constexpr long long kLanesMaxEnvsStep = 4096, kLanesMaxEnvsRollout = 6144;
+    static constexpr long long kTwoLanesMaxEnvsStep = 16384, kTwoLanesMaxEnvsRollout = 65536;   // 10 spots, two lanes per env (launch_step_n)
     int lanes_per_env = 0;    // 0 auto (4 for specialised stations of more than 32 spots), 1 / 2: that many lanes per env
     int num_sms = 148;
     size_t smem_optin = 0;
@@ -949,6 +950,16 @@ public:
                     return launch_simple<NCT, ND, 1, FIXED>(tail, tail.actions, tail.obs, tail.reward, tail.done, 1, STAGE_SCALAR, st);
                 }
             }
+        }
+        if constexpr (!EXACT && FIXED && NCT == 10) {
+            // two lanes per env at 10 spots: half the per-warp chain for batches that are a single wave of warps anyway
+            // (whole 32-env blocks; bit-identical).  Measured (scripts/lanes_sweep.py --two, us per step, two lanes vs one):
+            // 24 steps per launch 8,192 envs 2.14 vs 3.37, 16,384 envs 2.39 vs 3.58, 32,768 envs 3.25 vs 4.47, 65,536 envs 5.13
+            // vs 5.31, 131,072 envs 9.3 vs 7.6; per-step launches 8,192 envs 3.34 vs 3.59, 16,384 envs 3.61 vs 3.75, 32,768 equal
+            const bool mid = lanes_per_env == 0 && kernel_variant == 0 && lanes_kernel == 0 &&
+                             q.n_envs <= (n_steps > 1 ? kTwoLanesMaxEnvsRollout : kTwoLanesMaxEnvsStep);
+            if ((lanes_per_env == 2 || mid) && q.n_envs % kBlock == 0)
+                return launch_simple<NCT, ND, 2, FIXED>(q, actions, obs, reward, done, n_steps, bulk, st);
         }
         return launch_simple<NCT, ND, 1, FIXED>(q, actions, obs, reward, done, n_steps, bulk, st);
     }

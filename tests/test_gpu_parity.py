@@ -369,6 +369,36 @@ def test_kernel_variants_are_bit_identical(kw):
         e.close()
 
 
+@pytest.mark.parametrize("E", [1280, 8192])
+def test_small_batch_kernel_forms_are_bit_identical(E):
+    """What the host picks by batch size for the 10-spot default station -- one lane per SPOT (at most 4,096 envs per step
+    launch / 6,144 per rollout launch), two lanes per env (up to 16,384 / 65,536 envs, whole 32-env blocks), one lane per env
+    -- is invisible in the results: the default choice, each form forced (set_pipeline 4 / 3) and the one-block-per-warp
+    kernel (5) agree bit for bit, step by step and through sng_rollout, across an auto-reset."""
+    n = 30
+    envs = []
+    for variant in (5, 0, 3, 4):
+        env = _env(E, "float32", number_of_chargers=10, seed=19)
+        env.set_pipeline(variant)
+        env.reset()
+        envs.append(env)
+    g = torch.Generator(device="cuda:0").manual_seed(8)
+    actions = torch.stack([envs[0].sample_actions(g) for _ in range(n)])
+    for s in range(n):
+        outs = [e.step(actions[s]) for e in envs]
+        for e, o in zip(envs[1:], outs[1:]):
+            assert torch.equal(o[0], outs[0][0]) and torch.equal(o[1], outs[0][1]) and torch.equal(o[2], outs[0][2]), s
+            assert torch.equal(envs[0]._spot, e._spot) and torch.equal(envs[0]._envst, e._envst), s
+            assert torch.equal(envs[0].terminal_obs, e.terminal_obs) and torch.equal(envs[0].diag, e.diag), s
+    rolls = [e.rollout(actions) for e in envs]
+    for e, r in zip(envs[1:], rolls[1:]):
+        assert all(torch.equal(x, y) for x, y in zip(r, rolls[0]))
+        assert torch.equal(envs[0]._spot, e._spot) and torch.equal(envs[0]._envst, e._envst)
+    for e in envs:
+        assert e.error_flags() == 0
+        e.close()
+
+
 @pytest.mark.parametrize("lanes_rollout", [4, 5])
 def test_rollout_equals_repeated_step_and_step_host(lanes_rollout):
     E, n = 2777, 30
