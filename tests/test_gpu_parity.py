@@ -559,8 +559,10 @@ def test_shard_equivalence():
         e.close()
 
 
-def test_error_flags_mirror_reference_raises():
+@pytest.mark.parametrize("variant", [0, 5])     # 64 envs: by default the one-lane-per-spot kernel; 5: one block per warp
+def test_error_flags_mirror_reference_raises(variant):
     env = _env(64, "float32", number_of_chargers=4)
+    env.set_pipeline(variant)
     env.reset()
     a = torch.zeros(64, 5, device="cuda:0")
     env.step(a)
@@ -574,6 +576,25 @@ def test_error_flags_mirror_reference_raises():
     a[:] = float("nan")
     env.step(a)
     assert env.error_flags() & 4
+    env.close()
+
+
+@pytest.mark.parametrize("variant", [0, 5])
+def test_nan_action_flags_only_its_own_env(variant):
+    """A NaN / infinite action is reported for the env that received it and for no other (the one-lane-per-spot kernel
+    votes over the 16 lanes of an env, two envs per warp)."""
+    E = 71
+    env = _env(E, "float32", number_of_chargers=10)
+    env.set_pipeline(variant)
+    env.reset()
+    a = torch.full((E, 11), 0.25, device="cuda:0")
+    a[3, 2] = float("nan")       # a charger action of env 3 (lower half of its warp)
+    a[6, 10] = float("inf")      # the battery action of env 6
+    a[9, 9] = float("-inf")      # the last charger of env 9 (upper half of its warp)
+    a[70, 0] = float("nan")      # the last env of an odd batch (its warp's upper half has no env)
+    env.step(a)
+    flagged = (env.err & 4).nonzero().flatten().tolist()
+    assert flagged == [3, 6, 9, 70], flagged
     env.close()
 
 
