@@ -824,7 +824,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs")
     ap.add_argument("--rollout-pdl", default="", help="programmatic dependent launch inside the rollout loop of the c3 legs: "
                     "off, policy (default), step, both (optionally +x: policy CTAs claim their SM's whole shared memory)")
-    ap.add_argument("--legs", default="all", help="'all', 'none' or a comma list of c4_strong,pattern_ceiling,c5,c3,c3_fused,c3_sharded,c3_sb3,c2,rollout_kernel,generic")
+    ap.add_argument("--legs", default="all", help="'all', 'none' or a comma list of c4_strong,pattern_ceiling,c5,c3,c3_fused,c3_sharded,c3_full_waves,c3_sb3,c2,rollout_kernel,generic")
     ap.add_argument("--rollout", type=int, default=0, help="legacy: same as --legs c3 with this many steps per rollout")
     args = ap.parse_args()
     PDL_ARG[0] = args.pdl
@@ -916,6 +916,11 @@ def main():
                 elif name == "c3":
                     legs[name] = rollout_leg(ctx, "c4", 65536, args.rollout or 24)
                     legs[name]["what"] = "BASELINE config 3: PPO rollout collection over 65,536 envs per GPU, N=10 station"
+                elif name == "c3_full_waves":
+                    # by name only: 4 x 148 tiles of 128 envs, i.e. every policy CTA gets exactly four tiles (65,536 envs are
+                    # 512 tiles: 3.46 per SM, four rounds for 68 SMs and three for the other 80)
+                    legs[name] = rollout_leg(ctx, "c4", 4 * 148 * 128, args.rollout or 24)
+                    legs[name]["what"] = "BASELINE config 3 at 75,776 envs per GPU (a whole number of policy tiles per SM): what the tile quantisation at 65,536 envs costs"
                 elif name == "c3_fused":
                     legs[name] = rollout_leg(ctx, "c4", 65536, args.rollout or 24, fuse_step=True)
                     legs[name]["what"] = "BASELINE config 3 with ONE launch per rollout step (policy forward + env step fused, sng_policy_step)"
