@@ -552,7 +552,7 @@ def rollout_kernel_leg(ctx, wl_key, E, floor_us, n_steps=24, min_ms=150.0):
     env = make_env(ctx, wl_key, E, ctx.rank * E)
     cfg = env.cfg
     g = torch.Generator(device=ctx.dev).manual_seed(77 + ctx.rank)
-    acts = torch.stack([env.sample_actions(g) for _ in range(n_steps)]).contiguous()
+    acts = env.random_actions(77, 0, n_steps)      # sng_sample_actions: the random policy, keyed by global env id and step
     obs = torch.empty(n_steps, E, cfg.obs_dim, device=ctx.dev)
     rew = torch.empty(n_steps, E, device=ctx.dev)
     done = torch.empty(n_steps, E, device=ctx.dev, dtype=torch.uint8)

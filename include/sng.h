@@ -15,6 +15,7 @@
  *   sng_step_host       the same call made with host (numpy) arrays, as a gym caller does
  *   sng_rollout         n consecutive step() calls of a trainer's rollout loop   solvers/RL/ppo_train.py:94-101
  *   sng_sample_plan     the `initial_values.json` dump        utils/charging_station.py:173-186
+ *   sng_sample_actions  env.action_space.sample() per env     envs/smart_nanogrid_environment.py:101-118
  *   sng_error_flags     the reference's `raise ValueError` sites
  *                       (central_management_system.py:158-159, penaliser.py:111)
  *   sng_gae             (next row of the path) stable_baselines3 RolloutBuffer.compute_returns_and_advantage,
@@ -185,6 +186,14 @@ int sng_step_host(sng_env *env, const void *actions_host, float *obs_host, void 
 /* Eagerly generate the whole-day schedule of the CURRENT episode of every env into `plan`
  * (same Philox streams the lazy in-step sampler uses), for export / inspection. */
 int sng_sample_plan(sng_env *env, void *stream);
+
+/* The random policy (BASELINE config 2; reference: env.action_space.sample() per env and step, bounds of
+ * envs/smart_nanogrid_environment.py:101-118): fills actions [n_steps][E][act_dim] (device, the env's real type) with
+ * low + u * (high - low), u uniform in [0, 1) with 24 bits, from Philox4x32-10 keyed by `seed` with counter (global env id,
+ * step0 + s, column group): the draw of env e at step s does not depend on how the batch is sharded (env_gid0), on n_steps or
+ * on the batch size, and is disjoint from the schedule sampler's streams even for the same seed.  step0 + n_steps < 2^32.
+ * Feed the slab to sng_rollout (or a slice to sng_step): SURVEY's `sng_rollout(env, NULL, ...)` with the buffer caller-owned. */
+int sng_sample_actions(sng_env *env, uint64_t seed, uint64_t step0, int n_steps, void *actions, void *stream);
 
 /* OR of all per-env error flags (synchronises the stream). */
 int sng_error_flags(sng_env *env, uint32_t *host_out, void *stream);

@@ -20,7 +20,7 @@ FLAG_NEG_DEMAND, FLAG_BATT_SOC_GT1, FLAG_NAN_ACTION = 1, 2, 4
 DIAG = ("total_ch", "total_dis", "solar", "batt_power", "grid_power", "grid_cost", "pen_veh", "pen_batt")
 
 EXPORTS = ("sng_abi_version", "sng_sizeof", "sng_last_error", "sng_query_layout", "sng_create", "sng_destroy", "sng_bind",
-           "sng_reset", "sng_load_schedule", "sng_step", "sng_rollout", "sng_step_host", "sng_sample_plan",
+           "sng_reset", "sng_load_schedule", "sng_step", "sng_rollout", "sng_step_host", "sng_sample_plan", "sng_sample_actions",
            "sng_error_flags", "sng_launch_count", "sng_set_tuning", "sng_set_pipeline", "sng_gae", "sng_policy_forward", "sng_null_launch",
            "sng_policy_packed_bytes", "sng_policy_pack", "sng_policy_forward_packed", "sng_policy_forward_sampled", "sng_debug_arrival_gap", "sng_set_launch_mode", "sng_policy_set_launch_mode", "sng_policy_step", "sng_debug_traffic_skeleton", "sng_debug_stamp")
 
@@ -104,6 +104,7 @@ def lib():
         L.sng_rollout.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.sng_step_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.sng_sample_plan.argtypes = [C.c_void_p, C.c_void_p]
+        L.sng_sample_actions.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p]
         L.sng_error_flags.argtypes = [C.c_void_p, C.POINTER(C.c_uint32), C.c_void_p]
         L.sng_launch_count.argtypes = [C.c_void_p]
         L.sng_launch_count.restype = C.c_int64

@@ -396,6 +396,16 @@ class BatchedSmartNanogridEnv:
         u = torch.rand(self.num_envs, self.cfg.act_dim, device=self.device, dtype=self.real, generator=generator)
         return self.action_low + (self.action_high - self.action_low) * u
 
+    def random_actions(self, seed: int, step0: int = 0, n_steps: int = 1, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """The random policy as a counter-based draw (include/sng.h sng_sample_actions): actions [n_steps, E, A] uniform in
+        the action box, a function of (seed, GLOBAL env id, step0 + s) only -- the same for any sharding, batch size or
+        n_steps.  Feed the slab to `rollout`, or slab[s] to `step`."""
+        E, A = self.num_envs, self.cfg.act_dim
+        out = torch.empty(n_steps, E, A, dtype=self.real, device=self.device) if out is None else out
+        self._check_tensor(out, (n_steps, E, A), self.real, "out")
+        nat.check(self._lib.sng_sample_actions(self._h, int(seed), int(step0), int(n_steps), _ptr(out), self._stream()))
+        return out
+
     def rbc_actions(self, obs: torch.Tensor) -> torch.Tensor:
         """The reference's rule-based controller (solvers/RBC/rbc.py:6-29) with generic offsets
         (SURVEY 8c): per spot 0 if no vehicle, 1 if it departs within 3 h, else the mean of the current

@@ -174,6 +174,12 @@ int sng_sample_plan(sng_env *env, void *stream)
     return done(env, env->eng->sample_plan((cudaStream_t)stream));
 }
 
+int sng_sample_actions(sng_env *env, uint64_t seed, uint64_t step0, int n_steps, void *actions, void *stream)
+{
+    SNG_ENV_CHECK(env);
+    return done(env, env->eng->sample_actions(seed, step0, n_steps, actions, (cudaStream_t)stream));
+}
+
 int sng_error_flags(sng_env *env, uint32_t *host_out, void *stream)
 {
     SNG_ENV_CHECK(env);

@@ -42,6 +42,7 @@ struct EngineBase {
     virtual int rollout(const void *actions, float *obs, void *reward, uint8_t *done, int n_steps, cudaStream_t st) = 0;
     virtual int step_host(const void *a, float *obs, void *rew, uint8_t *done, cudaStream_t st) = 0;
     virtual int sample_plan(cudaStream_t st) = 0;
+    virtual int sample_actions(uint64_t seed, uint64_t step0, int n_steps, void *actions, cudaStream_t st) = 0;
     virtual int error_flags(uint32_t *out, cudaStream_t st) = 0;
     virtual int probe_arrival_gap(const uint32_t *x, uint32_t *g, long long n, cudaStream_t st) = 0;
     virtual int traffic_skeleton(int variant, cudaStream_t st) = 0;
@@ -547,6 +548,36 @@ __global__ void __launch_bounds__(256) sample_plan_kernel(const Params<real> p, 
         memset(&z, 0, sizeof(z));
         z.hdr = make_hdr(kNoVehicle, 0, 0, kNoVehicle);
         pl[v] = z;
+    }
+}
+
+// Uniform random actions from the action box (the random policy of BASELINE config 2; reference: env.action_space.sample(),
+// envs/smart_nanogrid_environment.py:101-118 for the bounds): thread = (step, env, group of four action columns), one
+// Philox4x32-10 block each, key = the caller's seed, counter = (global env id, step, kCtrActions | group) -- disjoint from the
+// schedule sampler's counters, and a function of the GLOBAL env id, so a sharded batch draws the same actions.
+constexpr uint32_t kCtrActions = 0xAC710000u;
+template <typename real>
+__global__ void __launch_bounds__(256) sample_actions_kernel(const Params<real> p, real *actions, unsigned long long seed,
+                                                             unsigned long long step0, int n_steps)
+{
+    const int groups = (p.A + 3) / 4;
+    const long long total = (long long)n_steps * p.n_envs * groups;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int g = (int)(i % groups);
+        const long long row = i / groups, e = row % p.n_envs, s = row / p.n_envs;
+        const unsigned long long gid = p.gid0 + (unsigned long long)e, step = step0 + (unsigned long long)s;
+        uint32_t x[4];
+        philox4x32_10((uint32_t)gid, (uint32_t)(gid >> 32), (uint32_t)step, kCtrActions | (uint32_t)g, (uint32_t)seed, (uint32_t)(seed >> 32), x);
+        real *a = actions + (size_t)row * p.A;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int k = 4 * g + j;
+            if (k < p.A) {
+                const float u = __fmul_rn((float)(x[j] >> 8), 5.9604644775390625e-08f);            // [0, 1), 24 bits
+                const float low = (k < p.N && !p.v2x) ? 0.0f : -1.0f;                               // chargers: [0 | -1, 1); battery: [-1, 1)
+                a[k] = (real)__fmaf_rn(1.0f - low, u, low);
+            }
+        }
     }
 }
 
@@ -1153,6 +1184,18 @@ public:
         if (p.mode != MODE_SAMPLE) { error = "sng_sample_plan: handle is in replay mode"; return SNG_ERR_STATE; }
         DeviceGuard guard(device);
         sample_plan_kernel<real><<<grid_for(p.n_envs * p.N), 256, 0, st>>>(p, (PlanRec<real> *)buf.plan);
+        ++launches;
+        SNG_CUDA(cudaGetLastError());
+        return SNG_OK;
+    }
+
+    int sample_actions(uint64_t seed, uint64_t step0, int n_steps, void *actions, cudaStream_t st) override
+    {
+        if (!actions || n_steps < 1) { error = "sng_sample_actions: bad arguments"; return SNG_ERR_ARG; }
+        if (step0 + (uint64_t)n_steps > 0xFFFFFFFFull) { error = "sng_sample_actions: step0 + n_steps must stay below 2^32"; return SNG_ERR_ARG; }
+        DeviceGuard guard(device);
+        const long long blocks = ((long long)n_steps * p.n_envs * ((p.A + 3) / 4) + 255) / 256;
+        sample_actions_kernel<real><<<(unsigned)(blocks < 148 * 64 ? blocks : 148 * 64), 256, 0, st>>>(p, (real *)actions, seed, step0, n_steps);
         ++launches;
         SNG_CUDA(cudaGetLastError());
         return SNG_OK;

@@ -559,6 +559,45 @@ def test_shard_equivalence():
         e.close()
 
 
+@pytest.mark.parametrize("kw", [dict(number_of_chargers=10), dict(number_of_chargers=4, vehicle_to_everything=True),
+                                dict(number_of_chargers=7, battery_system_available_in_model=False)])
+def test_random_policy_actions_are_counter_based(kw):
+    """sng_sample_actions (the random policy of BASELINE config 2): exactly low + u * (high - low) with u from Philox4x32-10
+    keyed by the seed, counter (global env, step, column group) -- bit for bit against the oracle's Philox --, inside the
+    action box, independent of sharding, slab length and batch size, and a valid input of sng_rollout."""
+    from oracle.oracle import philox4x32_10
+    E, n, seed, gid0 = 777, 6, 0xFEDCBA9876543210, 5000
+    env = _env(E, "float32", seed=3, env_gid0=gid0, **kw)
+    cfg = env.cfg
+    A = cfg.act_dim
+    lo, hi = cfg.action_bounds()
+    acts = env.random_actions(seed, step0=4, n_steps=n)
+    a = acts.cpu().numpy()
+    assert a.shape == (n, E, A) and (a >= lo).all() and (a < hi).all()
+    for s, e in ((0, 0), (1, 5), (n - 1, E - 1), (3, 400)):
+        for g in range((A + 3) // 4):
+            x = philox4x32_10([(gid0 + e) & 0xFFFFFFFF, (gid0 + e) >> 32, 4 + s, 0xAC710000 | g], [seed & 0xFFFFFFFF, seed >> 32])
+            u = (x >> 8).astype(np.float32) * np.float32(2.0 ** -24)
+            for j in range(min(4, A - 4 * g)):
+                k = 4 * g + j
+                want = np.float32(np.float64(lo[k]) + np.float64(hi[k] - lo[k]) * np.float64(u[j]))     # one rounding, like the fma
+                assert a[s, e, k] == want, (s, e, k, a[s, e, k], want)
+    # every column covers its range (4,662 draws each)
+    assert (np.abs(a.reshape(-1, A).mean(0) - (lo + hi) / 2) < 0.03 * (hi - lo)).all()
+    assert (a.reshape(-1, A).min(0) < lo + 0.01 * (hi - lo)).all() and (a.reshape(-1, A).max(0) > hi - 0.01 * (hi - lo)).all()
+    # a shard, a longer slab from an earlier step and a slab of another handle draw the same values
+    part = _env(100, "float32", seed=99, env_gid0=gid0 + 300, **kw)
+    assert torch.equal(part.random_actions(seed, step0=2, n_steps=5)[2:], acts[:3, 300:400])
+    assert not torch.equal(env.random_actions(seed + 1, step0=4, n_steps=1)[0], acts[0])
+    # ... and drive a rollout across an auto-reset
+    env.reset()
+    slab = env.random_actions(seed, 0, cfg.n_steps + 3)
+    obs, rew, done = env.rollout(slab)
+    assert done[cfg.n_steps - 1].all() and int(done.sum()) == E and torch.isfinite(rew).all() and env.error_flags() == 0
+    env.close()
+    part.close()
+
+
 @pytest.mark.parametrize("variant", [0, 5])     # 64 envs: by default the one-lane-per-spot kernel; 5: one block per warp
 def test_error_flags_mirror_reference_raises(variant):
     env = _env(64, "float32", number_of_chargers=4)
