@@ -589,6 +589,10 @@ def test_random_policy_actions_are_counter_based(kw):
     part = _env(100, "float32", seed=99, env_gid0=gid0 + 300, **kw)
     assert torch.equal(part.random_actions(seed, step0=2, n_steps=5)[2:], acts[:3, 300:400])
     assert not torch.equal(env.random_actions(seed + 1, step0=4, n_steps=1)[0], acts[0])
+    f64 = _env(64, "float64", seed=1, env_gid0=gid0 + 10, **kw)          # the float64 validation build draws the same numbers
+    a64 = f64.random_actions(seed, step0=4, n_steps=2)
+    assert a64.dtype == torch.float64 and torch.equal(a64, acts[:2, 10:74].double())
+    f64.close()
     # ... and drive a rollout across an auto-reset
     env.reset()
     slab = env.random_actions(seed, 0, cfg.n_steps + 3)
