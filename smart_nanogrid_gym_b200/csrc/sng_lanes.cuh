@@ -21,9 +21,7 @@
 
 namespace sng {
 
-
 // (included by sng_engine.cuh behind pdl_wait / pdl_launch_dependents / publish_dep_table_warp)
-
 constexpr int kLaneGroup = 16;   // lanes per env
 
 template <int NCT, bool MULTI>
