@@ -509,10 +509,10 @@ def test_small_and_ragged_batches_with_masked_resets_vs_oracle(n_envs, precision
     env.close()
 
 
-def test_step_is_cuda_graph_capturable():
+@pytest.mark.parametrize("E", [4096, 8192, 32768])     # one lane per spot / two lanes per env / one block per warp
+def test_step_is_cuda_graph_capturable(E):
     """sng_step makes no hidden allocation or synchronisation: an episode of steps captured in a CUDA graph
     and replayed equals the same steps launched one by one."""
-    E = 4096
     a_env = _env(E, "float32", number_of_chargers=10, seed=13)
     b_env = _env(E, "float32", number_of_chargers=10, seed=13)
     a_env.reset()
@@ -755,12 +755,15 @@ def test_prediction_results_trace_matches_reference_recording(tag, tmp_path):
     env.close()
 
 
-def test_unaligned_buffers_take_the_scalar_path_and_agree():
+@pytest.mark.parametrize("variant", [5, 0])     # the one-block-per-warp kernel's scalar staging / what a batch this small runs on by default
+def test_unaligned_buffers_take_the_scalar_path_and_agree(variant):
     """Rollout-buffer slabs that are not 16-byte aligned (odd E) cannot use the copy engine or vector
     accesses; the scalar staging path must give the same results as stepping into the env's own buffers."""
     E, n = 33, 6
     a_env = _env(E, "float32", number_of_chargers=10, seed=2)
     b_env = _env(E, "float32", number_of_chargers=10, seed=2)
+    a_env.set_pipeline(variant)
+    b_env.set_pipeline(variant)
     a_env.reset()
     b_env.reset()
     buf_o = torch.zeros(n, E, 29, device="cuda:0")
