@@ -313,10 +313,10 @@ int sng_policy_set_launch_mode(int mode);
 /* Tuning knob: which step kernel runs: 0 (default) one 32-env block per warp, with four lanes per env for
  * specialised stations of more than 32 spots; 1 the persistent software-pipelined kernel (measured slower,
  * see DESIGN.md); 2 one block per warp and always one lane per env; 3 like 0 with two lanes per env.
- * Latency-bound batches: with 0, small batches of the reference's default station shape (PV, 3 steps ahead, battery, no
- * requested SoC; 4, 8 or 10 spots; float32; at most 4,096 envs per sng_step launch, 6,144 per sng_rollout launch) run the
- * one-lane-per-SPOT kernel (two envs per warp, station sums by shuffles), and 10-spot batches of whole 32-env blocks up to
- * 16,384 / 65,536 envs run with two lanes per env -- bit-identical results either way; 3 also means two lanes per env for
+ * Latency-bound batches: with 0, small batches of the reference's default station shape (PV, 3 steps ahead, battery; 4, 8
+ * or 10 spots; float32; sampled or replayed schedules; at most 4,096 envs per sng_step launch, 6,144 per sng_rollout launch)
+ * run the one-lane-per-SPOT kernel (two envs per warp, station sums by shuffles), and 10-spot batches of whole 32-env blocks
+ * up to 16,384 / 65,536 envs (sampled, no requested SoC) run with two lanes per env -- bit-identical results either way; 3 also means two lanes per env for
  * such 10-spot batches of any size; 4 = the one-lane-per-spot kernel at every batch size; 5 = like 0 without either form.
  * ctas_per_sm caps the resident CTAs per SM of the pipelined kernel (0 = as many as fit). */
 int sng_set_pipeline(sng_env *env, int kernel_variant, int ctas_per_sm);

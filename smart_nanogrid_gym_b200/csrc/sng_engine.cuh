@@ -897,7 +897,8 @@ public:
     int launch_lanes(const Params<real> &q, const real *actions, float *obs, real *reward, uint8_t *done, int n_steps, cudaStream_t st)
     {
         if constexpr (!EXACT && NCT <= kLaneGroup) {
-            auto kern = n_steps > 1 ? step_lanes_kernel<NCT, true> : step_lanes_kernel<NCT, false>;
+            auto kern = q.has_req ? (n_steps > 1 ? step_lanes_kernel<NCT, true, true> : step_lanes_kernel<NCT, false, true>)
+                                  : (n_steps > 1 ? step_lanes_kernel<NCT, true, false> : step_lanes_kernel<NCT, false, false>);
             const int wpb = (warps_per_cta > 0 && warps_per_cta < 4) ? warps_per_cta : 4;
             const long long warps = (q.n_envs + 1) / 2;
             const unsigned grid = (unsigned)((warps + wpb - 1) / wpb);
@@ -1012,17 +1013,19 @@ public:
             // shape (PV on, 3 steps ahead: 8 disturbance entries); everything else runs the generic kernel
             // (keyed on the flags themselves: PV off with 7 steps ahead also has 8 disturbance entries, but a
             // different layout -- eight prices)
+            // latency-bound batches of that shape with a battery (sampled or replayed, with or without requested SoCs): one lane
+            // per spot (bit-identical; 4,096 envs are only 128 warps of the kernels below)
+            if (!use_generic && q.pv && q.H == 3 && q.pv_days == 1 && q.batt && kernel_variant == 0 &&
+                (lanes_kernel > 0 || (lanes_kernel == 0 && q.n_envs <= (n_steps > 1 ? kLanesMaxEnvsRollout : kLanesMaxEnvsStep)))) {
+                switch (q.N) {
+                case 4: return launch_lanes<4>(q, actions, obs, reward, done, n_steps, st);
+                case 8: return launch_lanes<8>(q, actions, obs, reward, done, n_steps, st);
+                case 10: return launch_lanes<10>(q, actions, obs, reward, done, n_steps, st);
+                default: break;
+                }
+            }
             if (!use_generic && q.pv && q.H == 3 && q.pv_days == 1 && q.batt && !q.has_req) {
                 // ... and the rest of the reference's default station (battery, no requested-SoC plane) at compile time too
-                // latency-bound batches: one lane per spot (bit-identical; 4,096 envs are 128 warps of the kernel below)
-                if (kernel_variant == 0 && (lanes_kernel > 0 || (lanes_kernel == 0 && q.n_envs <= (n_steps > 1 ? kLanesMaxEnvsRollout : kLanesMaxEnvsStep)))) {
-                    switch (q.N) {
-                    case 4: return launch_lanes<4>(q, actions, obs, reward, done, n_steps, st);
-                    case 8: return launch_lanes<8>(q, actions, obs, reward, done, n_steps, st);
-                    case 10: return launch_lanes<10>(q, actions, obs, reward, done, n_steps, st);
-                    default: break;
-                    }
-                }
                 switch (q.N) {
                 case 4: return launch_step_n<4, 8, true>(q, actions, obs, reward, done, n_steps, bulk, st);
                 case 8: return launch_step_n<8, 8, true>(q, actions, obs, reward, done, n_steps, bulk, st);

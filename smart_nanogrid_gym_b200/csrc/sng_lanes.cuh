@@ -14,8 +14,9 @@
 // sums (spot index mod 2), each accumulated in spot order starting from +0, V2X discharges added behind the charging
 // powers, then c0 + c1 -- by walking the spots with shuffles instead of reducing by butterfly.
 //
-// Scope: float32, the reference's default station shape (PV on, 3 steps ahead, battery on, every vehicle requests SoC 1.0:
-// the FIXED instantiations), N <= 16 spots.  Reference lines as in env_step (sng_device.cuh).
+// Scope: float32, the reference's default station shape (PV on, 3 steps ahead, battery on), N <= 16 spots, sampled or
+// replayed schedules, with or without individual requested SoCs (the third state plane, kept in a register like the other
+// two).  Reference lines as in env_step (sng_device.cuh).
 #pragma once
 #include "sng_device.cuh"
 
@@ -24,7 +25,9 @@ namespace sng {
 // (included by sng_engine.cuh behind pdl_wait / pdl_launch_dependents / publish_dep_table_warp)
 constexpr int kLaneGroup = 16;   // lanes per env
 
-template <int NCT, bool MULTI>
+// REQ: vehicles carry individual requested SoCs (the third state plane); false: every vehicle requests 1.0 and the plane is
+// neither read nor written (compile time: the common case keeps its registers and its instruction count).
+template <int NCT, bool MULTI, bool REQ>
 __global__ void __launch_bounds__(128)
     step_lanes_kernel(const Params<float> p, const float *actions, float *obs_out, float *reward_out, uint8_t *done_out, int n_steps)
 {
@@ -44,15 +47,17 @@ __global__ void __launch_bounds__(128)
     const size_t plane = (size_t)p.plane;
     uint32_t *const sp = p.spot + (size_t)(e / kBlock) * (size_t)(NCT * kBlock) + (size_t)sub * kBlock + (size_t)(e % kBlock);
     // lanes without a spot carry an empty header: never present, never checked, never arriving
+    constexpr bool has_req = REQ;
     uint32_t hd = make_hdr(kNoVehicle, 0, 0, kNoVehicle);
-    float soc = 0.0f;
+    float soc = 0.0f, rq = 1.0f;
     EnvSt<float> es = {0.0f, 0.0f, 0.0f, 0u};
     if (own) {
         hd = sp[PL_HDR * plane];
         soc = __uint_as_float(sp[PL_SOC * plane]);
+        if (has_req) rq = __uint_as_float(sp[PL_REQ * plane]);
     }
     if (valid) es = p.envst[e];
-    const uint32_t hd_loaded = hd;
+    bool new_vehicle = false;                                    // header (and requested SoC) changed since they were loaded
     // the action of this lane's spot and the battery action (actions[-1], read by every lane of the env); a rollout
     // requests the next step's pair one step ahead, so that their way from L2 is off the step-to-step chain
     float a_next = own ? actions[(size_t)e * A + sub] : 0.0f;
@@ -89,7 +94,6 @@ __global__ void __launch_bounds__(128)
         uint32_t err = 0;
 
         // ---- per-spot phase (charging_station.py:281-300, charger.py:37-140, penaliser.py:39-87) ----
-        const float rq = 1.0f;
         const float s_prev = soc;
         const int arr = (int)(hd & 0xFFu), dep = (int)((hd >> 8) & 0xFFu);
         const bool checked = arr < t && t <= dep && dep - t < p.max_togo;
@@ -190,6 +194,8 @@ __global__ void __launch_bounds__(128)
                     const Vehicle<float> v = fetch_vehicle<float, true>(p, NCT, e, sub, episode, tn, dep_base);
                     hd = v.hdr;
                     soc = v.soc0;
+                    if (has_req) rq = v.req;
+                    new_vehicle = true;
                 }
                 es.t_ep = (episode << 8) | (uint32_t)tn;
             } else {
@@ -213,6 +219,8 @@ __global__ void __launch_bounds__(128)
                 if (next == 0u) v = fetch_vehicle<float, true>(p, NCT, e, sub, episode, 0, dep_base);
                 hd = v.hdr;
                 soc = v.soc0;
+                if (has_req) rq = v.req;
+                new_vehicle = true;
                 const bool present0 = (v.hdr & 0xFFu) == 0u;
                 soc_i = present0 ? v.soc0 : 0.0f;
                 dep_i = present0 ? dep_lookup<true>(p, dep_base, (int)((v.hdr >> 8) & 0xFFu)) : 0.0f;
@@ -229,7 +237,10 @@ __global__ void __launch_bounds__(128)
     }
     // ---- the state goes back once per launch ----
     if (own) {
-        if (hd != hd_loaded) sp[PL_HDR * plane] = hd;
+        if (new_vehicle) {
+            sp[PL_HDR * plane] = hd;
+            if (has_req) sp[PL_REQ * plane] = __float_as_uint(rq);
+        }
         sp[PL_SOC * plane] = __float_as_uint(soc);
     }
     if (valid && sub == 0) p.envst[e] = es;

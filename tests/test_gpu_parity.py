@@ -334,6 +334,7 @@ def test_default_station_kernel_equals_the_replay_kernel(n_spots):
     dict(number_of_chargers=64, time_interval="30min", vehicle_to_everything=True, vehicle_uncharged_penalty_mode="dense"),
     dict(number_of_chargers=32, hours_ahead=2),
     dict(number_of_chargers=8, time_interval="15min", enable_different_vehicle_battery_capacities=True),   # 96-step days on the small-batch kernel
+    dict(number_of_chargers=10, enable_requested_state_of_charge=True, vehicle_to_everything=True),        # ... with the requested-SoC plane
 ])
 def test_kernel_variants_are_bit_identical(kw):
     """The persistent pipelined and the one-block-per-warp kernel, the specialised (compile-time N) and the
